@@ -1,0 +1,7 @@
+"""Host-side stand-in for the parts of Gridap / GridapGmsh that nuPGCM calls at set-up time."""
+from .mshio import RawMesh, read_msh
+from .fem import (CellIntegrator, DiscreteModel, FacetIntegrator, LagrangeSpace, restrict,
+                  restrict_vector)
+
+__all__ = ["RawMesh", "read_msh", "CellIntegrator", "DiscreteModel", "FacetIntegrator",
+           "LagrangeSpace", "restrict", "restrict_vector"]
