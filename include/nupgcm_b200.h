@@ -1,0 +1,182 @@
+/*
+ * nupgcm_b200.h — C ABI of libnupgcm_b200.so: nuPGCM's per-timestep solve path on NVIDIA B200.
+ *
+ * This is the drop-in boundary behind nuPGCM's CPU()/GPU() architecture switch
+ * (reference src/architectures.jl:4-20, extended today by ext/nuPGCMCUDAExt.jl:24-33 with
+ * CUDA.jl arrays).  A host (Julia via ccall — see INTEGRATION.md; Python via ctypes in
+ * nupgcm_b200/lib.py) hands over already-assembled, already-permuted operands once, and then
+ * drives whole solves: no per-Krylov-iteration call crosses this boundary.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative nupgcm_status on failure;
+ *     nupgcm_last_error(ctx) (ctx may be NULL for creation failures) gives the message;
+ *   - handles are opaque; the library owns all device memory; host pointers are borrowed only
+ *     for the duration of a call; calls on one context must be serialised by the caller;
+ *   - a call returns after the results named in its out-parameters are valid on the host;
+ *   - all floating point is IEEE binary64; indices cross the boundary as int64 (Julia Int) with
+ *     an explicit index_base (1 for Julia, 0 for C/Python) and are stored as int32 on the device;
+ *   - Krylov non-convergence is NOT an error: status 0 with *solved = 0, exactly as the
+ *     reference ignores it (src/iterative_solvers.jl:58-67);
+ *   - there is no CPU fallback: without a usable sm_100 device nupgcm_create fails.
+ */
+#ifndef NUPGCM_B200_H
+#define NUPGCM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NUPGCM_B200_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+    NUPGCM_OK = 0,
+    NUPGCM_ERR_INVALID = -1,   /* bad argument (null handle, size mismatch, bad enum ...) */
+    NUPGCM_ERR_CUDA = -2,      /* a CUDA runtime call failed */
+    NUPGCM_ERR_NO_DEVICE = -3, /* no CUDA device / not an sm_100 device */
+    NUPGCM_ERR_NCCL = -4,      /* NCCL unavailable or a NCCL call failed */
+    NUPGCM_ERR_ALLOC = -5      /* host or device allocation failed */
+} nupgcm_status;
+
+typedef struct nupgcm_ctx nupgcm_ctx;
+typedef struct nupgcm_vec nupgcm_vec;
+typedef struct nupgcm_index nupgcm_index;
+typedef struct nupgcm_csr nupgcm_csr;
+typedef struct nupgcm_mesh nupgcm_mesh;
+
+int32_t nupgcm_version(void);
+const char *nupgcm_last_error(const nupgcm_ctx *ctx);
+
+/* ---- context ---------------------------------------------------------------------------
+ * Replaces what `using CUDA` + GPU() give the reference (ext/nuPGCMCUDAExt.jl:8-16 device
+ * listing, :33 print_memory_status -> CUDA.pool_status()). */
+int32_t nupgcm_create(int32_t device, nupgcm_ctx **out);
+int32_t nupgcm_destroy(nupgcm_ctx *ctx);
+int32_t nupgcm_synchronize(nupgcm_ctx *ctx);
+int32_t nupgcm_mem_status(nupgcm_ctx *ctx, size_t *free_bytes, size_t *total_bytes);
+/* name: buffer of >= 64 bytes (may be NULL) */
+int32_t nupgcm_device_info(nupgcm_ctx *ctx, int32_t *sm_count, int32_t *cc_major,
+                           int32_t *cc_minor, char *name);
+/* CUDA-event timing of the library's stream (for bench.py): *ms = elapsed between the two marks */
+int32_t nupgcm_timer_start(nupgcm_ctx *ctx);
+int32_t nupgcm_timer_stop(nupgcm_ctx *ctx, float *ms);
+/* number of kernels this context has launched since creation */
+int32_t nupgcm_launch_count(nupgcm_ctx *ctx, int64_t *count);
+
+/* ---- vectors (replace CuVector{Float64}: ext/nuPGCMCUDAExt.jl:24-26,32) ------------------ */
+int32_t nupgcm_vec_create(nupgcm_ctx *ctx, int64_t n, nupgcm_vec **out); /* zero-filled */
+int32_t nupgcm_vec_destroy(nupgcm_vec *v);
+int32_t nupgcm_vec_size(const nupgcm_vec *v, int64_t *n);
+int32_t nupgcm_vec_upload(nupgcm_vec *v, const double *host, int64_t n);   /* on_architecture(GPU(), a) */
+int32_t nupgcm_vec_download(const nupgcm_vec *v, double *host, int64_t n); /* on_architecture(CPU(), a) */
+int32_t nupgcm_vec_fill(nupgcm_vec *v, double value);
+int32_t nupgcm_vec_copy(nupgcm_vec *dst, const nupgcm_vec *src);
+/* y = alpha*x + beta*y (kaxpby!) */
+int32_t nupgcm_vec_axpby(nupgcm_vec *y, double alpha, const nupgcm_vec *x, double beta);
+int32_t nupgcm_vec_dot(const nupgcm_vec *x, const nupgcm_vec *y, double *out);
+int32_t nupgcm_vec_norm2(const nupgcm_vec *x, double *out);
+/* max |x_i| over the first `count` entries (count <= 0: all) and NaN flag: the blow-up check
+ * of src/model.jl:149-153 (count = nu restricts the [u; p] solution vector to the velocity) */
+int32_t nupgcm_vec_maxabs(const nupgcm_vec *x, int64_t count, double *maxabs, int32_t *has_nan);
+/* z = d .* r — mul!(z, ::Diagonal, r) of src/inversion.jl:54, src/evolution.jl:149,167 */
+int32_t nupgcm_diag_apply(nupgcm_vec *z, const nupgcm_vec *d, const nupgcm_vec *r);
+
+/* device-resident index vector; replaces the per-step upload of `inv_perm` in
+ * `solver.x[inv_perm]` (src/model.jl:282,312) */
+int32_t nupgcm_index_create(nupgcm_ctx *ctx, const int64_t *idx, int64_t n, int32_t index_base,
+                            nupgcm_index **out);
+int32_t nupgcm_index_destroy(nupgcm_index *ix);
+/* dst[i] = src[idx[i]], i < n(idx); dst may be longer than the index (tail untouched) */
+int32_t nupgcm_vec_gather(nupgcm_vec *dst, const nupgcm_vec *src, const nupgcm_index *idx);
+
+/* ---- CSR matrices (replace CuSparseMatrixCSR: ext/nuPGCMCUDAExt.jl:27) -------------------
+ * rowptr has n_rows+1 entries.  drop_zeros != 0 removes explicitly stored zeros (32 % of the
+ * Gridap-assembled inversion matrix) from the device copy; update_values still takes the
+ * original nnz values in the original order. */
+int32_t nupgcm_csr_create(nupgcm_ctx *ctx, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                          const int64_t *rowptr, const int64_t *colidx, const double *vals,
+                          int32_t index_base, int32_t drop_zeros, nupgcm_csr **out);
+int32_t nupgcm_csr_destroy(nupgcm_csr *A);
+int32_t nupgcm_csr_info(const nupgcm_csr *A, int64_t *n_rows, int64_t *n_cols,
+                        int64_t *nnz_given, int64_t *nnz_stored);
+int32_t nupgcm_csr_update_values(nupgcm_csr *A, const double *vals, int64_t nnz);
+/* out = M + theta*(Kh + Kv) on four matrices created from the same pattern with the same
+ * drop_zeros=0 setting — collect_evolution_LHS (src/evolution.jl:143-177, src/model.jl:251-261) */
+int32_t nupgcm_csr_combine(nupgcm_csr *out, const nupgcm_csr *M, const nupgcm_csr *Kh,
+                           const nupgcm_csr *Kv, double theta);
+/* dinv = 1 ./ diag(A) — the Jacobi preconditioner of src/evolution.jl:149,167 */
+int32_t nupgcm_csr_inv_diag(const nupgcm_csr *A, nupgcm_vec *dinv);
+/* y = alpha*A*x + beta*y — mul!(y, A, x) and `B*b .+ b0` of src/inversion.jl:104 */
+int32_t nupgcm_spmv(const nupgcm_csr *A, const nupgcm_vec *x, nupgcm_vec *y, double alpha,
+                    double beta);
+
+/* ---- Krylov solvers (replace Krylov.krylov_solve! at src/iterative_solvers.jl:58) ---------
+ * x is in/out: its content on entry is the warm start (the reference aliases x to workspace.x,
+ * src/iterative_solvers.jl:26-29).  itmax == 0 means 2n (Krylov.jl default).  The stopping
+ * measure is the preconditioned one, compared with atol + rtol*(initial measure).
+ * Preconditioner: dinv != NULL -> M = diag(dinv); else M = pscale*I (pass 1.0 for none).
+ * resid_hist (may be NULL) receives up to hist_cap measures (initial one first); *hist_len is
+ * how many were written.  Out-pointers may be NULL. */
+typedef struct {
+    int64_t niter;
+    int32_t solved;
+    int32_t inconsistent;
+    int32_t breakdown;     /* GMRES only */
+    int32_t reserved;
+    double  rnorm;         /* last value of the stopping measure */
+    double  rnorm0;        /* initial value of the stopping measure */
+    float   device_ms;     /* CUDA-event duration of the solve kernel(s) */
+    int32_t launches;      /* kernels launched by this call */
+    int64_t hist_len;
+} nupgcm_solve_stats;
+
+/* CG with Jacobi/scalar left preconditioner (CgWorkspace, src/evolution.jl:118-126) */
+int32_t nupgcm_cg_solve(const nupgcm_csr *A, const nupgcm_vec *dinv, double pscale,
+                        const nupgcm_vec *y, nupgcm_vec *x, double atol, double rtol,
+                        int64_t itmax, double *resid_hist, int64_t hist_cap,
+                        nupgcm_solve_stats *stats);
+
+/* orthogonalisation variants of the Arnoldi step */
+#define NUPGCM_ORTH_MGS 0  /* modified Gram-Schmidt, what Krylov.jl does: parity default */
+#define NUPGCM_ORTH_CGS2 1 /* classical Gram-Schmidt twice: 3 grid reductions per iteration */
+
+/* restarted GMRES(memory), left preconditioned (GmresWorkspace, src/inversion.jl:74-94) */
+int32_t nupgcm_gmres_solve(const nupgcm_csr *A, const nupgcm_vec *dinv, double pscale,
+                           const nupgcm_vec *y, nupgcm_vec *x, double atol, double rtol,
+                           int64_t itmax, int32_t memory, int32_t orth, double *resid_hist,
+                           int64_t hist_cap, nupgcm_solve_stats *stats);
+
+/* ---- per-step element right-hand side (replaces the CPU Gridap assemble_vector of
+ *      src/model.jl:269-275 and the broadcast of :278) -----------------------------------
+ * P2 tetrahedra (n_loc = 10) or P2 triangles (n_loc = 6).
+ *   cell_b[c*n_loc + i]            index of local buoyancy DOF i of cell c in the extended vector
+ *                                  [free values in solver order (nb) ; Dirichlet values (nbd)]
+ *   cell_u[(c*n_loc + i)*3 + comp] same for the velocity [free (nu) ; Dirichlet (nud)]
+ *   grad[(c*(d+1) + k)*3 + j]      d/dx_j of barycentric coordinate k, vol[c] the cell measure
+ *   bary[q*(d+1) + k], w[q]        quadrature rule (weights sum to 1)
+ * Indices are 0-based int32. */
+int32_t nupgcm_mesh_create(nupgcm_ctx *ctx, int64_t n_cells, int32_t n_loc,
+                           const int32_t *cell_b, const int32_t *cell_u, const double *grad,
+                           const double *vol, int32_t nq, const double *bary, const double *w,
+                           int64_t nb, const double *b_dirichlet, int64_t nbd, int64_t nu,
+                           const double *u_dirichlet, int64_t nud, nupgcm_mesh **out);
+int32_t nupgcm_mesh_destroy(nupgcm_mesh *m);
+/* scheme 1: ∫(b − Δt(u·∇b + w N²)) d   (src/model.jl:292-295)
+ * scheme 2: ∫(4/3 b − 1/3 b⁻ − 2/3 Δt((2u−u⁻)·∇(2b−b⁻) + (2w−w⁻) N²)) d   (:297-300)
+ * b, b_prev: nb; u, u_prev: vectors whose first nu entries are the velocity in solver order
+ * (the inversion solution vector [u; p] can be passed directly); out: nb. */
+int32_t nupgcm_rhs_adv(nupgcm_mesh *m, int32_t scheme, double dt, double N2, const nupgcm_vec *b,
+                       const nupgcm_vec *b_prev, const nupgcm_vec *u, const nupgcm_vec *u_prev,
+                       nupgcm_vec *out);
+/* out = rhs_adv + theta*rhs_diff + dt*rhs_flux − (rhs_m + theta*(rhs_h + rhs_v))  (src/model.jl:278) */
+int32_t nupgcm_rhs_combine(nupgcm_vec *out, const nupgcm_vec *rhs_adv, double theta, double dt,
+                           const nupgcm_vec *rhs_diff, const nupgcm_vec *rhs_flux,
+                           const nupgcm_vec *rhs_m, const nupgcm_vec *rhs_h,
+                           const nupgcm_vec *rhs_v);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NUPGCM_B200_H */

@@ -1,0 +1,181 @@
+// Shared declarations of libnupgcm_b200: handle layouts, error plumbing, device-side helpers.
+// Built for sm_100a only (B200); there is deliberately no other code path.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/nupgcm_b200.h"
+
+// -------------------------------------------------------------------------------------------
+// host-side handle layouts
+// -------------------------------------------------------------------------------------------
+
+struct nupgcm_ctx {
+    int device;
+    int sm_count;
+    int cc_major, cc_minor;
+    char name[64];
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;          // nupgcm_timer_*
+    cudaEvent_t sev0, sev1;        // per-solve timing
+    int64_t launches;
+    // persistent-kernel scratch: grid barrier word, reduction slots, result mailbox
+    unsigned long long *d_barrier; // [4]
+    double *d_partials;            // [kPartialSlots * grid]
+    double *d_scalars;             // [64] device scalars
+    double *h_scalars;             // pinned mirror
+    double *d_hist;                // residual history
+    int64_t hist_cap;
+    int coop_grid;                 // CTAs of the persistent solver kernels
+    char err[512];
+};
+
+struct nupgcm_vec {
+    nupgcm_ctx *ctx;
+    int64_t n;
+    double *d;
+};
+
+struct nupgcm_index {
+    nupgcm_ctx *ctx;
+    int64_t n;
+    int64_t max_value;             // largest index held (bounds check at gather time)
+    int32_t *d;
+};
+
+struct nupgcm_csr {
+    nupgcm_ctx *ctx;
+    int64_t n_rows, n_cols;
+    int64_t nnz_given;             // entries handed over by the host
+    int64_t nnz;                   // entries stored on the device (after optional zero drop)
+    int32_t *d_rowptr;             // [n_rows+1]
+    int32_t *d_colidx;             // [nnz]
+    double *d_vals;                // [nnz]
+    int32_t *d_keep;               // [nnz] position in the host value array (only when dropping)
+    double *d_stage;               // staging for update_values when dropping
+    int32_t *d_part;               // [coop_grid+1] row ranges of the persistent kernels
+    int tpr;                       // threads per row of the SpMV variant chosen from row lengths
+    int dropped;
+};
+
+struct nupgcm_mesh {
+    nupgcm_ctx *ctx;
+    int64_t n_cells;
+    int n_loc, n_vert, nq;
+    int64_t nb, nbd, nu, nud;
+    int32_t *d_cell_b;             // [n_loc][n_cells]   (transposed: coalesced over cells)
+    int32_t *d_cell_u;             // [n_loc*3][n_cells]
+    double *d_grad;                // [n_vert*3][n_cells]
+    double *d_vol;                 // [n_cells]
+    double *d_bdir, *d_udir;       // Dirichlet values
+    double *d_elem;                // [n_loc][n_cells] elemental vectors
+    int32_t *d_gptr;               // [nb+1] gather lists: per free DOF, the elemental slots
+    int32_t *d_gidx;               //        sorted by cell id (deterministic summation order)
+    double *d_phi;                 // [nq][n_loc] basis values
+    double *d_dphi;                // [nq][n_loc][n_vert] barycentric derivatives
+    double *d_w;                   // [nq]
+};
+
+static const int kPartialSlots = 24;   // >= memory+2 of GMRES
+static const int kMaxMemory = 20;
+
+// -------------------------------------------------------------------------------------------
+// error plumbing
+// -------------------------------------------------------------------------------------------
+
+extern char g_nupgcm_err[512];
+
+static inline int nupgcm_fail(nupgcm_ctx *ctx, int code, const char *fmt, const char *a = "",
+                              const char *b = "") {
+    char *dst = ctx ? ctx->err : g_nupgcm_err;
+    snprintf(dst, 512, fmt, a, b);
+    if (ctx) snprintf(g_nupgcm_err, 512, "%s", dst);
+    return code;
+}
+
+#define NUPGCM_CUDA(ctx, call)                                                                  \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return nupgcm_fail((ctx), NUPGCM_ERR_CUDA, "CUDA error: %s at %s",                  \
+                               cudaGetErrorString(e_), #call);                                  \
+    } while (0)
+
+#define NUPGCM_REQUIRE(ctx, cond, msg)                                                          \
+    do {                                                                                        \
+        if (!(cond)) return nupgcm_fail((ctx), NUPGCM_ERR_INVALID, "invalid argument: %s", msg); \
+    } while (0)
+
+// -------------------------------------------------------------------------------------------
+// device helpers
+// -------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// L2-coherent load: data written by other CTAs of the same (persistent) kernel must not be
+// served from this SM's L1.
+__device__ __forceinline__ double ld_cg(const double *p) { return __ldcg(p); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int T>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+    for (int o = T / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide sum with a fixed reduction tree (deterministic).  `red` needs 32 doubles.
+// Result valid in every thread.
+__device__ __forceinline__ double block_sum(double v, double *red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    double t = (lane < nw) ? red[lane] : 0.0;
+    t = warp_sum(t);
+    return t;
+}
+
+// Grid-wide barrier for co-resident CTAs (cooperative launch).  Monotonic 64-bit ticket counter:
+// barrier number g (1-based) completes when the counter reaches g*gridDim.x.
+struct GridBarrier {
+    unsigned long long *counter;
+    unsigned long long gen;
+
+    __device__ __forceinline__ void init(unsigned long long *c) {
+        counter = c;
+        gen = 0;
+    }
+    __device__ __forceinline__ void sync() {
+        __syncthreads();
+        gen += 1;
+        if (threadIdx.x == 0) {
+            const unsigned long long target = gen * (unsigned long long)gridDim.x;
+            __threadfence();                       // release this CTA's writes
+            atomicAdd(counter, 1ULL);
+            unsigned long long seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(counter)
+                             : "memory");
+            } while (seen < target);
+        }
+        __syncthreads();
+    }
+};
+
+#endif  // __CUDACC__

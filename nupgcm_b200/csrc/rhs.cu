@@ -1,0 +1,272 @@
+// Per-step element right-hand side of the buoyancy equation and the RHS combine.
+//
+// Replaces the CPU Gridap `assemble_vector(d -> advection_lform(...), B_test)` of reference
+// src/model.jl:269-273 (forms :292-300), the `rhs_adv[perm]` + host->device copy of :274-275 and
+// the broadcast of :278.  Two kernels, no atomics:
+//   1. k_elem: one thread per cell evaluates the P2 fields at the quadrature points and writes
+//      the cell's n_loc elemental integrals to d_elem[i][cell] (tables are stored transposed so
+//      that consecutive threads read consecutive addresses; u and b are gathered through the
+//      cell's DOF indices, Dirichlet values living behind the free ones);
+//   2. k_gather: one thread per free buoyancy DOF sums its elemental slots in a FIXED order
+//      (sorted by cell id at set-up), so the result is independent of scheduling and GPU count.
+#include <vector>
+
+#include "common.cuh"
+
+template <int NV>   // vertices per cell: 4 (tetrahedra) or 3 (triangles embedded in 3-D)
+struct P2 {
+    static constexpr int NE = NV * (NV - 1) / 2;
+    static constexpr int NLOC = NV + NE;
+};
+
+__device__ __constant__ int c_edge_a[6] = {0, 0, 1, 0, 1, 2};
+__device__ __constant__ int c_edge_b[6] = {1, 2, 2, 3, 3, 3};
+
+template <int NV>
+__global__ void __launch_bounds__(128)
+k_elem(const int32_t *__restrict__ cell_b, const int32_t *__restrict__ cell_u,
+       const double *__restrict__ grad, const double *__restrict__ vol,
+       const double *__restrict__ bary, const double *__restrict__ w, int nq, int64_t n_cells,
+       const double *__restrict__ b, const double *__restrict__ bp, const double *__restrict__ bdir,
+       int64_t nb, const double *__restrict__ u, const double *__restrict__ up,
+       const double *__restrict__ udir, int64_t nu, int scheme, double dt, double N2,
+       double *__restrict__ elem) {
+    constexpr int NLOC = P2<NV>::NLOC;
+    constexpr int NE = P2<NV>::NE;
+    extern __shared__ double s_q[];               // bary[nq][NV], w[nq]
+    for (int i = threadIdx.x; i < nq * NV; i += blockDim.x) s_q[i] = bary[i];
+    for (int i = threadIdx.x; i < nq; i += blockDim.x) s_q[nq * NV + i] = w[i];
+    __syncthreads();
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+
+    // gather the cell's fields: b* (advected), lin (time-derivative part), u* (advecting)
+    double bs[NLOC], lin[NLOC], us[NLOC][3];
+#pragma unroll
+    for (int i = 0; i < NLOC; ++i) {
+        const int32_t ib = cell_b[i * n_cells + c];
+        const double b0 = ib < nb ? b[ib] : bdir[ib - nb];
+        const double b1 = ib < nb ? bp[ib] : bdir[ib - nb];
+        if (scheme == 2) {
+            bs[i] = 2.0 * b0 - b1;
+            lin[i] = (4.0 / 3.0) * b0 - (1.0 / 3.0) * b1;
+        } else {
+            bs[i] = b0;
+            lin[i] = b0;
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const int32_t iu = cell_u[(i * 3 + d) * n_cells + c];
+            const double u0 = iu < nu ? u[iu] : udir[iu - nu];
+            const double u1 = iu < nu ? up[iu] : udir[iu - nu];
+            us[i][d] = scheme == 2 ? 2.0 * u0 - u1 : u0;
+        }
+    }
+    double gl[NV][3];
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) gl[k][d] = grad[(k * 3 + d) * n_cells + c];
+    const double fac = scheme == 2 ? (2.0 / 3.0) * dt : dt;
+    const double vc = vol[c];
+
+    double out[NLOC];
+#pragma unroll
+    for (int i = 0; i < NLOC; ++i) out[i] = 0.0;
+
+    for (int q = 0; q < nq; ++q) {
+        double lam[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) lam[k] = s_q[q * NV + k];
+        // P2 basis values and gradients at this point
+        double phi[NLOC];
+        double gb[3] = {0.0, 0.0, 0.0}, uq[3] = {0.0, 0.0, 0.0}, lq = 0.0;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            phi[i] = lam[i] * (2.0 * lam[i] - 1.0);
+            const double dl = 4.0 * lam[i] - 1.0;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) gb[d] = fma(bs[i] * dl, gl[i][d], gb[d]);
+        }
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const int ia = c_edge_a[e], ib = c_edge_b[e];
+            phi[NV + e] = 4.0 * lam[ia] * lam[ib];
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+                gb[d] = fma(4.0 * bs[NV + e], fma(lam[ia], gl[ib][d], lam[ib] * gl[ia][d]), gb[d]);
+        }
+#pragma unroll
+        for (int i = 0; i < NLOC; ++i) {
+            lq = fma(phi[i], lin[i], lq);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) uq[d] = fma(phi[i], us[i][d], uq[d]);
+        }
+        const double adv = uq[0] * gb[0] + uq[1] * gb[1] + uq[2] * gb[2] + uq[2] * N2;
+        const double val = (lq - fac * adv) * (s_q[nq * NV + q] * vc);
+#pragma unroll
+        for (int i = 0; i < NLOC; ++i) out[i] = fma(val, phi[i], out[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NLOC; ++i) elem[i * n_cells + c] = out[i];
+}
+
+__global__ void k_gather_elem(const int32_t *__restrict__ gptr, const int32_t *__restrict__ gidx,
+                              const double *__restrict__ elem, double *__restrict__ out, int64_t nb) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nb;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int32_t k = gptr[i]; k < gptr[i + 1]; ++k) acc += elem[gidx[k]];
+        out[i] = acc;
+    }
+}
+
+__global__ void k_rhs_combine(double *out, const double *adv, double theta, double dt,
+                              const double *diff, const double *flux, const double *rm,
+                              const double *rh, const double *rv, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        // rhs_adv + θ*rhs_diff + Δt*rhs_flux − (rhsₘ + θ*(rhsₕ + rhsᵥ)), model.jl:278
+        out[i] = adv[i] + theta * diff[i] + dt * flux[i] - (rm[i] + theta * (rh[i] + rv[i]));
+}
+
+// ---- C ABI --------------------------------------------------------------------------------
+
+template <class Tp>
+static cudaError_t upload(Tp **dst, const std::vector<Tp> &src) {
+    cudaError_t e = cudaMalloc(dst, (src.size() ? src.size() : 1) * sizeof(Tp));
+    if (e != cudaSuccess) return e;
+    if (src.size()) e = cudaMemcpy(*dst, src.data(), src.size() * sizeof(Tp), cudaMemcpyHostToDevice);
+    return e;
+}
+
+extern "C" int32_t nupgcm_mesh_create(nupgcm_ctx *ctx, int64_t n_cells, int32_t n_loc,
+                                      const int32_t *cell_b, const int32_t *cell_u,
+                                      const double *grad, const double *vol, int32_t nq,
+                                      const double *bary, const double *w, int64_t nb,
+                                      const double *b_dirichlet, int64_t nbd, int64_t nu,
+                                      const double *u_dirichlet, int64_t nud, nupgcm_mesh **out) {
+    NUPGCM_REQUIRE(nullptr, ctx, "ctx is NULL");
+    NUPGCM_REQUIRE(ctx, out && cell_b && cell_u && grad && vol && bary && w, "mesh_create: NULL argument");
+    NUPGCM_REQUIRE(ctx, n_loc == 10 || n_loc == 6, "mesh_create: n_loc must be 10 (tets) or 6 (triangles)");
+    NUPGCM_REQUIRE(ctx, n_cells > 0 && nq > 0 && nq <= 64, "mesh_create: bad n_cells or nq");
+    NUPGCM_REQUIRE(ctx, nb >= 0 && nbd >= 0 && nu >= 0 && nud >= 0, "mesh_create: negative size");
+    NUPGCM_REQUIRE(ctx, (nbd == 0 || b_dirichlet) && (nud == 0 || u_dirichlet), "mesh_create: NULL Dirichlet values");
+    NUPGCM_REQUIRE(ctx, n_cells * n_loc * 3 < INT32_MAX, "mesh_create: mesh too large for int32 slots");
+    const int nv = n_loc == 10 ? 4 : 3;
+    // transpose tables to [local][cell]; validate indices; build the per-DOF gather lists
+    std::vector<int32_t> tb((size_t)n_cells * n_loc), tu((size_t)n_cells * n_loc * 3);
+    std::vector<double> tg((size_t)n_cells * nv * 3);
+    std::vector<int32_t> gptr(nb + 1, 0);
+    for (int64_t c = 0; c < n_cells; ++c) {
+        for (int i = 0; i < n_loc; ++i) {
+            const int32_t ib = cell_b[c * n_loc + i];
+            if (ib < 0 || ib >= nb + nbd)
+                return nupgcm_fail(ctx, NUPGCM_ERR_INVALID, "invalid argument: %s", "mesh_create: cell_b index out of range");
+            tb[(size_t)i * n_cells + c] = ib;
+            if (ib < nb) gptr[ib + 1]++;
+            for (int d = 0; d < 3; ++d) {
+                const int32_t iu = cell_u[(c * n_loc + i) * 3 + d];
+                if (iu < 0 || iu >= nu + nud)
+                    return nupgcm_fail(ctx, NUPGCM_ERR_INVALID, "invalid argument: %s", "mesh_create: cell_u index out of range");
+                tu[((size_t)i * 3 + d) * n_cells + c] = iu;
+            }
+        }
+        for (int k = 0; k < nv; ++k)
+            for (int d = 0; d < 3; ++d) tg[((size_t)k * 3 + d) * n_cells + c] = grad[(c * nv + k) * 3 + d];
+    }
+    for (int64_t i = 0; i < nb; ++i) gptr[i + 1] += gptr[i];
+    std::vector<int32_t> gidx(gptr[nb]), fill(gptr.begin(), gptr.end() - 1);
+    for (int64_t c = 0; c < n_cells; ++c)          // cells in order -> lists sorted by cell id
+        for (int i = 0; i < n_loc; ++i) {
+            const int32_t ib = cell_b[c * n_loc + i];
+            if (ib < nb) gidx[fill[ib]++] = (int32_t)((int64_t)i * n_cells + c);
+        }
+    nupgcm_mesh *m = (nupgcm_mesh *)calloc(1, sizeof(nupgcm_mesh));
+    if (!m) return nupgcm_fail(ctx, NUPGCM_ERR_ALLOC, "%s", "host allocation failed");
+    m->ctx = ctx;
+    m->n_cells = n_cells;
+    m->n_loc = n_loc;
+    m->n_vert = nv;
+    m->nq = nq;
+    m->nb = nb;
+    m->nbd = nbd;
+    m->nu = nu;
+    m->nud = nud;
+    NUPGCM_CUDA(ctx, cudaSetDevice(ctx->device));
+    NUPGCM_CUDA(ctx, upload(&m->d_cell_b, tb));
+    NUPGCM_CUDA(ctx, upload(&m->d_cell_u, tu));
+    NUPGCM_CUDA(ctx, upload(&m->d_grad, tg));
+    NUPGCM_CUDA(ctx, upload(&m->d_vol, std::vector<double>(vol, vol + n_cells)));
+    NUPGCM_CUDA(ctx, upload(&m->d_bdir, std::vector<double>(b_dirichlet, b_dirichlet + nbd)));
+    NUPGCM_CUDA(ctx, upload(&m->d_udir, std::vector<double>(u_dirichlet, u_dirichlet + nud)));
+    NUPGCM_CUDA(ctx, upload(&m->d_gptr, gptr));
+    NUPGCM_CUDA(ctx, upload(&m->d_gidx, gidx));
+    NUPGCM_CUDA(ctx, upload(&m->d_phi, std::vector<double>(bary, bary + (size_t)nq * nv)));   // bary
+    NUPGCM_CUDA(ctx, upload(&m->d_w, std::vector<double>(w, w + nq)));
+    NUPGCM_CUDA(ctx, cudaMalloc(&m->d_elem, (size_t)n_cells * n_loc * sizeof(double)));
+    *out = m;
+    return NUPGCM_OK;
+}
+
+extern "C" int32_t nupgcm_mesh_destroy(nupgcm_mesh *m) {
+    if (!m) return NUPGCM_OK;
+    cudaStreamSynchronize(m->ctx->stream);
+    cudaFree(m->d_cell_b);
+    cudaFree(m->d_cell_u);
+    cudaFree(m->d_grad);
+    cudaFree(m->d_vol);
+    cudaFree(m->d_bdir);
+    cudaFree(m->d_udir);
+    cudaFree(m->d_gptr);
+    cudaFree(m->d_gidx);
+    cudaFree(m->d_phi);
+    cudaFree(m->d_w);
+    cudaFree(m->d_elem);
+    free(m);
+    return NUPGCM_OK;
+}
+
+extern "C" int32_t nupgcm_rhs_adv(nupgcm_mesh *m, int32_t scheme, double dt, double N2,
+                                  const nupgcm_vec *b, const nupgcm_vec *b_prev, const nupgcm_vec *u,
+                                  const nupgcm_vec *u_prev, nupgcm_vec *out) {
+    NUPGCM_REQUIRE(nullptr, m && b && b_prev && u && u_prev && out, "rhs_adv: NULL argument");
+    nupgcm_ctx *ctx = m->ctx;
+    NUPGCM_REQUIRE(ctx, scheme == 1 || scheme == 2, "rhs_adv: scheme must be 1 (BDF1) or 2 (BDF2)");
+    NUPGCM_REQUIRE(ctx, b->n == m->nb && b_prev->n == m->nb && out->n == m->nb, "rhs_adv: buoyancy length mismatch");
+    NUPGCM_REQUIRE(ctx, u->n >= m->nu && u_prev->n >= m->nu, "rhs_adv: velocity vector shorter than nu");
+    NUPGCM_REQUIRE(ctx, out->d != b->d && out->d != b_prev->d, "rhs_adv: out must not alias b");
+    const int block = 128;
+    const int grid = (int)((m->n_cells + block - 1) / block);
+    const size_t smem = (size_t)m->nq * (m->n_vert + 1) * sizeof(double);
+    if (m->n_vert == 4)
+        k_elem<4><<<grid, block, smem, ctx->stream>>>(m->d_cell_b, m->d_cell_u, m->d_grad, m->d_vol, m->d_phi, m->d_w, m->nq, m->n_cells, b->d, b_prev->d, m->d_bdir, m->nb, u->d, u_prev->d, m->d_udir, m->nu, scheme, dt, N2, m->d_elem);
+    else
+        k_elem<3><<<grid, block, smem, ctx->stream>>>(m->d_cell_b, m->d_cell_u, m->d_grad, m->d_vol, m->d_phi, m->d_w, m->nq, m->n_cells, b->d, b_prev->d, m->d_bdir, m->nb, u->d, u_prev->d, m->d_udir, m->nu, scheme, dt, N2, m->d_elem);
+    NUPGCM_CUDA(ctx, cudaGetLastError());
+    if (m->nb > 0) {
+        int g2 = (int)((m->nb + 255) / 256);
+        if (g2 > ctx->sm_count * 8) g2 = ctx->sm_count * 8;
+        k_gather_elem<<<g2, 256, 0, ctx->stream>>>(m->d_gptr, m->d_gidx, m->d_elem, out->d, m->nb);
+        NUPGCM_CUDA(ctx, cudaGetLastError());
+    }
+    ctx->launches += 2;
+    return NUPGCM_OK;
+}
+
+extern "C" int32_t nupgcm_rhs_combine(nupgcm_vec *out, const nupgcm_vec *rhs_adv, double theta,
+                                      double dt, const nupgcm_vec *rhs_diff, const nupgcm_vec *rhs_flux,
+                                      const nupgcm_vec *rhs_m, const nupgcm_vec *rhs_h,
+                                      const nupgcm_vec *rhs_v) {
+    NUPGCM_REQUIRE(nullptr, out && rhs_adv && rhs_diff && rhs_flux && rhs_m && rhs_h && rhs_v, "rhs_combine: NULL argument");
+    nupgcm_ctx *ctx = out->ctx;
+    const int64_t n = out->n;
+    NUPGCM_REQUIRE(ctx, rhs_adv->n == n && rhs_diff->n == n && rhs_flux->n == n && rhs_m->n == n && rhs_h->n == n && rhs_v->n == n, "rhs_combine: length mismatch");
+    if (n == 0) return NUPGCM_OK;
+    int g = (int)((n + 255) / 256);
+    if (g > ctx->sm_count * 8) g = ctx->sm_count * 8;
+    k_rhs_combine<<<g, 256, 0, ctx->stream>>>(out->d, rhs_adv->d, theta, dt, rhs_diff->d, rhs_flux->d, rhs_m->d, rhs_h->d, rhs_v->d, n);
+    ctx->launches++;
+    NUPGCM_CUDA(ctx, cudaGetLastError());
+    return NUPGCM_OK;
+}

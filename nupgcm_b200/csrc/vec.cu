@@ -1,0 +1,293 @@
+// Device vectors and the BLAS-1 style entry points used for unit parity and by the host-side
+// mirror of the reference API.  Inside the Krylov solvers these operations are fused into the
+// persistent kernels (cg.cu, gmres.cu); the stand-alone kernels here replace the separate
+// cublasDdot / cublasDnrm2 / cublasDaxpy / broadcast launches of the reference's CUDA.jl path
+// (SURVEY.md §2.1).
+#include "common.cuh"
+
+static const int kBlock = 256;
+
+static inline int grid_for(const nupgcm_ctx *ctx, int64_t n, int per_thread = 1) {
+    int64_t b = (n + (int64_t)kBlock * per_thread - 1) / ((int64_t)kBlock * per_thread);
+    int64_t cap = (int64_t)ctx->sm_count * 8;    // grid-stride beyond 8 CTAs per SM
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// ---- kernels ------------------------------------------------------------------------------
+
+__global__ void k_fill(double *x, int64_t n, double v) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        x[i] = v;
+}
+
+__global__ void k_axpby(double *y, const double *x, int64_t n, double a, double b) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = (b == 0.0) ? a * x[i] : a * x[i] + b * y[i];
+}
+
+__global__ void k_diag_apply(double *z, const double *d, const double *r, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        z[i] = d[i] * r[i];
+}
+
+__global__ void k_gather(double *dst, const double *src, const int32_t *idx, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = src[idx[i]];
+}
+
+// Two-stage deterministic reductions: stage 1 writes one partial per CTA, stage 2 (one CTA)
+// sums the partials in index order.
+__global__ void k_dot_stage1(const double *x, const double *y, int64_t n, double *partial) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        acc = fma(x[i], y[i], acc);
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+__global__ void k_sum_stage2(const double *partial, int np, double *out, int take_sqrt) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) acc += partial[i];
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) out[0] = take_sqrt ? sqrt(acc) : acc;
+}
+
+__global__ void k_maxabs_stage1(const double *x, int64_t n, double *partial) {
+    __shared__ double red[32];
+    double m = 0.0, nan = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double v = x[i];
+        if (v != v) nan = 1.0;
+        m = fmax(m, fabs(v));
+    }
+    m = warp_max(m);
+    nan = warp_max(nan);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ double rn[32];
+    if (lane == 0) { red[wid] = m; rn[wid] = nan; }
+    __syncthreads();
+    if (wid == 0) {
+        const int nw = blockDim.x >> 5;
+        m = lane < nw ? red[lane] : 0.0;
+        nan = lane < nw ? rn[lane] : 0.0;
+        m = warp_max(m);
+        nan = warp_max(nan);
+        if (lane == 0) { partial[2 * blockIdx.x] = m; partial[2 * blockIdx.x + 1] = nan; }
+    }
+}
+
+__global__ void k_maxabs_stage2(const double *partial, int np, double *out) {
+    double m = 0.0, nan = 0.0;
+    for (int i = threadIdx.x; i < np; i += 32) {
+        m = fmax(m, partial[2 * i]);
+        nan = fmax(nan, partial[2 * i + 1]);
+    }
+    m = warp_max(m);
+    nan = warp_max(nan);
+    if (threadIdx.x == 0) { out[0] = m; out[1] = nan; }
+}
+
+// ---- C ABI --------------------------------------------------------------------------------
+
+extern "C" int32_t nupgcm_vec_create(nupgcm_ctx *ctx, int64_t n, nupgcm_vec **out) {
+    NUPGCM_REQUIRE(nullptr, ctx, "ctx is NULL");
+    NUPGCM_REQUIRE(ctx, out && n >= 0, "vec_create: out is NULL or n < 0");
+    nupgcm_vec *v = (nupgcm_vec *)calloc(1, sizeof(nupgcm_vec));
+    if (!v) return nupgcm_fail(ctx, NUPGCM_ERR_ALLOC, "%s", "host allocation failed");
+    v->ctx = ctx;
+    v->n = n;
+    NUPGCM_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(&v->d, (size_t)(n > 0 ? n : 1) * sizeof(double));
+    if (e != cudaSuccess) {
+        free(v);
+        return nupgcm_fail(ctx, NUPGCM_ERR_ALLOC, "device allocation failed: %s", cudaGetErrorString(e));
+    }
+    NUPGCM_CUDA(ctx, cudaMemsetAsync(v->d, 0, (size_t)(n > 0 ? n : 1) * sizeof(double), ctx->stream));
+    *out = v;
+    return NUPGCM_OK;
+}
+
+extern "C" int32_t nupgcm_vec_destroy(nupgcm_vec *v) {
+    if (!v) return NUPGCM_OK;
+    cudaStreamSynchronize(v->ctx->stream);
+    cudaFree(v->d);
+    free(v);
+    return NUPGCM_OK;
+}
+
+extern "C" int32_t nupgcm_vec_size(const nupgcm_vec *v, int64_t *n) {
+    NUPGCM_REQUIRE(nullptr, v && n, "vec_size: NULL argument");
+    *n = v->n;
+    return NUPGCM_OK;
+}
+
+extern "C" int32_t nupgcm_vec_upload(nupgcm_vec *v, const double *host, int64_t n) {
+    NUPGCM_REQUIRE(nullptr, v, "vec is NULL");
+    NUPGCM_REQUIRE(v->ctx, host && n == v->n, "vec_upload: host is NULL or length mismatch");
+    NUPGCM_CUDA(v->ctx, cudaMemcpyAsync(v->d, host, (size_t)n * sizeof(double),
+                                        cudaMemcpyHostToDevice, v->ctx->stream));
+    NUPGCM_CUDA(v->ctx, cudaStreamSynchronize(v->ctx->stream));
+    return NUPGCM_OK;
+}
+
+extern "C" int32_t nupgcm_vec_download(const nupgcm_vec *v, double *host, int64_t n) {
+    NUPGCM_REQUIRE(nullptr, v, "vec is NULL");
+    NUPGCM_REQUIRE(v->ctx, host && n == v->n, "vec_download: host is NULL or length mismatch");
+    NUPGCM_CUDA(v->ctx, cudaMemcpyAsync(host, v->d, (size_t)n * sizeof(double),
+                                        cudaMemcpyDeviceToHost, v->ctx->stream));
+    NUPGCM_CUDA(v->ctx, cudaStreamSynchronize(v->ctx->stream));
+    return NUPGCM_OK;
+}
+
+extern "C" int32_t nupgcm_vec_fill(nupgcm_vec *v, double value) {
+    NUPGCM_REQUIRE(nullptr, v, "vec is NULL");
+    nupgcm_ctx *ctx = v->ctx;
+    if (v->n == 0) return NUPGCM_OK;
+    k_fill<<<grid_for(ctx, v->n), kBlock, 0, ctx->stream>>>(v->d, v->n, value);
+    ctx->launches++;
+    NUPGCM_CUDA(ctx, cudaGetLastError());
+    return NUPGCM_OK;
+}
+
+extern "C" int32_t nupgcm_vec_copy(nupgcm_vec *dst, const nupgcm_vec *src) {
+    NUPGCM_REQUIRE(nullptr, dst && src, "vec is NULL");
+    NUPGCM_REQUIRE(dst->ctx, dst->n == src->n, "vec_copy: length mismatch");
+    NUPGCM_CUDA(dst->ctx, cudaMemcpyAsync(dst->d, src->d, (size_t)src->n * sizeof(double),
+                                          cudaMemcpyDeviceToDevice, dst->ctx->stream));
+    return NUPGCM_OK;
+}
+
+extern "C" int32_t nupgcm_vec_axpby(nupgcm_vec *y, double alpha, const nupgcm_vec *x, double beta) {
+    NUPGCM_REQUIRE(nullptr, y && x, "vec is NULL");
+    nupgcm_ctx *ctx = y->ctx;
+    NUPGCM_REQUIRE(ctx, y->n == x->n, "vec_axpby: length mismatch");
+    if (y->n == 0) return NUPGCM_OK;
+    k_axpby<<<grid_for(ctx, y->n), kBlock, 0, ctx->stream>>>(y->d, x->d, y->n, alpha, beta);
+    ctx->launches++;
+    NUPGCM_CUDA(ctx, cudaGetLastError());
+    return NUPGCM_OK;
+}
+
+static int32_t fetch_scalars(nupgcm_ctx *ctx, int n) {
+    NUPGCM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, n * sizeof(double),
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+    NUPGCM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NUPGCM_OK;
+}
+
+static int32_t dot_impl(const nupgcm_vec *x, const nupgcm_vec *y, double *out, int take_sqrt) {
+    nupgcm_ctx *ctx = x->ctx;
+    int g = grid_for(ctx, x->n, 4);
+    if (g > ctx->coop_grid * kPartialSlots) g = ctx->coop_grid * kPartialSlots;
+    k_dot_stage1<<<g, kBlock, 0, ctx->stream>>>(x->d, y->d, x->n, ctx->d_partials);
+    k_sum_stage2<<<1, kBlock, 0, ctx->stream>>>(ctx->d_partials, g, ctx->d_scalars, take_sqrt);
+    ctx->launches += 2;
+    NUPGCM_CUDA(ctx, cudaGetLastError());
+    int32_t rc = fetch_scalars(ctx, 1);
+    if (rc) return rc;
+    *out = ctx->h_scalars[0];
+    return NUPGCM_OK;
+}
+
+extern "C" int32_t nupgcm_vec_dot(const nupgcm_vec *x, const nupgcm_vec *y, double *out) {
+    NUPGCM_REQUIRE(nullptr, x && y && out, "vec_dot: NULL argument");
+    NUPGCM_REQUIRE(x->ctx, x->n == y->n, "vec_dot: length mismatch");
+    return dot_impl(x, y, out, 0);
+}
+
+extern "C" int32_t nupgcm_vec_norm2(const nupgcm_vec *x, double *out) {
+    NUPGCM_REQUIRE(nullptr, x && out, "vec_norm2: NULL argument");
+    return dot_impl(x, x, out, 1);
+}
+
+extern "C" int32_t nupgcm_vec_maxabs(const nupgcm_vec *x, int64_t count, double *maxabs, int32_t *has_nan) {
+    NUPGCM_REQUIRE(nullptr, x, "vec is NULL");
+    nupgcm_ctx *ctx = x->ctx;
+    NUPGCM_REQUIRE(ctx, count <= x->n, "vec_maxabs: count exceeds the vector length");
+    const int64_t n = count > 0 ? count : x->n;
+    int g = grid_for(ctx, n, 4);
+    if (g > ctx->coop_grid * kPartialSlots / 2) g = ctx->coop_grid * kPartialSlots / 2;
+    k_maxabs_stage1<<<g, kBlock, 0, ctx->stream>>>(x->d, n, ctx->d_partials);
+    k_maxabs_stage2<<<1, 32, 0, ctx->stream>>>(ctx->d_partials, g, ctx->d_scalars);
+    ctx->launches += 2;
+    NUPGCM_CUDA(ctx, cudaGetLastError());
+    int32_t rc = fetch_scalars(ctx, 2);
+    if (rc) return rc;
+    if (maxabs) *maxabs = ctx->h_scalars[0];
+    if (has_nan) *has_nan = ctx->h_scalars[1] != 0.0;
+    return NUPGCM_OK;
+}
+
+extern "C" int32_t nupgcm_diag_apply(nupgcm_vec *z, const nupgcm_vec *d, const nupgcm_vec *r) {
+    NUPGCM_REQUIRE(nullptr, z && d && r, "diag_apply: NULL argument");
+    nupgcm_ctx *ctx = z->ctx;
+    NUPGCM_REQUIRE(ctx, z->n == d->n && z->n == r->n, "diag_apply: length mismatch");
+    if (z->n == 0) return NUPGCM_OK;
+    k_diag_apply<<<grid_for(ctx, z->n), kBlock, 0, ctx->stream>>>(z->d, d->d, r->d, z->n);
+    ctx->launches++;
+    NUPGCM_CUDA(ctx, cudaGetLastError());
+    return NUPGCM_OK;
+}
+
+extern "C" int32_t nupgcm_index_create(nupgcm_ctx *ctx, const int64_t *idx, int64_t n,
+                                       int32_t index_base, nupgcm_index **out) {
+    NUPGCM_REQUIRE(nullptr, ctx, "ctx is NULL");
+    NUPGCM_REQUIRE(ctx, out && idx && n >= 0, "index_create: NULL argument or n < 0");
+    int32_t *h = (int32_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(int32_t));
+    if (!h) return nupgcm_fail(ctx, NUPGCM_ERR_ALLOC, "%s", "host allocation failed");
+    int64_t maxv = -1;
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t v = idx[i] - index_base;
+        if (v < 0 || v > INT32_MAX) {
+            free(h);
+            return nupgcm_fail(ctx, NUPGCM_ERR_INVALID, "invalid argument: %s", "index out of int32 range");
+        }
+        h[i] = (int32_t)v;
+        if (v > maxv) maxv = v;
+    }
+    nupgcm_index *ix = (nupgcm_index *)calloc(1, sizeof(nupgcm_index));
+    ix->ctx = ctx;
+    ix->n = n;
+    ix->max_value = maxv;
+    cudaError_t e = cudaMalloc(&ix->d, (size_t)(n > 0 ? n : 1) * sizeof(int32_t));
+    if (e == cudaSuccess)
+        e = cudaMemcpy(ix->d, h, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice);
+    free(h);
+    if (e != cudaSuccess) {
+        free(ix);
+        return nupgcm_fail(ctx, NUPGCM_ERR_CUDA, "CUDA error: %s at %s", cudaGetErrorString(e), "index_create");
+    }
+    *out = ix;
+    return NUPGCM_OK;
+}
+
+extern "C" int32_t nupgcm_index_destroy(nupgcm_index *ix) {
+    if (!ix) return NUPGCM_OK;
+    cudaStreamSynchronize(ix->ctx->stream);
+    cudaFree(ix->d);
+    free(ix);
+    return NUPGCM_OK;
+}
+
+extern "C" int32_t nupgcm_vec_gather(nupgcm_vec *dst, const nupgcm_vec *src, const nupgcm_index *idx) {
+    NUPGCM_REQUIRE(nullptr, dst && src && idx, "vec_gather: NULL argument");
+    nupgcm_ctx *ctx = dst->ctx;
+    NUPGCM_REQUIRE(ctx, idx->n <= dst->n, "vec_gather: index longer than destination");
+    NUPGCM_REQUIRE(ctx, idx->max_value < src->n, "vec_gather: index exceeds source length");
+    NUPGCM_REQUIRE(ctx, dst->d != src->d, "vec_gather: in-place gather is not supported");
+    if (idx->n == 0) return NUPGCM_OK;
+    k_gather<<<grid_for(ctx, idx->n), kBlock, 0, ctx->stream>>>(dst->d, src->d, idx->d, idx->n);
+    ctx->launches++;
+    NUPGCM_CUDA(ctx, cudaGetLastError());
+    return NUPGCM_OK;
+}

@@ -33,6 +33,29 @@ class RawMesh:
     def dim(self) -> int:
         return max(d for d, e in self.elements.items() if len(e))
 
+    # compact binary form (the repository ships meshes as .npz, see tools/make_fixtures.py)
+    def save_npz(self, path: str):
+        names = sorted({n for d in range(4) for t in self.element_names.get(d, []) for n in t})
+        bit = {n: 1 << i for i, n in enumerate(names)}
+        out = {"nodes": self.nodes, "names": np.array(names)}
+        for d in range(4):
+            el = self.elements.get(d, np.zeros((0, d + 1), dtype=np.int64))
+            out[f"elements{d}"] = el.astype(np.int32)
+            out[f"mask{d}"] = np.array([sum(bit[n] for n in t) for t in self.element_names.get(d, [])],
+                                       dtype=np.uint32)
+        np.savez_compressed(path, **out)
+
+    @staticmethod
+    def load_npz(path: str) -> "RawMesh":
+        z = np.load(path)
+        names = [str(n) for n in z["names"]]
+        elements, element_names = {}, {}
+        for d in range(4):
+            elements[d] = z[f"elements{d}"].astype(np.int64)
+            element_names[d] = [tuple(n for i, n in enumerate(names) if m >> i & 1)
+                                for m in z[f"mask{d}"].tolist()]
+        return RawMesh(nodes=z["nodes"], elements=elements, element_names=element_names)
+
 
 def _sections(text: str) -> dict:
     out = {}

@@ -1,0 +1,372 @@
+"""ctypes binding of ``libnupgcm_b200.so`` (the C ABI declared in ``include/nupgcm_b200.h``).
+
+This is the Python twin of the ``ccall`` stubs a nuPGCM maintainer would put in
+``ext/nuPGCMB200Ext.jl``.  There is no fallback: if the shared library is
+missing, or no B200 is present when a context is created, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from ctypes import POINTER, byref, c_char_p, c_double, c_float, c_int32, c_int64, c_size_t, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnupgcm_b200.so")
+
+ORTH_MGS, ORTH_CGS2 = 0, 1
+
+
+class NupgcmError(RuntimeError):
+    pass
+
+
+class SolveStats(C.Structure):
+    _fields_ = [("niter", c_int64), ("solved", c_int32), ("inconsistent", c_int32),
+                ("breakdown", c_int32), ("reserved", c_int32), ("rnorm", c_double),
+                ("rnorm0", c_double), ("device_ms", c_float), ("launches", c_int32),
+                ("hist_len", c_int64)]
+
+
+_P = c_void_p
+_dp = POINTER(c_double)
+_ip = POINTER(c_int64)
+_i32p = POINTER(c_int32)
+
+# name -> (argtypes); every function returns int32 except the two noted below
+SIGNATURES = {
+    "nupgcm_create": [c_int32, POINTER(_P)],
+    "nupgcm_destroy": [_P],
+    "nupgcm_synchronize": [_P],
+    "nupgcm_mem_status": [_P, POINTER(c_size_t), POINTER(c_size_t)],
+    "nupgcm_device_info": [_P, _i32p, _i32p, _i32p, c_char_p],
+    "nupgcm_timer_start": [_P],
+    "nupgcm_timer_stop": [_P, POINTER(c_float)],
+    "nupgcm_launch_count": [_P, _ip],
+    "nupgcm_vec_create": [_P, c_int64, POINTER(_P)],
+    "nupgcm_vec_destroy": [_P],
+    "nupgcm_vec_size": [_P, _ip],
+    "nupgcm_vec_upload": [_P, _dp, c_int64],
+    "nupgcm_vec_download": [_P, _dp, c_int64],
+    "nupgcm_vec_fill": [_P, c_double],
+    "nupgcm_vec_copy": [_P, _P],
+    "nupgcm_vec_axpby": [_P, c_double, _P, c_double],
+    "nupgcm_vec_dot": [_P, _P, _dp],
+    "nupgcm_vec_norm2": [_P, _dp],
+    "nupgcm_vec_maxabs": [_P, c_int64, _dp, _i32p],
+    "nupgcm_diag_apply": [_P, _P, _P],
+    "nupgcm_index_create": [_P, _ip, c_int64, c_int32, POINTER(_P)],
+    "nupgcm_index_destroy": [_P],
+    "nupgcm_vec_gather": [_P, _P, _P],
+    "nupgcm_csr_create": [_P, c_int64, c_int64, c_int64, _ip, _ip, _dp, c_int32, c_int32, POINTER(_P)],
+    "nupgcm_csr_destroy": [_P],
+    "nupgcm_csr_info": [_P, _ip, _ip, _ip, _ip],
+    "nupgcm_csr_update_values": [_P, _dp, c_int64],
+    "nupgcm_csr_combine": [_P, _P, _P, _P, c_double],
+    "nupgcm_csr_inv_diag": [_P, _P],
+    "nupgcm_spmv": [_P, _P, _P, c_double, c_double],
+    "nupgcm_cg_solve": [_P, _P, c_double, _P, _P, c_double, c_double, c_int64, _dp, c_int64,
+                        POINTER(SolveStats)],
+    "nupgcm_gmres_solve": [_P, _P, c_double, _P, _P, c_double, c_double, c_int64, c_int32, c_int32,
+                           _dp, c_int64, POINTER(SolveStats)],
+    "nupgcm_mesh_create": [_P, c_int64, c_int32, _i32p, _i32p, _dp, _dp, c_int32, _dp, _dp, c_int64,
+                           _dp, c_int64, c_int64, _dp, c_int64, POINTER(_P)],
+    "nupgcm_mesh_destroy": [_P],
+    "nupgcm_rhs_adv": [_P, c_int32, c_double, c_double, _P, _P, _P, _P, _P],
+    "nupgcm_rhs_combine": [_P, _P, c_double, c_double, _P, _P, _P, _P, _P],
+}
+OTHER_SYMBOLS = ["nupgcm_version", "nupgcm_last_error"]
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and declare every prototype.  Fails loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NupgcmError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` or `make -C nupgcm_b200/csrc`.  There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = c_int32
+    lib.nupgcm_version.restype = c_int32
+    lib.nupgcm_version.argtypes = []
+    lib.nupgcm_last_error.restype = c_char_p
+    lib.nupgcm_last_error.argtypes = [_P]
+    _lib = lib
+    return lib
+
+
+def _check(rc, ctx=None):
+    if rc != 0:
+        msg = load().nupgcm_last_error(ctx)
+        raise NupgcmError(f"libnupgcm_b200 error {rc}: {msg.decode() if msg else '?'}")
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a, typ=_dp):
+    return a.ctypes.data_as(typ)
+
+
+class Context:
+    """One B200 (``nupgcm_create``).  Owns a stream; all objects created from it share it."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = _P()
+        _check(self.lib.nupgcm_create(device, byref(h)))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if self.h:
+            self.lib.nupgcm_destroy(self.h)
+            self.h = None
+
+    def synchronize(self):
+        _check(self.lib.nupgcm_synchronize(self.h), self.h)
+
+    def mem_status(self):
+        f, t = c_size_t(), c_size_t()
+        _check(self.lib.nupgcm_mem_status(self.h, byref(f), byref(t)), self.h)
+        return f.value, t.value
+
+    def device_info(self):
+        sm, ma, mi = c_int32(), c_int32(), c_int32()
+        name = C.create_string_buffer(64)
+        _check(self.lib.nupgcm_device_info(self.h, byref(sm), byref(ma), byref(mi), name), self.h)
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "name": name.value.decode()}
+
+    def timer_start(self):
+        _check(self.lib.nupgcm_timer_start(self.h), self.h)
+
+    def timer_stop(self) -> float:
+        ms = c_float()
+        _check(self.lib.nupgcm_timer_stop(self.h, byref(ms)), self.h)
+        return ms.value
+
+    def launch_count(self) -> int:
+        n = c_int64()
+        _check(self.lib.nupgcm_launch_count(self.h, byref(n)), self.h)
+        return n.value
+
+    # factories ------------------------------------------------------------------------------
+    def vector(self, data_or_n):
+        return Vector(self, data_or_n)
+
+    def index(self, idx, index_base=0):
+        return Index(self, idx, index_base)
+
+    def csr(self, mat, drop_zeros=False):
+        return CsrMatrix(self, mat, drop_zeros)
+
+
+class Vector:
+    """Device FP64 vector (the ``CuVector{Float64}`` of the reference's GPU path)."""
+
+    def __init__(self, ctx: Context, data_or_n):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        h = _P()
+        if isinstance(data_or_n, (int, np.integer)):
+            n, data = int(data_or_n), None
+        else:
+            data = _f64(data_or_n).ravel()
+            n = data.size
+        _check(self.lib.nupgcm_vec_create(ctx.h, n, byref(h)), ctx.h)
+        self.h = h
+        self.n = n
+        if data is not None and n:
+            self.upload(data)
+
+    def __len__(self):
+        return self.n
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.lib.nupgcm_vec_destroy(self.h)
+        except Exception:
+            pass
+
+    def upload(self, data):
+        data = _f64(data).ravel()
+        _check(self.lib.nupgcm_vec_upload(self.h, _ptr(data), data.size), self.ctx.h)
+        return self
+
+    def download(self, out=None):
+        out = np.empty(self.n) if out is None else out
+        _check(self.lib.nupgcm_vec_download(self.h, _ptr(out), out.size), self.ctx.h)
+        return out
+
+    def fill(self, v):
+        _check(self.lib.nupgcm_vec_fill(self.h, float(v)), self.ctx.h)
+        return self
+
+    def copy_from(self, other: "Vector"):
+        _check(self.lib.nupgcm_vec_copy(self.h, other.h), self.ctx.h)
+        return self
+
+    def axpby(self, alpha, x: "Vector", beta):
+        _check(self.lib.nupgcm_vec_axpby(self.h, float(alpha), x.h, float(beta)), self.ctx.h)
+        return self
+
+    def dot(self, other: "Vector") -> float:
+        out = c_double()
+        _check(self.lib.nupgcm_vec_dot(self.h, other.h, byref(out)), self.ctx.h)
+        return out.value
+
+    def norm2(self) -> float:
+        out = c_double()
+        _check(self.lib.nupgcm_vec_norm2(self.h, byref(out)), self.ctx.h)
+        return out.value
+
+    def maxabs(self, count=0):
+        m, nan = c_double(), c_int32()
+        _check(self.lib.nupgcm_vec_maxabs(self.h, int(count), byref(m), byref(nan)), self.ctx.h)
+        return m.value, bool(nan.value)
+
+    def gather_from(self, src: "Vector", idx: "Index"):
+        _check(self.lib.nupgcm_vec_gather(self.h, src.h, idx.h), self.ctx.h)
+        return self
+
+
+def diag_apply(z: Vector, d: Vector, r: Vector):
+    _check(z.lib.nupgcm_diag_apply(z.h, d.h, r.h), z.ctx.h)
+    return z
+
+
+class Index:
+    def __init__(self, ctx: Context, idx, index_base=0):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        h = _P()
+        _check(self.lib.nupgcm_index_create(ctx.h, _ptr(idx, _ip), idx.size, index_base, byref(h)),
+               ctx.h)
+        self.h = h
+        self.n = idx.size
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.lib.nupgcm_index_destroy(self.h)
+        except Exception:
+            pass
+
+
+class CsrMatrix:
+    """Device CSR matrix built from a SciPy sparse matrix (explicit zeros are kept unless
+    ``drop_zeros``)."""
+
+    def __init__(self, ctx: Context, mat, drop_zeros=False):
+        import scipy.sparse as sp
+        self.ctx = ctx
+        self.lib = ctx.lib
+        m = mat if sp.isspmatrix_csr(mat) else sp.csr_matrix(mat)
+        rowptr = np.ascontiguousarray(m.indptr, dtype=np.int64)
+        col = np.ascontiguousarray(m.indices, dtype=np.int64)
+        val = _f64(m.data)
+        h = _P()
+        _check(self.lib.nupgcm_csr_create(ctx.h, m.shape[0], m.shape[1], val.size,
+                                          _ptr(rowptr, _ip), _ptr(col, _ip), _ptr(val), 0,
+                                          1 if drop_zeros else 0, byref(h)), ctx.h)
+        self.h = h
+        self.shape = m.shape
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.lib.nupgcm_csr_destroy(self.h)
+        except Exception:
+            pass
+
+    def info(self):
+        a, b, c, d = c_int64(), c_int64(), c_int64(), c_int64()
+        _check(self.lib.nupgcm_csr_info(self.h, byref(a), byref(b), byref(c), byref(d)), self.ctx.h)
+        return {"n_rows": a.value, "n_cols": b.value, "nnz_given": c.value, "nnz_stored": d.value}
+
+    def update_values(self, vals):
+        vals = _f64(vals)
+        _check(self.lib.nupgcm_csr_update_values(self.h, _ptr(vals), vals.size), self.ctx.h)
+
+    def combine(self, M, Kh, Kv, theta):
+        _check(self.lib.nupgcm_csr_combine(self.h, M.h, Kh.h, Kv.h, float(theta)), self.ctx.h)
+
+    def inv_diag(self, out: Vector):
+        _check(self.lib.nupgcm_csr_inv_diag(self.h, out.h), self.ctx.h)
+        return out
+
+    def spmv(self, x: Vector, y: Vector, alpha=1.0, beta=0.0):
+        _check(self.lib.nupgcm_spmv(self.h, x.h, y.h, float(alpha), float(beta)), self.ctx.h)
+        return y
+
+
+def _solve(fn, A, dinv, pscale, y, x, atol, rtol, itmax, extra, history):
+    cap = int(history) if history else 0
+    hist = np.empty(max(cap, 1))
+    st = SolveStats()
+    rc = fn(A.h, dinv.h if dinv is not None else None, float(pscale), y.h, x.h, float(atol),
+            float(rtol), int(itmax), *extra, _ptr(hist) if cap else None, cap, byref(st))
+    _check(rc, A.ctx.h)
+    return st, hist[:st.hist_len].copy()
+
+
+def cg_solve(A: CsrMatrix, y: Vector, x: Vector, dinv: Vector | None = None, pscale=1.0,
+             atol=1e-6, rtol=1e-6, itmax=0, history=0):
+    return _solve(A.lib.nupgcm_cg_solve, A, dinv, pscale, y, x, atol, rtol, itmax, (), history)
+
+
+def gmres_solve(A: CsrMatrix, y: Vector, x: Vector, dinv: Vector | None = None, pscale=1.0,
+                atol=1e-6, rtol=1e-6, itmax=0, memory=20, orth=ORTH_MGS, history=0):
+    return _solve(A.lib.nupgcm_gmres_solve, A, dinv, pscale, y, x, atol, rtol, itmax,
+                  (int(memory), int(orth)), history)
+
+
+class ElementMesh:
+    """Device-side element tables of the advection RHS (``nupgcm_mesh_create``)."""
+
+    def __init__(self, ctx: Context, tables: dict):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        cb = np.ascontiguousarray(tables["cell_b"], dtype=np.int32)
+        cu = np.ascontiguousarray(tables["cell_u"], dtype=np.int32)
+        grad = _f64(tables["grad"])
+        vol = _f64(tables["vol"])
+        bary = _f64(tables["bary"])
+        w = _f64(tables["w"])
+        bd = _f64(tables["b_dirichlet"])
+        ud = _f64(tables["u_dirichlet"])
+        h = _P()
+        _check(self.lib.nupgcm_mesh_create(
+            ctx.h, cb.shape[0], cb.shape[1], _ptr(cb, _i32p), _ptr(cu, _i32p), _ptr(grad),
+            _ptr(vol), w.size, _ptr(bary), _ptr(w), int(tables["nb"]), _ptr(bd), bd.size,
+            int(tables["nu"]), _ptr(ud), ud.size, byref(h)), ctx.h)
+        self.h = h
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.lib.nupgcm_mesh_destroy(self.h)
+        except Exception:
+            pass
+
+    def rhs_adv(self, scheme, dt, N2, b, b_prev, u, u_prev, out):
+        _check(self.lib.nupgcm_rhs_adv(self.h, int(scheme), float(dt), float(N2), b.h, b_prev.h,
+                                       u.h, u_prev.h, out.h), self.ctx.h)
+        return out
+
+
+def rhs_combine(out, rhs_adv, theta, dt, rhs_diff, rhs_flux, rhs_m, rhs_h, rhs_v):
+    _check(out.lib.nupgcm_rhs_combine(out.h, rhs_adv.h, float(theta), float(dt), rhs_diff.h,
+                                      rhs_flux.h, rhs_m.h, rhs_h.h, rhs_v.h), out.ctx.h)
+    return out

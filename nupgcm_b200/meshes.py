@@ -14,7 +14,12 @@ class Mesh:
     def __init__(self, ifile, degree: int = 4, surface_tags=("surface",), tet_rule=None):
         if degree != 4:
             raise ValueError("only the reference's default degree=4 measures are provided")
-        raw = ifile if isinstance(ifile, RawMesh) else read_msh(ifile)
+        if isinstance(ifile, RawMesh):
+            raw = ifile
+        elif str(ifile).endswith(".npz"):
+            raw = RawMesh.load_npz(ifile)
+        else:
+            raw = read_msh(ifile)
         self.model = DiscreteModel(raw)
         self.dΩ = CellIntegrator(self.model, tet_rule=tet_rule)
         self.surface_tags = tuple(surface_tags)

@@ -1,0 +1,168 @@
+"""``State``, ``Model``, ``run!``, ``evolve!``, ``invert!``, ``sync_flow!``.
+
+Mirrors reference ``src/model.jl:1-28`` (structs), ``:47-75`` (constructors), ``:77-88``
+(``set_b!``), ``:90-211`` (``run!``), ``:213-285`` (``evolve!``), ``:302-317``
+(``invert!`` / ``sync_flow!``).  Julia's ``f!`` is spelled ``f_`` here.
+
+Difference by design: the state lives on the device in solver order between steps.  The
+reference keeps it on the host in Gridap order and crosses PCIe four times per step
+(model.jl:275,282,312; inversion.jl:104); here host copies are made only on request
+(``State.u/p/b`` properties, or ``run_(..., sync_state=True)`` which reproduces the reference's
+per-step host synchronisation for end-to-end timing)."""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import lib
+from .architectures import GPU
+from .dofs import FEData
+from .element_tables import element_tables
+from .evolution import EvolutionToolkit, collect_evolution_LHS_
+from .inputs import Forcings, Parameters
+from .inversion import InversionToolkit, invert_ as _invert_toolkit
+from .iterative_solvers import iterative_solve_
+from .timesteppers import AbstractTimestepper, BDF2, evolution_parameter, update_t_, update_Δt_
+
+
+class State:
+    """u, p, b.  Device-resident: ``xu`` = [u; p] and ``xb`` = b in solver order; the
+    properties give host copies in Gridap order (what ``save_state`` stores, IO.jl:1-10)."""
+
+    def __init__(self, model: "Model"):
+        self._m = model
+
+    @property
+    def u(self):
+        m = self._m
+        x = m.inversion.solver.x.download()
+        return x[m.fe_data.dofs.inv_p_inversion][:m.fe_data.dofs.nu]
+
+    @property
+    def p(self):
+        m = self._m
+        x = m.inversion.solver.x.download()
+        return x[m.fe_data.dofs.inv_p_inversion][m.fe_data.dofs.nu:]
+
+    @property
+    def b(self):
+        m = self._m
+        return m.xb.download()[m.fe_data.dofs.inv_p_b]
+
+
+class Model:
+    def __init__(self, arch, params: Parameters, forcings: Forcings, fe_data: FEData,
+                 inversion: InversionToolkit, evolution: EvolutionToolkit | None = None,
+                 timestepper: AbstractTimestepper | None = None, tables: dict | None = None):
+        if not isinstance(arch, GPU):
+            raise NotImplementedError("nupgcm_b200 only provides the GPU() architecture")
+        self.arch = arch
+        self.params = params
+        self.forcings = forcings
+        self.fe_data = fe_data
+        self.inversion = inversion
+        self.evolution = evolution
+        self.timestepper = timestepper
+        ctx = arch.ctx
+        nb = fe_data.dofs.nb
+        N = fe_data.dofs.nu + fe_data.dofs.np
+        # rest state (model.jl:64-75): solver vectors are zero-initialised
+        self.xb = evolution.solver.x if evolution is not None else ctx.vector(nb)
+        self.state = State(self)
+        self.step_log = []
+        if evolution is not None:
+            self.mesh = lib.ElementMesh(ctx, tables if tables is not None else element_tables(fe_data))
+            self._rhs_adv = ctx.vector(nb)
+            self._b_prev, self._b_curr = ctx.vector(nb), ctx.vector(nb)
+            self._u_prev, self._u_curr = ctx.vector(N), ctx.vector(N)
+
+
+def set_b_(model: Model, b):
+    """``set_b!`` (model.jl:77-88): a function of x (interpolated) or free values in Gridap order."""
+    Bs = model.fe_data.spaces.B
+    vals = Bs.interpolate(b)[0] if callable(b) else np.asarray(b, dtype=np.float64)
+    model.xb.upload(vals[model.fe_data.dofs.p_b])
+    return model
+
+
+def invert_(model: Model, b: lib.Vector | None = None):
+    """``invert!(model)`` (model.jl:302-309).  ``sync_flow!`` is implicit: the flow *is* the
+    solver vector."""
+    _invert_toolkit(model.inversion, model.xb if b is None else b)
+    return model
+
+
+def sync_flow_(model: Model):
+    """``sync_flow!`` (model.jl:311-317): host copies of u and p in Gridap order."""
+    x = model.inversion.solver.x.download()[model.fe_data.dofs.inv_p_inversion]
+    nu = model.fe_data.dofs.nu
+    return x[:nu], x[nu:]
+
+
+def evolve_(model: Model, u_prev: lib.Vector, b_prev: lib.Vector):
+    """``evolve!`` (model.jl:213-285): element RHS -> combine -> CG, all on the device."""
+    ev = model.evolution
+    ts = model.timestepper
+    solver = ev.solver
+    θ = evolution_parameter(model.params, ts)                      # model.jl:227
+    model.mesh.rhs_adv(ts.scheme, ts.Δt, model.params.N2, model.xb, b_prev,
+                       model.inversion.solver.x, u_prev, model._rhs_adv)   # model.jl:269-275
+    lib.rhs_combine(solver.y, model._rhs_adv, θ, ts.Δt, ev.rhs_diff, ev.rhs_flux, ev.rhs_m,
+                    ev.rhs_h, ev.rhs_v)                             # model.jl:278
+    iterative_solve_(solver)                                        # model.jl:279
+    return model
+
+
+def run_(model: Model, n_info=10, n_save=float("inf"), n_steps=None, sync_state=False,
+         host_state=None, log=None):
+    """``run!`` (model.jl:90-211).  ``n_steps`` bounds the number of steps taken by this call
+    (the reference loops until ``t >= t_stop``).  With ``sync_state`` the state is copied to the
+    host (Gridap order) and back every step, reproducing the reference's PCIe pattern."""
+    ts = model.timestepper
+    xu = model.inversion.solver.x
+    xb = model.xb
+    nu = model.fe_data.dofs.nu
+    dofs = model.fe_data.dofs
+    # copies of previous and current u, b (model.jl:120-123)
+    model._u_prev.copy_from(xu)
+    model._b_prev.copy_from(xb)
+    i = getattr(model, "_step_index", 1)
+    done = 0
+    while ts.t < ts.t_stop and (n_steps is None or done < n_steps):
+        update_Δt_(ts)                                              # model.jl:131
+        if i == 2 and isinstance(ts, BDF2):
+            collect_evolution_LHS_(model.evolution, model.params, model.forcings, ts)  # :134-137
+        if sync_state and host_state is not None:
+            # host -> device of the state the step starts from (pinned buffers)
+            xb.upload(host_state["b"][dofs.p_b])
+            xu.upload(np.concatenate([host_state["u"], host_state["p"]])[dofs.p_inversion])
+        model._u_curr.copy_from(xu)                                 # model.jl:140-141
+        model._b_curr.copy_from(xb)
+        evolve_(model, model._u_prev, model._b_prev)                # model.jl:144
+        invert_(model)                                              # model.jl:145
+        update_t_(ts)                                               # model.jl:146
+        u_max, u_nan = xu.maxabs(nu)                                # model.jl:149-153
+        b_max, b_nan = xb.maxabs()
+        if max(u_max, b_max) > 1e3 or u_nan or b_nan:
+            raise RuntimeError("Blow-up detected, stopping simulation")
+        model._u_prev, model._u_curr = model._u_curr, model._u_prev  # model.jl:156-157
+        model._b_prev, model._b_curr = model._b_curr, model._b_prev
+        if sync_state and host_state is not None:
+            x = xu.download()[dofs.inv_p_inversion]
+            host_state["u"], host_state["p"] = x[:nu], x[nu:]
+            host_state["b"] = xb.download()[dofs.inv_p_b]
+        rec = {"i": i, "t": ts.t, "cg_iters": model.evolution.solver.stats.niter,
+               "gmres_iters": model.inversion.solver.stats.niter,
+               "cg_ms": model.evolution.solver.stats.timer * 1e3,
+               "gmres_ms": model.inversion.solver.stats.timer * 1e3,
+               "cg_solved": model.evolution.solver.stats.solved,
+               "gmres_solved": model.inversion.solver.stats.solved,
+               "u_max": u_max, "b_max": b_max}
+        model.step_log.append(rec)
+        if log is not None and i % n_info == 0:
+            log(rec)
+        i += 1
+        done += 1
+    model._step_index = i
+    return model

@@ -1,0 +1,141 @@
+"""The reference's test and example set-ups as data (BASELINE.json ``configs``).
+
+Each function returns a ``Workload``: parameters, forcings, mesh, spaces arguments, timestepper
+and initial buoyancy, restating
+
+* ``bowl_mixing``       — reference ``test/bowl_mixing_tests.jl:15-77`` (config 1)
+* ``bowl_wind``         — ``test/bowl_wind_tests.jl:14-64``
+* ``bowl_dirichlet``    — ``test/bowl_dirichlet_tests.jl:14-64``
+* ``bowl_surface_flux`` — ``test/bowl_surface_flux_tests.jl:14-62``
+* ``bowl_example``      — ``examples/bowl_mixing.jl:35-52,83,159,171`` (config 2: h=0.08, μϱ=1,
+  BDF2 Δt=1e-3, b(0) = 0.1 exp(−(z+H)/(0.1α)))
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+from typing import Any, Callable
+
+import numpy as np
+
+from .dofs import FEData
+from .inputs import Forcings, Parameters, SurfaceDirichletBC, SurfaceFluxBC
+from .meshes import Mesh
+from .spaces import Spaces
+from .timesteppers import BDF2
+
+MESH_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "meshes")
+
+
+def mesh_path(dim: int, h: float) -> str:
+    return os.path.join(MESH_DIR, f"bowl{dim}D_h{h:.2f}.npz")
+
+
+@dataclass
+class Workload:
+    name: str
+    params: Parameters
+    forcings: Forcings
+    mesh: Any                      # path or RawMesh
+    spaces_kwargs: dict
+    timestepper_kwargs: dict       # for BDF2
+    b0: Callable | float | None    # initial buoyancy
+    invert_first: bool = False     # examples/bowl_mixing.jl:194 inverts before run!
+    tet_rule: str | None = None
+    _fe: FEData | None = field(default=None, repr=False)
+
+    def fe_data(self) -> FEData:
+        if self._fe is None:
+            mesh = Mesh(self.mesh, tet_rule=self.tet_rule)
+            self._fe = FEData(mesh, Spaces(mesh, **self.spaces_kwargs))
+        return self._fe
+
+    def timestepper(self):
+        return BDF2(**self.timestepper_kwargs)
+
+
+_U_DIRI = dict(u_diri_tags=["bottom", "coastline", "surface"],
+               u_diri_vals=[(0, 0, 0)] * 3,
+               u_diri_masks=[(True, True, True), (True, True, True), (False, False, True)])
+
+
+def _H(α):
+    return lambda x: α * (1 - x[:, 0] ** 2 - x[:, 1] ** 2)
+
+
+def _kappa_bottom(α):
+    H = _H(α)
+    return lambda x: 1e-2 + np.exp(-(x[:, 2] + H(x)) / (0.1 * α))
+
+
+def bowl_mixing(dim: int = 3, h: float = 0.1, mesh=None) -> Workload:
+    ε, α, μϱ = 2e-1, 0.5, 1e1
+    params = Parameters(ε=ε, α=α, μϱ=μϱ, N2=1 / α, f=lambda x: 1 + 0.5 * x[:, 1], H=_H(α))
+    κ = _kappa_bottom(α)
+    forcings = Forcings(1, κ, κ, 0.0, 0.0, SurfaceDirichletBC(0.0))
+    Δt = 1e-4 * μϱ / (α * ε) ** 2
+    return Workload(f"bowl_mixing_{dim}D", params, forcings, mesh or mesh_path(dim, h),
+                    dict(_U_DIRI, b_diri_tags=["coastline", "surface"], b_diri_vals=[0.0, 0.0]),
+                    dict(t_start=0.0, t_stop=50 * Δt, Δt=Δt), None)
+
+
+def _wind_like(name, κ, τx, b_surface, b0):
+    ε, α = np.sqrt(1e-1), 0.5
+    params = Parameters(ε=ε, α=α, μϱ=1, N2=0, f=lambda x: 0 + 0.5 * x[:, 1], H=_H(α))
+    forcings = Forcings(1, κ, κ, τx, 0.0, SurfaceDirichletBC(b_surface))
+    return Workload(name, params, forcings, mesh_path(3, 0.1),
+                    dict(_U_DIRI, b_diri_tags=["coastline", "surface"],
+                         b_diri_vals=[b_surface, b_surface]),
+                    dict(t_start=0.0, t_stop=50 * 1e-1, Δt=1e-1), b0)
+
+
+def bowl_wind() -> Workload:
+    α = 0.5
+    return _wind_like("bowl_wind", _kappa_bottom(α), lambda x: -1e-1 * np.cos(np.pi * x[:, 1] / 2),
+                      0.0, lambda x: x[:, 2] / α)
+
+
+def bowl_dirichlet() -> Workload:
+    b_surface = lambda x: x[:, 1]                                   # noqa: E731
+    return _wind_like("bowl_dirichlet", 1.0, 0.0, b_surface, b_surface)
+
+
+def bowl_surface_flux() -> Workload:
+    ε, α = np.sqrt(1e-1), 0.5
+    params = Parameters(ε=ε, α=α, μϱ=1, N2=0, f=lambda x: np.ones(len(x)), H=_H(α))
+    forcings = Forcings(1, 1e-2, 1e-2, 0.0, 0.0,
+                        SurfaceFluxBC(lambda x: 1e-3 * np.sin(np.pi * x[:, 0])))
+    return Workload("bowl_surface_flux", params, forcings, mesh_path(3, 0.1), dict(_U_DIRI),
+                    dict(t_start=0.0, t_stop=50 * 1e-1, Δt=1e-1), lambda x: x[:, 2] / α)
+
+
+def bowl_example(h: float = 0.08, mesh=None, n_steps: int | None = None) -> Workload:
+    ε, α, μϱ = 2e-1, 0.5, 1.0
+    H = _H(α)
+    params = Parameters(ε=ε, α=α, μϱ=μϱ, N2=1 / α, f=lambda x: 1.0 + 0.5 * x[:, 1], H=H)
+    κ = _kappa_bottom(α)
+    forcings = Forcings(1, κ, κ, 0.0, 0.0, SurfaceDirichletBC(0.0))
+    Δt = 1e-3
+    t_stop = 0.1 * μϱ / ε ** 2 if n_steps is None else n_steps * Δt
+    return Workload(f"bowl_example_h{h:g}", params, forcings, mesh or mesh_path(3, h),
+                    dict(_U_DIRI, b_diri_tags=["coastline", "surface"], b_diri_vals=[0.0, 0.0]),
+                    dict(t_start=0.0, t_stop=t_stop, Δt=Δt),
+                    lambda x: 0.1 * np.exp(-(x[:, 2] + H(x)) / (0.1 * α)), invert_first=True)
+
+
+def host_operands(w: Workload) -> dict:
+    """Every host-side operand of the solve path, in solver (permuted) order — what a Julia host
+    would hand over the C ABI.  Also the input of the CPU oracle."""
+    from .element_tables import element_tables
+    from .evolution import permuted_evolution_system
+    from .inversion import permuted_inversion_system
+    fe = w.fe_data()
+    A, B, b0, pscale = permuted_inversion_system(fe, w.params, w.forcings)
+    ops = permuted_evolution_system(fe, w.params, w.forcings)
+    ops.update(A=A, B=B, b0=b0, pscale=pscale, tables=element_tables(fe),
+               nu=fe.dofs.nu, np=fe.dofs.np, nb=fe.dofs.nb)
+    if w.b0 is None:
+        ops["b_init"] = np.zeros(fe.dofs.nb)
+    else:
+        ops["b_init"] = fe.spaces.B.interpolate(w.b0)[0][fe.dofs.p_b]
+    return ops

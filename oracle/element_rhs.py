@@ -1,0 +1,71 @@
+"""CPU restatement of the per-step advection right-hand side.  TEST INFRASTRUCTURE ONLY.
+
+Restates ``assemble_vector(d -> advection_lform(...), B_test)`` of reference
+``src/model.jl:269-273`` with the linear forms of ``src/model.jl:292-295`` (BDF1) and
+``:297-300`` (BDF2), followed by ``rhs_adv[perm]`` (``:274``), and the RHS combine of ``:278``.
+Gridap (which executes it in the reference) is not vendored; the quadrature rule is a parameter
+(SURVEY.md App. D item 10).  Written independently of the CUDA kernel *and* of
+``nupgcm_b200.gridap_lite`` (own basis tabulation) so that it can check both.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+_EDGES = {4: [(0, 1), (0, 2), (1, 2), (0, 3), (1, 3), (2, 3)], 3: [(0, 1), (0, 2), (1, 2)]}
+
+
+def _p2(bary):
+    nq, nb = bary.shape
+    edges = _EDGES[nb]
+    val = np.empty((nq, nb + len(edges)))
+    der = np.zeros((nq, nb + len(edges), nb))
+    for i in range(nb):
+        val[:, i] = bary[:, i] * (2.0 * bary[:, i] - 1.0)
+        der[:, i, i] = 4.0 * bary[:, i] - 1.0
+    for e, (i, j) in enumerate(edges):
+        val[:, nb + e] = 4.0 * bary[:, i] * bary[:, j]
+        der[:, nb + e, i] = 4.0 * bary[:, j]
+        der[:, nb + e, j] = 4.0 * bary[:, i]
+    return val, der
+
+
+def rhs_adv(tables, scheme, dt, N2, b, b_prev, u, u_prev):
+    """Advection RHS in solver (permuted) row order.
+
+    ``tables``: dict with ``cell_b`` (nc, nloc) and ``cell_u`` (nc, nloc, 3) indices into the
+    *extended* vectors (free DOFs in permuted order followed by Dirichlet values), ``grad``
+    (nc, d+1, 3), ``vol`` (nc,), ``bary`` (nq, d+1), ``w`` (nq,), ``nb`` free count,
+    ``b_dirichlet``, ``u_dirichlet`` value arrays.  ``b, b_prev`` (nb) and ``u, u_prev`` (nu) are
+    free values in permuted order.
+    """
+    cb, cu = tables["cell_b"], tables["cell_u"]
+    phi, dphi = _p2(tables["bary"])
+    grad = tables["grad"]
+    wq = tables["w"][None, :] * tables["vol"][:, None]                    # (nc, nq)
+    bx = np.concatenate([b, tables["b_dirichlet"]])
+    bpx = np.concatenate([b_prev, tables["b_dirichlet"]])
+    ux = np.concatenate([u, tables["u_dirichlet"]])
+    upx = np.concatenate([u_prev, tables["u_dirichlet"]])
+    if scheme == 2:          # model.jl:297-300
+        bs = 2.0 * bx[cb] - bpx[cb]
+        us = 2.0 * ux[cu] - upx[cu]
+        lin = (4.0 / 3.0) * bx[cb] - (1.0 / 3.0) * bpx[cb]
+        fac = (2.0 / 3.0) * dt
+    elif scheme == 1:        # model.jl:292-295
+        bs, us, lin, fac = bx[cb], ux[cu], bx[cb], dt
+    else:
+        raise ValueError("scheme must be 1 (BDF1) or 2 (BDF2)")
+    gphi = np.einsum("qik,ckd->cqid", dphi, grad)                         # ∇φᵢ at q
+    gb = np.einsum("cqid,ci->cqd", gphi, bs)                              # ∇b*
+    uq = np.einsum("qi,cid->cqd", phi, us)                                # u*
+    lq = np.einsum("qi,ci->cq", phi, lin)
+    val = lq - fac * (np.einsum("cqd,cqd->cq", uq, gb) + uq[:, :, 2] * N2)
+    fe = np.einsum("cq,cq,qi->ci", wq, val, phi)
+    out = np.zeros(tables["nb"] + tables["b_dirichlet"].size)
+    np.add.at(out, cb.ravel(), fe.ravel())
+    return out[:tables["nb"]]
+
+
+def rhs_combine(rhs_adv_v, θ, dt, rhs_diff, rhs_flux, rhs_m, rhs_h, rhs_v):
+    """``y = rhs_adv + θ rhs_diff + Δt rhs_flux − (rhsₘ + θ (rhsₕ + rhsᵥ))`` (model.jl:278)."""
+    return rhs_adv_v + θ * rhs_diff + dt * rhs_flux - (rhs_m + θ * (rhs_h + rhs_v))
