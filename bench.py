@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""Benchmark of nuPGCM's per-timestep solve path on B200 (BASELINE.json metric: timesteps/sec,
+bowl3D, FP64).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload at every N: BASELINE.json configs[1] — bowl3D h=0.08 mesh, examples/bowl_mixing.jl set-up
+(ε=0.2, α=½, μϱ=1, BDF2 Δt=1e-3, b(0)=0.1 exp(−(z+H)/(0.1α)), initial inversion), synthetic
+forcing, random-free deterministic data.  A "step" is one model timestep: element RHS assembly +
+RHS combine + CG solve (evolve!) and SpMV + restarted GMRES(20) solve (invert!) with the
+reference's default tolerances (atol = rtol = 1e-6), plus the blow-up check.
+
+Lines printed (rank 0, one JSON line):
+  value     timesteps/s with the state resident in HBM (device time, CUDA events per step)
+  e2e       same metric through the public Python API with the state on the HOST: every step
+            uploads (u, p, b) from host memory and downloads the new (u, p, b), as the reference's
+            host-resident state does (src/model.jl:275,282,312)
+  roofline  the dominant kernel (persistent GMRES): algorithmic bytes of its iterations / its
+            CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the CPU oracle (reference's CPU algorithm: LU factor once, direct solves per
+            step + NumPy element RHS) timed on a bounded sample of the same workload
+`--impl reference` times that CPU path alone with the same metric/config.
+
+For N > 1 each rank currently steps an independent replica of the workload (row-block sharding of
+one mesh across GPUs is designed in DESIGN.md but not built yet), so scaling is "weak".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "timesteps/sec (bowl3D, FP64)"
+UNIT = "timesteps/s"
+
+
+def workload_config(h):
+    return {"workload": f"bowl3D h={h:g} mesh, examples/bowl_mixing.jl set-up (BASELINE configs[1]): "
+                        "evolve! (element RHS + CG) + invert! (GMRES(20), P=I/h^3), atol=rtol=1e-6",
+            "mesh_h": h, "l2": "flushed between timed steps (256 MiB fill); the 29 MB matrix is "
+                              "re-read thousands of times inside one step regardless"}
+
+
+# ---------------------------------------------------------------------------------------------
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def spmv_bytes(n, nnz):
+    return 12.0 * nnz + 20.0 * n
+
+
+def gmres_bytes(n, nnz, niter, mem=20):
+    """Algorithmic bytes of `niter` GMRES(mem) iterations with MGS:
+    inner iteration j moves B_spmv + 8n(2j+3); a restart cycle adds one residual SpMV and the
+    solution update: full cycle of 20 = 21 B_spmv + 4040 n."""
+    bs = spmv_bytes(n, nnz)
+    full, part = divmod(int(niter), mem)
+    per_cycle = (mem + 1) * bs + 8.0 * n * (sum(2 * j + 3 for j in range(1, mem + 1)) + mem + 2 + 3)
+    tail = part * bs + 8.0 * n * sum(2 * j + 3 for j in range(1, part + 1))
+    if part:
+        tail += bs + 8.0 * n * (part + 2 + 3)
+    return full * per_cycle + tail
+
+
+def cg_bytes(n, nnz, niter):
+    return niter * (spmv_bytes(n, nnz) + 88.0 * n)
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i] == "Active" for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]),
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_run(w, ops, steps, warmup):
+    """The reference's CPU algorithm on this box's host cores: LU factorisations at set-up
+    (src/inversion.jl:58, src/evolution.jl:152,170), then per step NumPy element RHS + two
+    triangular-solve pairs.  Returns (timesteps/s, seconds per step list)."""
+    from oracle.stepping import cpu_model_for
+    m = cpu_model_for(w, ops, solver="direct")
+    m.invert()                                   # examples/bowl_mixing.jl:194 (also factorises)
+    m.run(n_steps=warmup)
+    t0 = time.perf_counter()
+    m.run(n_steps=steps)
+    dt = time.perf_counter() - t0
+    return steps / dt, dt
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from nupgcm_b200 import workloads as W
+    w = W.bowl_example(h=args.h)
+    ops = W.host_operands(w)
+    steps = max(1, args.steps)
+    val, secs = cpu_reference_run(w, ops, steps, min(args.warmup, 2))
+    sample = (f"{steps} timesteps of the same workload after LU factorisation (SciPy SuperLU "
+              "stands in for UMFPACK); single-threaded triangular solves + NumPy element RHS")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 / val,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args.h),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--h", type=float, default=0.08)
+    ap.add_argument("--orth", default="mgs", choices=["mgs", "cgs2"])
+    ap.add_argument("--drop-zeros", action="store_true")
+    ap.add_argument("--cpu-sample-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import nupgcm_b200 as npg
+    from nupgcm_b200 import lib
+    from nupgcm_b200 import workloads as W
+
+    w = W.bowl_example(h=args.h)
+    ops = W.host_operands(w)
+    arch = npg.GPU(local)
+    ctx = arch.ctx
+    orth = lib.ORTH_MGS if args.orth == "mgs" else lib.ORTH_CGS2
+
+    def make_model():
+        inv = npg.InversionToolkit(arch, ops["A"], ops["pscale"], ops["B"], ops["b0"], orth=orth,
+                                   drop_zeros=args.drop_zeros)
+        ts = w.timestepper()
+        ts.t_stop = float("inf")
+        evo = npg.EvolutionToolkit(arch, ops, w.params, w.forcings, ts)
+        m = npg.Model(arch, w.params, w.forcings, w.fe_data(), inv, evo, ts, tables=ops["tables"])
+        m.xb.upload(ops["b_init"])
+        npg.invert_(m)                           # examples/bowl_mixing.jl:194
+        return m
+
+    flush = ctx.vector(32 * 1024 * 1024)         # 256 MiB > 126 MB L2
+
+    def barrier():
+        ctx.synchronize()
+        if dist is not None:
+            dist.barrier()
+        ctx.synchronize()
+
+    # ---------------- device-resident run -------------------------------------------------
+    m = make_model()
+    init_gmres = m.inversion.solver.stats.niter
+    npg.run_(m, n_steps=args.warmup)
+    barrier()
+    launches0 = ctx.launch_count()
+    step_ms = []
+    with ClockSampler(local) as clocks:
+        t_wall0 = time.perf_counter()
+        for _ in range(args.steps):
+            flush.fill(0.0)
+            ctx.timer_start()
+            npg.run_(m, n_steps=1)
+            step_ms.append(ctx.timer_stop())
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    launches = ctx.launch_count() - launches0 - args.steps        # minus the L2-flush fills
+    total_ms = float(np.sum(step_ms))
+    log = m.step_log[-args.steps:]
+
+    # ---------------- end-to-end run: host-resident state ----------------------------------
+    m2 = make_model()
+    d = w.fe_data().dofs
+    x0 = m2.inversion.solver.x.download()[d.inv_p_inversion]
+    host = {"u": x0[:d.nu].copy(), "p": x0[d.nu:].copy(), "b": m2.xb.download()[d.inv_p_b]}
+    npg.run_(m2, n_steps=args.warmup, sync_state=True, host_state=host)
+    barrier()
+    t0 = time.perf_counter()
+    npg.run_(m2, n_steps=args.steps, sync_state=True, host_state=host)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    state_bytes = 8 * (d.nu + d.np + d.nb)
+
+    # ---------------- max over ranks ---------------------------------------------------------
+    if dist is not None:
+        import torch
+        t = torch.tensor([total_ms, e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s = float(t[0]), float(t[1])
+    value = world * args.steps / (total_ms * 1e-3)
+    e2e = world * args.steps / e2e_s
+
+    # ---------------- roofline of the dominant kernel (persistent GMRES) ---------------------
+    infoA = m.inversion.solver.A.info()
+    n, nnz = infoA["n_rows"], infoA["nnz_stored"]
+    g_iters = np.array([r["gmres_iters"] for r in log], dtype=float)
+    g_ms = np.array([r["gmres_ms"] for r in log], dtype=float)
+    c_iters = np.array([r["cg_iters"] for r in log], dtype=float)
+    c_ms = np.array([r["cg_ms"] for r in log], dtype=float)
+    peak, peak_src = peaks()
+    g_bytes = float(np.mean([gmres_bytes(n, nnz, k) for k in g_iters]))
+    achieved = g_bytes / (float(np.mean(g_ms)) * 1e-3) / 1e9 if g_ms.mean() > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_gmres (persistent GMRES(20), one launch per invert!)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": g_bytes, "ms_per_launch": float(g_ms.mean()),
+                "nnz_counted": nnz, "share_of_step": float(g_ms.sum() / total_ms)}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": dict(workload_config(args.h), N=n, nnz=nnz, nb=d.nb, orth=args.orth,
+                       drop_zeros=bool(args.drop_zeros),
+                       parallelism="single GPU" if world == 1 else f"{world} independent replicas"),
+        "iterations": {"gmres_per_step_mean": float(g_iters.mean()), "gmres_per_step_min": float(g_iters.min()),
+                       "gmres_per_step_max": float(g_iters.max()), "cg_per_step_mean": float(c_iters.mean()),
+                       "gmres_us_per_iter": float(1e3 * g_ms.sum() / max(g_iters.sum(), 1)),
+                       "cg_us_per_iter": float(1e3 * c_ms.sum() / max(c_iters.sum(), 1)),
+                       "initial_inversion_gmres_iters": int(init_gmres),
+                       "all_solved": bool(all(r["gmres_solved"] and r["cg_solved"] for r in log))},
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": state_bytes,
+                "d2h_bytes_per_step": state_bytes},
+        "gpu_launches": int(launches),
+        "wall_ms_per_step": 1e3 * t_wall / args.steps,
+        "roofline": roofline,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, secs = cpu_reference_run(w, ops, args.cpu_sample_steps, 1)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": f"{args.cpu_sample_steps} timesteps of the same workload "
+                                         f"({secs:.1f} s) after LU factorisation; SciPy SuperLU direct "
+                                         "solves + NumPy element RHS, single-threaded"}
+    if rank == 0:
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

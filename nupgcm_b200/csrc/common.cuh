@@ -153,28 +153,63 @@ __device__ __forceinline__ double block_sum(double v, double *red) {
 
 // Grid-wide barrier for co-resident CTAs (cooperative launch).  Monotonic 64-bit ticket counter:
 // barrier number g (1-based) completes when the counter reaches g*gridDim.x.
+// Watchdog: a CTA that waits longer than kBarrierTimeoutNs raises the abort word (counter[1]);
+// every waiter polls it, so a lost CTA turns into a reported error instead of a hung GPU.
+static const unsigned long long kBarrierTimeoutNs = 4000000000ULL;
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 struct GridBarrier {
     unsigned long long *counter;
     unsigned long long gen;
+    bool dead;
 
     __device__ __forceinline__ void init(unsigned long long *c) {
         counter = c;
         gen = 0;
+        dead = false;
     }
+    __device__ __forceinline__ bool aborted() const { return dead; }
     __device__ __forceinline__ void sync() {
+        __shared__ int s_dead;
         __syncthreads();
         gen += 1;
         if (threadIdx.x == 0) {
-            const unsigned long long target = gen * (unsigned long long)gridDim.x;
-            __threadfence();                       // release this CTA's writes
-            atomicAdd(counter, 1ULL);
-            unsigned long long seen;
-            do {
-                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(counter)
-                             : "memory");
-            } while (seen < target);
+            int bad = 0;
+            if (!dead) {
+                const unsigned long long target = gen * (unsigned long long)gridDim.x;
+                __threadfence();                       // release this CTA's writes
+                atomicAdd(counter, 1ULL);
+                unsigned long long seen, t0 = 0;
+                unsigned spins = 0;
+                for (;;) {
+                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(counter)
+                                 : "memory");
+                    if (seen >= target) break;
+                    if ((++spins & 1023u) == 0) {
+                        unsigned long long flag;
+                        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(flag)
+                                     : "l"(counter + 1) : "memory");
+                        const unsigned long long now = global_timer_ns();
+                        if (t0 == 0) t0 = now;
+                        if (flag != 0 || now - t0 > kBarrierTimeoutNs) {
+                            atomicExch(counter + 1, 1ULL);
+                            bad = 1;
+                            break;
+                        }
+                    }
+                }
+            } else {
+                bad = 1;
+            }
+            s_dead = bad;
         }
         __syncthreads();
+        dead = s_dead != 0;
     }
 };
 

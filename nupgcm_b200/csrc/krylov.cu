@@ -45,7 +45,7 @@ struct KrylovArgs {
     double *partials;        // [2][kPartialSlots][grid]
     double *hist;
     long long hist_cap;
-    double *result;          // niter, solved, inconsistent, breakdown, rnorm, rnorm0, hist_len
+    double *result;          // niter, solved, inconsistent, breakdown, rnorm, rnorm0, hist_len, aborted
 };
 
 // ---- grid-wide reductions -------------------------------------------------------------------
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg(KrylovArgs a) {
     bool zero_curv = false;
     // Krylov.jl accumulates the iterate from 0 and adds Δx at the end; here α p is accumulated
     // straight into x (which holds Δx): the same sum up to the rounding of one addition per entry.
-    while (!(solved || tired || zero_curv)) {
+    while (!(solved || tired || zero_curv || gr.bar.aborted())) {
         // Ap = A p ; pAp = p·Ap
         double part = 0.0;
         spmv_rows<T>(a, p, r0, r1, [&](int row, double ap) {
@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg(KrylovArgs a) {
         a.result[4] = rnorm;
         a.result[5] = rnorm0;
         a.result[6] = (double)(nhist < a.hist_cap ? nhist : a.hist_cap);
+        a.result[7] = gr.bar.aborted() ? 1.0 : 0.0;
     }
 }
 
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(KrylovArgs a) {
     bool tired = iter >= itmax;
     int npass = 0;
 
-    while (!(solved || tired || breakdown)) {
+    while (!(solved || tired || breakdown || gr.bar.aborted())) {
         // ---- start of a pass ----
         if (tid < kMaxMemory) { sc[tid] = 0.0; ss[tid] = 0.0; }
         if (tid <= kMaxMemory) sz[tid] = 0.0;
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(KrylovArgs a) {
         int k = 0;          // inner_iter
         int nr = 0;
         bool inner_tired = false;
-        while (!(solved || inner_tired || breakdown)) {
+        while (!(solved || inner_tired || breakdown || gr.bar.aborted())) {
             k++;
             // ---- q = M A v_k on own rows (raw v_k gathered from qbuf[cur], scaled by inv_h)
             double *q = V + (size_t)k * n;               // slot of the next basis vector
@@ -496,6 +497,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(KrylovArgs a) {
         a.result[4] = rnorm;
         a.result[5] = rnorm0;
         a.result[6] = (double)(nhist < a.hist_cap ? nhist : a.hist_cap);
+        a.result[7] = gr.bar.aborted() ? 1.0 : 0.0;
     }
 }
 
@@ -624,6 +626,9 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
                                      cudaMemcpyDeviceToHost, ctx->stream));
     NUPGCM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const double *res = ctx->h_scalars;
+    if (res[7] != 0.0)
+        return nupgcm_fail(ctx, NUPGCM_ERR_CUDA, "%s",
+                           "persistent solver kernel aborted: grid barrier watchdog expired");
     const int64_t hist_len = (int64_t)res[6];
     if (hist_cap > 0 && hist_len > 0)
         NUPGCM_CUDA(ctx, cudaMemcpy(resid_hist, ctx->d_hist, (size_t)hist_len * sizeof(double), cudaMemcpyDeviceToHost));
