@@ -148,6 +148,16 @@ int32_t nupgcm_gmres_solve(const nupgcm_csr *A, const nupgcm_vec *dinv, double p
                            int64_t itmax, int32_t memory, int32_t orth, double *resid_hist,
                            int64_t hist_cap, nupgcm_solve_stats *stats);
 
+/* diagnostics: average latency (µs) of the grid-wide reduction the persistent solvers use.
+ * mode 0: flagged-slot exchange only; 1: + block reduction; 2: + release/acquire fences. */
+int32_t nupgcm_diag_reduce_latency(nupgcm_ctx *ctx, int32_t mode, int32_t reps, int32_t grid,
+                                   int32_t threads, float *us_per_reduction);
+
+/* diagnostics: round-trip time (µs) of a flag ping-pong between CTA 0 and CTA `peer` through L2;
+ * variant = 10*store_kind + load_kind (see csrc/krylov.cu). */
+int32_t nupgcm_diag_pingpong(nupgcm_ctx *ctx, int32_t peer, int32_t variant, int32_t reps,
+                             float *us_round_trip);
+
 /* ---- per-step element right-hand side (replaces the CPU Gridap assemble_vector of
  *      src/model.jl:269-275 and the broadcast of :278) -----------------------------------
  * P2 tetrahedra (n_loc = 10) or P2 triangles (n_loc = 6).

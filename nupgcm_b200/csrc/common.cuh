@@ -56,10 +56,21 @@ struct nupgcm_csr {
     double *d_vals;                // [nnz]
     int32_t *d_keep;               // [nnz] position in the host value array (only when dropping)
     double *d_stage;               // staging for update_values when dropping
-    int32_t *d_part;               // [coop_grid+1] row ranges of the persistent kernels
+    int32_t *d_part;               // [grid+1] row ranges of the persistent kernels
     int tpr;                       // threads per row of the SpMV variant chosen from row lengths
     int dropped;
+    // SM-resident form for the persistent solvers: per CTA, the sorted list of distinct columns
+    // its rows touch ("footprint") and, per stored entry, the 16-bit position of its column in
+    // that list.  With it a CTA keeps its matrix slice in shared memory for the whole solve.
+    uint16_t *d_loc;               // [nnz] local column index
+    int32_t *d_foot_ptr;           // [coop_grid+1]
+    int32_t *d_foot;               // [sum of footprints] global column ids
+    int res_max_nnz, res_max_foot, res_max_rows;   // maxima over CTAs (0 when unavailable)
+    int prepared_grid;             // grid the partition / resident tables were built for
+    int32_t *h_rowptr, *h_col;     // host copies of the structure
 };
+
+int32_t nupgcm_csr_prepare(nupgcm_csr *A, int grid);
 
 struct nupgcm_mesh {
     nupgcm_ctx *ctx;
@@ -150,67 +161,5 @@ __device__ __forceinline__ double block_sum(double v, double *red) {
     t = warp_sum(t);
     return t;
 }
-
-// Grid-wide barrier for co-resident CTAs (cooperative launch).  Monotonic 64-bit ticket counter:
-// barrier number g (1-based) completes when the counter reaches g*gridDim.x.
-// Watchdog: a CTA that waits longer than kBarrierTimeoutNs raises the abort word (counter[1]);
-// every waiter polls it, so a lost CTA turns into a reported error instead of a hung GPU.
-static const unsigned long long kBarrierTimeoutNs = 4000000000ULL;
-
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
-struct GridBarrier {
-    unsigned long long *counter;
-    unsigned long long gen;
-    bool dead;
-
-    __device__ __forceinline__ void init(unsigned long long *c) {
-        counter = c;
-        gen = 0;
-        dead = false;
-    }
-    __device__ __forceinline__ bool aborted() const { return dead; }
-    __device__ __forceinline__ void sync() {
-        __shared__ int s_dead;
-        __syncthreads();
-        gen += 1;
-        if (threadIdx.x == 0) {
-            int bad = 0;
-            if (!dead) {
-                const unsigned long long target = gen * (unsigned long long)gridDim.x;
-                __threadfence();                       // release this CTA's writes
-                atomicAdd(counter, 1ULL);
-                unsigned long long seen, t0 = 0;
-                unsigned spins = 0;
-                for (;;) {
-                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(counter)
-                                 : "memory");
-                    if (seen >= target) break;
-                    if ((++spins & 1023u) == 0) {
-                        unsigned long long flag;
-                        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(flag)
-                                     : "l"(counter + 1) : "memory");
-                        const unsigned long long now = global_timer_ns();
-                        if (t0 == 0) t0 = now;
-                        if (flag != 0 || now - t0 > kBarrierTimeoutNs) {
-                            atomicExch(counter + 1, 1ULL);
-                            bad = 1;
-                            break;
-                        }
-                    }
-                }
-            } else {
-                bad = 1;
-            }
-            s_dead = bad;
-        }
-        __syncthreads();
-        dead = s_dead != 0;
-    }
-};
 
 #endif  // __CUDACC__

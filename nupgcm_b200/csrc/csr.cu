@@ -86,6 +86,60 @@ static void build_partition(const std::vector<int32_t> &rowptr, int64_t n_rows, 
     for (int p = 1; p <= parts; ++p) part[p] = std::max(part[p], part[p - 1]);
 }
 
+// Row partition and SM-resident tables of the persistent solvers for a grid of `grid` CTAs.
+// Cached in the handle; rebuilt only when a solve asks for a different grid.
+int32_t nupgcm_csr_prepare(nupgcm_csr *A, int grid) {
+    nupgcm_ctx *ctx = A->ctx;
+    if (A->prepared_grid == grid) return NUPGCM_OK;
+    NUPGCM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(A->d_part); A->d_part = nullptr;
+    cudaFree(A->d_loc); A->d_loc = nullptr;
+    cudaFree(A->d_foot_ptr); A->d_foot_ptr = nullptr;
+    cudaFree(A->d_foot); A->d_foot = nullptr;
+    A->res_max_nnz = A->res_max_foot = A->res_max_rows = 0;
+    const int64_t n_rows = A->n_rows, kept = A->nnz;
+    std::vector<int32_t> h_rowptr(A->h_rowptr, A->h_rowptr + n_rows + 1), part;
+    build_partition(h_rowptr, n_rows, grid, part);
+    NUPGCM_CUDA(ctx, cudaMalloc(&A->d_part, part.size() * sizeof(int32_t)));
+    NUPGCM_CUDA(ctx, cudaMemcpy(A->d_part, part.data(), part.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (A->n_rows == A->n_cols && kept > 0) {
+        const int32_t *h_col = A->h_col;
+        std::vector<uint16_t> loc(kept);
+        std::vector<int32_t> foot_ptr(grid + 1, 0), foot, tmp;
+        bool ok = true;
+        int max_nnz = 0, max_foot = 0, max_rows = 0;
+        for (int p = 0; p < grid && ok; ++p) {
+            const int32_t k0 = h_rowptr[part[p]], k1 = h_rowptr[part[p + 1]];
+            tmp.assign(h_col + k0, h_col + k1);
+            std::sort(tmp.begin(), tmp.end());
+            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+            if (tmp.size() > 65535) { ok = false; break; }
+            for (int32_t k = k0; k < k1; ++k)
+                loc[k] = (uint16_t)(std::lower_bound(tmp.begin(), tmp.end(), h_col[k]) - tmp.begin());
+            foot.insert(foot.end(), tmp.begin(), tmp.end());
+            foot_ptr[p + 1] = (int32_t)foot.size();
+            max_nnz = std::max(max_nnz, (int)(k1 - k0));
+            max_foot = std::max(max_foot, (int)tmp.size());
+            max_rows = std::max(max_rows, (int)(part[p + 1] - part[p]));
+        }
+        if (ok) {
+            NUPGCM_CUDA(ctx, cudaMalloc(&A->d_loc, ((size_t)kept + 16) * sizeof(uint16_t)));
+            NUPGCM_CUDA(ctx, cudaMemset(A->d_loc, 0, ((size_t)kept + 16) * sizeof(uint16_t)));
+            NUPGCM_CUDA(ctx, cudaMemcpy(A->d_loc, loc.data(), (size_t)kept * sizeof(uint16_t), cudaMemcpyHostToDevice));
+            NUPGCM_CUDA(ctx, cudaMalloc(&A->d_foot_ptr, foot_ptr.size() * sizeof(int32_t)));
+            NUPGCM_CUDA(ctx, cudaMemcpy(A->d_foot_ptr, foot_ptr.data(), foot_ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            NUPGCM_CUDA(ctx, cudaMalloc(&A->d_foot, (foot.size() + 8) * sizeof(int32_t)));
+            NUPGCM_CUDA(ctx, cudaMemset(A->d_foot, 0, (foot.size() + 8) * sizeof(int32_t)));
+            NUPGCM_CUDA(ctx, cudaMemcpy(A->d_foot, foot.data(), foot.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            A->res_max_nnz = max_nnz;
+            A->res_max_foot = max_foot;
+            A->res_max_rows = max_rows;
+        }
+    }
+    A->prepared_grid = grid;
+    return NUPGCM_OK;
+}
+
 // ---- C ABI --------------------------------------------------------------------------------
 
 extern "C" int32_t nupgcm_csr_create(nupgcm_ctx *ctx, int64_t n_rows, int64_t n_cols, int64_t nnz,
@@ -135,9 +189,12 @@ extern "C" int32_t nupgcm_csr_create(nupgcm_ctx *ctx, int64_t n_rows, int64_t n_
     A->tpr = choose_tpr(n_rows ? (double)kept / (double)n_rows : 0.0);
     NUPGCM_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t nz = (size_t)(kept > 0 ? kept : 1);
-    NUPGCM_CUDA(ctx, cudaMalloc(&A->d_rowptr, (size_t)(n_rows + 1) * sizeof(int32_t)));
+    // a few elements of padding let the persistent kernels bulk-copy 16-byte aligned windows
+    NUPGCM_CUDA(ctx, cudaMalloc(&A->d_rowptr, (size_t)(n_rows + 1 + 8) * sizeof(int32_t)));
+    NUPGCM_CUDA(ctx, cudaMemset(A->d_rowptr, 0, (size_t)(n_rows + 1 + 8) * sizeof(int32_t)));
     NUPGCM_CUDA(ctx, cudaMalloc(&A->d_colidx, nz * sizeof(int32_t)));
-    NUPGCM_CUDA(ctx, cudaMalloc(&A->d_vals, nz * sizeof(double)));
+    NUPGCM_CUDA(ctx, cudaMalloc(&A->d_vals, (nz + 4) * sizeof(double)));
+    NUPGCM_CUDA(ctx, cudaMemset(A->d_vals, 0, (nz + 4) * sizeof(double)));
     NUPGCM_CUDA(ctx, cudaMemcpy(A->d_rowptr, h_rowptr.data(), (size_t)(n_rows + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
     if (kept) {
         NUPGCM_CUDA(ctx, cudaMemcpy(A->d_colidx, h_col.data(), kept * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -149,10 +206,14 @@ extern "C" int32_t nupgcm_csr_create(nupgcm_ctx *ctx, int64_t n_rows, int64_t n_
             NUPGCM_CUDA(ctx, cudaMemcpy(A->d_keep, h_keep.data(), kept * sizeof(int32_t), cudaMemcpyHostToDevice));
         NUPGCM_CUDA(ctx, cudaMalloc(&A->d_stage, (size_t)(nnz > 0 ? nnz : 1) * sizeof(double)));
     }
-    std::vector<int32_t> part;
-    build_partition(h_rowptr, n_rows, ctx->coop_grid, part);
-    NUPGCM_CUDA(ctx, cudaMalloc(&A->d_part, part.size() * sizeof(int32_t)));
-    NUPGCM_CUDA(ctx, cudaMemcpy(A->d_part, part.data(), part.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    // host copies of the structure: the persistent solvers derive their row partition and
+    // SM-resident tables from them for whatever grid size a solve uses (nupgcm_csr_prepare)
+    A->h_rowptr = (int32_t *)malloc((size_t)(n_rows + 1) * sizeof(int32_t));
+    A->h_col = (int32_t *)malloc(nz * sizeof(int32_t));
+    if (!A->h_rowptr || !A->h_col) return nupgcm_fail(ctx, NUPGCM_ERR_ALLOC, "%s", "host allocation failed");
+    memcpy(A->h_rowptr, h_rowptr.data(), (size_t)(n_rows + 1) * sizeof(int32_t));
+    if (kept) memcpy(A->h_col, h_col.data(), (size_t)kept * sizeof(int32_t));
+    A->prepared_grid = 0;
     *out = A;
     return NUPGCM_OK;
 }
@@ -166,6 +227,11 @@ extern "C" int32_t nupgcm_csr_destroy(nupgcm_csr *A) {
     cudaFree(A->d_keep);
     cudaFree(A->d_stage);
     cudaFree(A->d_part);
+    cudaFree(A->d_loc);
+    cudaFree(A->d_foot_ptr);
+    cudaFree(A->d_foot);
+    free(A->h_rowptr);
+    free(A->h_col);
     free(A);
     return NUPGCM_OK;
 }

@@ -10,11 +10,15 @@
 //   * one CTA of kThreads threads per SM, launched cooperatively so that all CTAs are
 //     co-resident; CTA b owns a contiguous row range (balanced on nnz) of the matrix and the same
 //     index range of every vector, so all vector updates are CTA-local;
+//   * when the CTA's matrix slice fits in shared memory (the reference's shipped meshes: 14-29 MB
+//     over 148 SMs) it is bulk-copied there once (TMA, cp.async.bulk) and stays for the whole
+//     solve, together with the CTA's rows of the Krylov basis; otherwise the matrix streams
+//     from L2/HBM;
 //   * the only cross-CTA traffic is (i) the gather of the multiplied vector in the SpMV, read
-//     with ld.global.cg (L2-coherent), and (ii) one 8-byte partial per CTA per dot product,
-//     combined after a grid barrier in a FIXED order (slot = CTA index; lane-strided sum, then
-//     xor-shuffle tree).  Every CTA therefore computes bit-identical scalars and takes identical
-//     branches; results are run-to-run reproducible (no floating-point atomics anywhere);
+//     with ld.global.cg (L2-coherent), and (ii) one flagged 16-byte word per CTA per dot product,
+//     combined in a FIXED order (slot = CTA index; lane-strided sum, then xor-shuffle tree).
+//     Every CTA therefore computes bit-identical scalars and takes identical branches; results
+//     are run-to-run reproducible (no floating-point atomics anywhere);
 //   * scalar recurrences (Givens rotations, packed R, back substitution) are replicated per CTA.
 //
 // The recurrences restate Krylov.jl 0.10 `cg!` and `gmres!`: warm start
@@ -24,145 +28,445 @@
 
 #include "common.cuh"
 
-static const int kThreads = 1024;
+static const int kThreads = 512;       // 16 warps: up to 128 registers per thread, cheap CTA barriers
+
+struct ResidentLayout {       // byte offsets into dynamic shared memory (all multiples of 16)
+    int vals, cols, xs, rp, bar, vec, total;
+    int vec_rows;             // row capacity of one vector slice (0: vectors stay in global memory)
+};
 
 struct KrylovArgs {
     const int32_t *rowptr;
     const int32_t *colidx;
     const double *vals;
     const int32_t *part;     // [grid+1] row ranges
+    const uint16_t *loc;     // SM-resident tables (see SpmvEngine)
+    const int32_t *foot_ptr;
+    const int32_t *foot;
+    ResidentLayout lay;
     int n;
     const double *dinv;      // diagonal preconditioner or NULL
     double pscale;           // scalar preconditioner when dinv == NULL
     const double *b;
     double *x;
-    double *work;            // CG: r, p, Ap (3n)   GMRES: V ((mem+1) n) then qbuf (2n)
+    double *work;            // CG: p, then r, Ap, p, x, d slices (6n)   GMRES: V ((mem+1) n), qbuf (2n)
     double atol, rtol;
     long long itmax;
     int mem;
     int orth;
+    int poll_depth;          // polls kept in flight per awaited word (GridReduce)
     unsigned long long *barrier;
-    double *partials;        // [2][kPartialSlots][grid]
+    double *partials;        // LLSlot [2][kPartialSlots][grid]
     double *hist;
     long long hist_cap;
     double *result;          // niter, solved, inconsistent, breakdown, rnorm, rnorm0, hist_len, aborted
 };
 
-// ---- grid-wide reductions -------------------------------------------------------------------
+// Watchdog of every cross-CTA wait: a CTA that waits longer than this raises the abort word and
+// all CTAs leave the solve, so a lost CTA becomes a reported error instead of a hung GPU.
+static const unsigned long long kWaitTimeoutNs = 4000000000ULL;
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// ---- grid-wide reductions ---------------------------------------------------------------------
+// All-to-all exchange of per-CTA partial sums without atomics and without a separate barrier
+// (NCCL "LL"-style flagged words): a value is stored as two 8-byte words {lo32|flag, hi32|flag};
+// 8-byte accesses are single-copy atomic, so a reader that sees the expected flag in both words
+// has the complete value.  flag = sequence number of the reduction inside this launch (slots are
+// zeroed before the launch); two banks alternate so that a fast CTA cannot overwrite a value a
+// slow CTA has not read yet.  Every CTA reads all grid slots of a value in the same fixed order:
+// bit-identical results in all CTAs.
+//
+// publish = true additionally makes the vector rows this CTA wrote before the call visible to
+// all CTAs after the call (release fence before the slot store, acquire fence after the poll):
+// that is the grid barrier of the SpMV gather.  Reductions that only carry scalars skip the fences.
+struct LLSlot {
+    unsigned long long a, b;
+};
+
+template <bool RELEASE>
+__device__ __forceinline__ void ll_store(LLSlot *p, double v, unsigned flag) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long a = (bits & 0xffffffffULL) | ((unsigned long long)flag << 32);
+    const unsigned long long b = (bits >> 32) | ((unsigned long long)flag << 32);
+    if (RELEASE)
+        asm volatile("st.release.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+    else
+        asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+
+template <bool ACQUIRE>
+__device__ __forceinline__ void ll_load_raw(const LLSlot *p, unsigned long long &a, unsigned long long &b) {
+    if (ACQUIRE)
+        asm volatile("ld.acquire.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+    else
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+
+static const int kPollWarps = 5;           // 5 x 32 lanes cover grids up to 160 CTAs (B200: 148 SMs)
+static const long long kPollStagger = 160; // cycles between the pipelined polls
+
+// All-to-all reduction: every CTA stores its partial into its slot and reads all slots, one slot
+// per lane (ceil(grid/32) warps per value), adding them in a fixed order.  Small grids keep
+// several polls of a slot in flight (a new value is then seen one stagger interval, not one L2
+// round trip, after it lands); at full-chip grids that would multiply the 148 x 148 reads hitting
+// the same few cache lines, so the depth drops to one.  Measured on B200 (tools/krylov_microbench):
+// 1.0 us per reduction at 2-16 CTAs, 2.5-3 us at 148.
 struct GridReduce {
-    GridBarrier bar;
-    double *partials;
-    int bank;
-    int grid, bid;
+    LLSlot *slots;                   // [2][kPartialSlots][replicas][grid_pad]
+    unsigned long long *abort_word;  // raised by the watchdog
+    unsigned gen;
+    int grid, bid, depth, nrep, gpad;
+    bool dead;
 
-    __device__ __forceinline__ void init(unsigned long long *counter, double *p) {
-        bar.init(counter);
-        partials = p;
-        bank = 0;
+    // poll_cfg = depth + 16 * replicas.  Each CTA stores its partial into `replicas` copies of the
+    // slot array and CTA b reads copy b % replicas, which divides the number of readers per cache
+    // line (the contended resource at full-chip grids) by `replicas`.
+    __device__ __forceinline__ void init(unsigned long long *barrier_words, double *p, int poll_cfg) {
+        slots = reinterpret_cast<LLSlot *>(p);
+        abort_word = barrier_words + 1;
+        gen = 0;
         grid = gridDim.x;
+        gpad = (grid + 7) & ~7;                   // replicas start on 128-byte lines
         bid = blockIdx.x;
+        depth = poll_cfg & 15;
+        nrep = poll_cfg >> 4;
+        if (nrep < 1) nrep = 1;
+        dead = false;
     }
-    __device__ __forceinline__ double *slot(int j) {
-        return partials + ((size_t)(bank * kPartialSlots + j)) * grid;
+    __device__ __forceinline__ bool aborted() const { return dead; }
+    __device__ __forceinline__ LLSlot *slot(int bank, int j, int replica) {
+        return slots + ((size_t)((bank * kPartialSlots + j) * nrep + replica)) * gpad;
     }
-    // plain barrier (publishes this CTA's vector rows to the other CTAs)
-    __device__ __forceinline__ void barrier() { bar.sync(); }
 
-    // Sum over all CTAs of `count` per-CTA values held in sm_in[0..count) (written by the caller
-    // before a __syncthreads()).  Results land in sm_out[0..count), valid for every thread.
-    __device__ __forceinline__ void sum(int count, const double *sm_in, double *sm_out) {
-        if ((int)threadIdx.x < count) slot(threadIdx.x)[bid] = sm_in[threadIdx.x];
-        bar.sync();
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        for (int j = wid; j < count; j += (blockDim.x >> 5)) {
-            const double *s = slot(j);
-            double acc = 0.0;
-            for (int i = lane; i < grid; i += 32) acc += ld_cg(s + i);
-            acc = warp_sum(acc);
-            if (lane == 0) sm_out[j] = acc;
+    // Wait until the word at p carries `flag` and return its value, with DEPTH polls in flight.
+    template <bool ACQUIRE, int DEPTH>
+    __device__ __noinline__ double wait_word(const LLSlot *p, unsigned flag, bool &bad) {
+        unsigned long long a[DEPTH], b[DEPTH];
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) {
+            ll_load_raw<ACQUIRE>(p, a[d], b[d]);
+            if (d + 1 < DEPTH) {
+                const long long c0 = clock64();
+                while (clock64() - c0 < kPollStagger) {}
+            }
         }
-        bank ^= 1;
+        unsigned spins = 0;
+        unsigned long long t0 = 0;
+        for (;;) {
+#pragma unroll
+            for (int d = 0; d < DEPTH; ++d) {
+                if ((unsigned)(a[d] >> 32) == flag && (unsigned)(b[d] >> 32) == flag)
+                    return __longlong_as_double((long long)((a[d] & 0xffffffffULL) | (b[d] << 32)));
+                ll_load_raw<ACQUIRE>(p, a[d], b[d]);
+            }
+            if ((++spins & 255u) == 0) {
+                unsigned long long fl;
+                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(fl) : "l"(abort_word) : "memory");
+                const unsigned long long now = global_timer_ns();
+                if (t0 == 0) t0 = now;
+                if (fl != 0 || now - t0 > kWaitTimeoutNs) {
+                    atomicExch(abort_word, 1ULL);
+                    bad = true;
+                    return 0.0;
+                }
+            }
+        }
+    }
+    template <bool ACQUIRE>
+    __device__ __forceinline__ double wait_any(const LLSlot *p, unsigned flag, bool &bad) {
+        if (depth >= 4) return wait_word<ACQUIRE, 4>(p, flag, bad);
+        if (depth == 2) return wait_word<ACQUIRE, 2>(p, flag, bad);
+        return wait_word<ACQUIRE, 1>(p, flag, bad);
+    }
+
+    // Sum of `count` (<= kPartialSlots) values per CTA.  Value j of this CTA must be in sm_in[j]
+    // (visible to all threads).  Results land in sm_out[j], valid for every thread on return.
+    // PUBLISH additionally makes the global-memory rows this CTA wrote before the call visible to
+    // every CTA after the call (release slot stores, acquire polls).
+    template <bool PUBLISH>
+    __device__ __forceinline__ void reduce(int count, const double *sm_in, double *sm_out) {
+        __shared__ double s_partn[kPartialSlots * kPollWarps];
+        gen += 1;
+        const int bank = gen & 1;
+        if (dead) return;
+        const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+        const int npw = (grid + 31) >> 5;          // poll warps per value
+        bool bad = false;
+        for (int u = tid; u < count * nrep; u += blockDim.x)
+            ll_store<PUBLISH>(slot(bank, u / nrep, u % nrep) + bid, sm_in[u / nrep], gen);
+        const int myrep = bid % nrep;
+        for (int u = wid; u < count * npw; u += nw) {
+            const int j = u / npw, w = u % npw, li = w * 32 + lane;
+            double t = li < grid ? wait_any<PUBLISH>(slot(bank, j, myrep) + li, gen, bad) : 0.0;
+            t = warp_sum(t);
+            if (lane == 0) s_partn[j * kPollWarps + w] = t;
+        }
+        dead = __syncthreads_or(bad ? 1 : 0) != 0;
+        if (tid < count) {
+            double total = 0.0;
+            for (int w = 0; w < npw; ++w) total += s_partn[tid * kPollWarps + w];
+            sm_out[tid] = total;
+        }
         __syncthreads();
+    }
+
+    // Sum of one value per CTA.  `v` must be valid in thread 0.  Result valid in every thread.
+    template <bool PUBLISH>
+    __device__ __forceinline__ double sum1(double v) {
+        __shared__ double s_in[1], s_out[1];
+        if (threadIdx.x == 0) s_in[0] = v;
+        if (nrep > 1) __syncthreads();         // threads 0..nrep-1 store the replicas
+        reduce<PUBLISH>(1, s_in, s_out);
+        return s_out[0];
+    }
+
+    __device__ __forceinline__ void sumN(int count, const double *sm_in, double *sm_out, bool publish) {
+        if (publish) reduce<true>(count, sm_in, sm_out);
+        else reduce<false>(count, sm_in, sm_out);
+    }
+
+    // Grid barrier that publishes this CTA's vector rows.
+    __device__ __forceinline__ void barrier() {
+        __syncthreads();
+        (void)sum1<true>(0.0);
     }
 };
 
-// Block partial of one value -> sm[0] (then __syncthreads so that GridReduce::sum can read it).
-__device__ __forceinline__ void block_partial_to(double v, double *red, double *dst) {
+static const int kMaxReplicas = 8;
+static size_t reduce_scratch_bytes(int grid) {
+    return (size_t)2 * kPartialSlots * kMaxReplicas * ((grid + 7) & ~7) * sizeof(LLSlot);
+}
+
+// Block-wide sum then grid-wide sum of one value.  All vector writes made by the CTA before the
+// call are covered by `publish` (block_sum synchronises the CTA before thread 0 stores its slot).
+__device__ __forceinline__ double grid_sum(GridReduce &gr, double v, double *red, bool publish) {
     v = block_sum(v, red);
-    if (threadIdx.x == 0) *dst = v;
-    __syncthreads();
+    return publish ? gr.sum1<true>(v) : gr.sum1<false>(v);
 }
 
 // ---- SpMV over the CTA's rows -----------------------------------------------------------------
-// f(row, (A xin)[row]) is called by one lane per row.  xin is read with ld.cg because its rows
-// are written by other CTAs earlier in the same kernel.
-template <int T, class F>
-__device__ __forceinline__ void spmv_rows(const KrylovArgs &a, const double *xin, int r0, int r1,
-                                          F &&f) {
-    const int lane = threadIdx.x & (T - 1);
-    const int g = threadIdx.x / T;
-    const int G = blockDim.x / T;
-    for (int base = r0; base < r1; base += G) {     // uniform trip count over the CTA
-        const int row = base + g;
-        const bool active = row < r1;
-        double acc = 0.0;
-        if (active) {
-            const int32_t beg = __ldg(a.rowptr + row), end = __ldg(a.rowptr + row + 1);
-            int32_t k = beg + lane;
-            // two independent accumulation chains keep more loads in flight per lane
-            double acc2 = 0.0;
-            for (; k + T < end; k += 2 * T) {
-                const double v0 = __ldg(a.vals + k), v1 = __ldg(a.vals + k + T);
-                const int32_t c0 = __ldg(a.colidx + k), c1 = __ldg(a.colidx + k + T);
-                acc = fma(v0, ld_cg(xin + c0), acc);
-                acc2 = fma(v1, ld_cg(xin + c1), acc2);
-            }
-            if (k < end) acc = fma(__ldg(a.vals + k), ld_cg(xin + __ldg(a.colidx + k)), acc);
-            acc += acc2;
-        }
-        acc = group_sum<T>(acc);
-        if (active && lane == 0) f(row, acc);
-    }
+// Two forms, chosen at launch:
+//  * streaming (RES = false): entries are read from global memory (L2/HBM) every time; the
+//    multiplied vector is gathered with ld.cg.  Used when the CTA's slice does not fit on chip.
+//  * SM-resident (RES = true): at kernel start the CTA bulk-copies (TMA, cp.async.bulk) its slice
+//    of values and 16-bit local column indices into shared memory, where it stays for the whole
+//    solve; each SpMV first stages the CTA's column footprint of the multiplied vector into
+//    shared memory (one ld.cg sweep) and then runs entirely out of shared memory.
+// f(row, (A xin)[row]) is called by one lane per row.
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ double precond(const KrylovArgs &a, int row, double v) {
-    return a.dinv ? __ldg(a.dinv + row) * v : a.pscale * v;
+// Shared-memory layout of the SM-resident form.  n_vec vector slices of vec_rows rows follow the
+// matrix when they fit as well.
+static ResidentLayout resident_layout(int max_nnz, int max_foot, int max_rows, int n_vec, int limit) {
+    ResidentLayout L;
+    int off = 0;
+    L.vals = off; off += ((max_nnz + 2 + 1) & ~1) * 8;
+    L.cols = off; off += (((max_nnz + 8 + 7) & ~7) * 2 + 15) & ~15;
+    L.xs = off;   off += ((max_foot + 1) & ~1) * 8;
+    L.rp = off;   off += ((max_rows + 1 + 4 + 3) & ~3) * 4;
+    L.bar = off;  off += 16;
+    L.vec = off;
+    L.vec_rows = 0;
+    const long long vec_bytes = (long long)n_vec * ((max_rows + 1) & ~1) * 8;
+    if (off + vec_bytes <= limit) {
+        L.vec_rows = (max_rows + 1) & ~1;
+        off += (int)vec_bytes;
+    }
+    L.total = off;
+    return L;
 }
+
+template <int T, bool RES>
+struct SpmvEngine {
+    const KrylovArgs &a;
+    int r0, r1;
+    // resident state (pointers are biased so that global positions index them directly)
+    const double *vs;
+    const uint16_t *cs;
+    const int32_t *rp;
+    const int32_t *foot;
+    double *xs;
+    int nfoot;
+
+    __device__ __forceinline__ SpmvEngine(const KrylovArgs &args, int r0_, int r1_, unsigned char *smem)
+        : a(args), r0(r0_), r1(r1_) {
+        if constexpr (RES) {
+            const ResidentLayout &L = a.lay;
+            uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.bar);
+            const int k0 = a.rowptr[r0], k1 = a.rowptr[r1];
+            const int f0 = a.foot_ptr[blockIdx.x], f1 = a.foot_ptr[blockIdx.x + 1];
+            const int ka = k0 & ~1, kc = k0 & ~7, ra = r0 & ~3;
+            const uint32_t bv = (uint32_t)(((k1 - ka + 1) & ~1) * 8);
+            const uint32_t bc = (uint32_t)(((k1 - kc + 7) & ~7) * 2);
+            const uint32_t br = (uint32_t)(((r1 + 1 - ra + 3) & ~3) * 4);
+            if (threadIdx.x == 0) {
+                mbar_init(bar, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(bar, bv + bc + br);
+                uint32_t done = 0;                            // values in <= 32 KB pieces
+                while (done < bv) {
+                    const uint32_t piece = min(bv - done, 32768u);
+                    bulk_g2s(smem + L.vals + done, reinterpret_cast<const unsigned char *>(a.vals + ka) + done, piece, bar);
+                    done += piece;
+                }
+                if (bc) bulk_g2s(smem + L.cols, a.loc + kc, bc, bar);
+                bulk_g2s(smem + L.rp, a.rowptr + ra, br, bar);
+            }
+            mbar_wait(bar, 0);
+            vs = reinterpret_cast<const double *>(smem + L.vals) - ka;
+            cs = reinterpret_cast<const uint16_t *>(smem + L.cols) - kc;
+            rp = reinterpret_cast<const int32_t *>(smem + L.rp) - ra;
+            xs = reinterpret_cast<double *>(smem + L.xs);
+            foot = a.foot + f0;
+            nfoot = f1 - f0;
+        }
+    }
+
+    template <class F>
+    __device__ __forceinline__ void run(const double *xin, F &&f) {
+        const int lane = threadIdx.x & (T - 1);
+        const int g = threadIdx.x / T;
+        const int G = blockDim.x / T;
+        if constexpr (RES) {
+            __syncthreads();                                 // previous readers of xs are done
+            for (int i = threadIdx.x; i < nfoot; i += blockDim.x) xs[i] = ld_cg(xin + __ldg(foot + i));
+            __syncthreads();
+            for (int base = r0; base < r1; base += G) {      // uniform trip count over the CTA
+                const int row = base + g;
+                const bool active = row < r1;
+                double acc = 0.0, acc2 = 0.0;
+                if (active) {
+                    const int beg = rp[row], end = rp[row + 1];
+                    int k = beg + lane;
+                    for (; k + T < end; k += 2 * T) {
+                        acc = fma(vs[k], xs[cs[k]], acc);
+                        acc2 = fma(vs[k + T], xs[cs[k + T]], acc2);
+                    }
+                    if (k < end) acc = fma(vs[k], xs[cs[k]], acc);
+                    acc += acc2;
+                }
+                acc = group_sum<T>(acc);
+                if (active && lane == 0) f(row, acc);
+            }
+        } else {
+            for (int base = r0; base < r1; base += G) {      // uniform trip count over the CTA
+                const int row = base + g;
+                const bool active = row < r1;
+                double acc = 0.0;
+                if (active) {
+                    const int32_t beg = __ldg(a.rowptr + row), end = __ldg(a.rowptr + row + 1);
+                    // issue the loads of up to 4 entries per lane before the dependent gathers
+                    int32_t k = beg + lane;
+                    double acc2 = 0.0;
+                    for (; k + 3 * T < end; k += 4 * T) {
+                        const double v0 = __ldg(a.vals + k), v1 = __ldg(a.vals + k + T);
+                        const double v2 = __ldg(a.vals + k + 2 * T), v3 = __ldg(a.vals + k + 3 * T);
+                        const int32_t c0 = __ldg(a.colidx + k), c1 = __ldg(a.colidx + k + T);
+                        const int32_t c2 = __ldg(a.colidx + k + 2 * T), c3 = __ldg(a.colidx + k + 3 * T);
+                        const double x0 = ld_cg(xin + c0), x1 = ld_cg(xin + c1);
+                        const double x2 = ld_cg(xin + c2), x3 = ld_cg(xin + c3);
+                        acc = fma(v0, x0, acc);
+                        acc2 = fma(v1, x1, acc2);
+                        acc = fma(v2, x2, acc);
+                        acc2 = fma(v3, x3, acc2);
+                    }
+                    for (; k < end; k += T) acc = fma(__ldg(a.vals + k), ld_cg(xin + __ldg(a.colidx + k)), acc);
+                    acc += acc2;
+                }
+                acc = group_sum<T>(acc);
+                if (active && lane == 0) f(row, acc);
+            }
+        }
+    }
+};
+
+// CTA-local storage of a family of vectors: rows [r0, r1) of vector i are at at(i)[row].
+// In shared memory when the launch reserved room for it, else in the global workspace.
+struct VecSlices {
+    double *base;
+    size_t stride;
+    __device__ __forceinline__ VecSlices(const KrylovArgs &a, unsigned char *smem, double *global, int r0) {
+        if (a.lay.vec_rows > 0) {
+            base = reinterpret_cast<double *>(smem + a.lay.vec) - r0;
+            stride = (size_t)a.lay.vec_rows;
+        } else {
+            base = global;
+            stride = (size_t)a.n;
+        }
+    }
+    __device__ __forceinline__ double *at(int i) const { return base + (size_t)i * stride; }
+};
 
 // =============================================================================================
 // CG  (Krylov.jl cg!)
 // =============================================================================================
-template <int T>
-__global__ void __launch_bounds__(kThreads, 1) k_cg(KrylovArgs a) {
+template <int T, bool RES>
+__global__ void __launch_bounds__(kThreads, 1) k_cg(const __grid_constant__ KrylovArgs a) {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ double red[32];
-    __shared__ double sm_in[4], sm_out[4];
     GridReduce gr;
-    gr.init(a.barrier, a.partials);
+    gr.init(a.barrier, a.partials, a.poll_depth);
     const int r0 = a.part[blockIdx.x], r1 = a.part[blockIdx.x + 1];
+    SpmvEngine<T, RES> eng(a, r0, r1, dyn_smem);
     const int n = a.n;
-    double *r = a.work, *p = a.work + n, *Ap = a.work + 2 * (size_t)n;
-    double *x = a.x;                      // holds Δx (the warm start) until the very end
+    // CTA-local vectors: r, Ap, local copy of p, the iterate, the Jacobi diagonal
+    VecSlices loc(a, dyn_smem, a.work + n, r0);       // global fallback: work[n .. 6n)
+    double *r = loc.at(0), *Ap = loc.at(1), *pl = loc.at(2), *xl = loc.at(3), *dl = loc.at(4);
+    double *pg = a.work;                               // p as the other CTAs gather it
     const double eps = 2.220446049250313e-16;
     const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
+    const int tid = threadIdx.x, nthr = blockDim.x;
     long long nhist = 0;
 
-    // r = b − A Δx ; z = M r ; p = z ; γ = r·z          (own rows; z is never stored)
-    double acc = 0.0;
-    {
-        double part = 0.0;
-        spmv_rows<T>(a, x, r0, r1, [&](int row, double ax) {
-            const double rv = a.b[row] - ax;
-            const double zv = precond(a, row, rv);
-            r[row] = rv;
-            p[row] = zv;
-            part = fma(rv, zv, part);
-        });
-        acc = part;
+    for (int row = r0 + tid; row < r1; row += nthr) {
+        xl[row] = a.x[row];                            // Δx, the warm start
+        dl[row] = a.dinv ? a.dinv[row] : a.pscale;
     }
-    block_partial_to(acc, red, &sm_in[0]);
-    gr.sum(1, sm_in, sm_out);             // also publishes p for the first SpMV
-    double gamma = sm_out[0];
+    __syncthreads();
+    // r = b − A Δx ; z = M r ; p = z ; γ = r·z          (own rows; z is never stored)
+    double part = 0.0;
+    eng.run(a.x, [&](int row, double ax) {
+        const double rv = a.b[row] - ax;
+        const double zv = dl[row] * rv;
+        r[row] = rv;
+        pl[row] = zv;
+        pg[row] = zv;
+        part = fma(rv, zv, part);
+    });
+    double gamma = grid_sum(gr, part, red, true);      // also publishes p for the first SpMV
     double rnorm = sqrt(gamma);
     const double rnorm0 = rnorm;
     if (lead && a.hist && nhist < a.hist_cap) a.hist[nhist] = rnorm;
@@ -176,17 +480,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg(KrylovArgs a) {
     bool tired = iter >= itmax;
     bool zero_curv = false;
     // Krylov.jl accumulates the iterate from 0 and adds Δx at the end; here α p is accumulated
-    // straight into x (which holds Δx): the same sum up to the rounding of one addition per entry.
-    while (!(solved || tired || zero_curv || gr.bar.aborted())) {
+    // straight onto Δx: the same sum up to the rounding of one addition per entry.
+    while (!(solved || tired || zero_curv || gr.aborted())) {
         // Ap = A p ; pAp = p·Ap
-        double part = 0.0;
-        spmv_rows<T>(a, p, r0, r1, [&](int row, double ap) {
+        part = 0.0;
+        eng.run(pg, [&](int row, double ap) {
             Ap[row] = ap;
-            part = fma(p[row], ap, part);
+            part = fma(pl[row], ap, part);
         });
-        block_partial_to(part, red, &sm_in[0]);
-        gr.sum(1, sm_in, sm_out);
-        const double pAp = sm_out[0];
+        const double pAp = grid_sum(gr, part, red, false);
         if (pAp <= eps * pnorm2 && fabs(pAp) <= eps * pnorm2) {
             zero_curv = true;
             continue;
@@ -194,15 +496,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg(KrylovArgs a) {
         const double alpha = gamma / pAp;
         // x += α p ; r −= α Ap ; z = M r ; γ⁺ = r·z       (own rows, thread-per-row)
         part = 0.0;
-        for (int row = r0 + threadIdx.x; row < r1; row += blockDim.x) {
-            x[row] = fma(alpha, p[row], x[row]);
+        for (int row = r0 + tid; row < r1; row += nthr) {
+            xl[row] = fma(alpha, pl[row], xl[row]);
             const double rv = fma(-alpha, Ap[row], r[row]);
             r[row] = rv;
-            part = fma(rv, precond(a, row, rv), part);
+            part = fma(rv, dl[row] * rv, part);
         }
-        block_partial_to(part, red, &sm_in[0]);
-        gr.sum(1, sm_in, sm_out);
-        const double gamma_next = sm_out[0];
+        const double gamma_next = grid_sum(gr, part, red, false);
         rnorm = sqrt(gamma_next);
         if (lead && a.hist && nhist < a.hist_cap) a.hist[nhist] = rnorm;
         nhist++;
@@ -212,13 +512,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg(KrylovArgs a) {
             pnorm2 = gamma_next + beta * beta * pnorm2;
             gamma = gamma_next;
             // p = z + β p   (own rows), then publish p for the next SpMV gather
-            for (int row = r0 + threadIdx.x; row < r1; row += blockDim.x)
-                p[row] = fma(beta, p[row], precond(a, row, r[row]));
+            for (int row = r0 + tid; row < r1; row += nthr) {
+                const double pv = fma(beta, pl[row], dl[row] * r[row]);
+                pl[row] = pv;
+                pg[row] = pv;
+            }
             gr.barrier();
         }
         iter++;
         tired = iter >= itmax;
     }
+    for (int row = r0 + tid; row < r1; row += nthr) a.x[row] = xl[row];
     if (lead) {
         a.result[0] = (double)iter;
         a.result[1] = solved ? 1.0 : 0.0;
@@ -227,7 +531,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg(KrylovArgs a) {
         a.result[4] = rnorm;
         a.result[5] = rnorm0;
         a.result[6] = (double)(nhist < a.hist_cap ? nhist : a.hist_cap);
-        a.result[7] = gr.bar.aborted() ? 1.0 : 0.0;
+        a.result[7] = gr.aborted() ? 1.0 : 0.0;
     }
 }
 
@@ -258,22 +562,28 @@ __device__ __forceinline__ void sym_givens(double a, double b, double &c, double
     }
 }
 
-template <int T>
-__global__ void __launch_bounds__(kThreads, 1) k_gmres(KrylovArgs a) {
+__device__ __forceinline__ double precond(const KrylovArgs &a, int row, double v) {
+    return a.dinv ? __ldg(a.dinv + row) * v : a.pscale * v;
+}
+
+template <int T, bool RES>
+__global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ KrylovArgs a) {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ double red[32];
     __shared__ double sm_in[kPartialSlots], sm_out[kPartialSlots];
     __shared__ double sc[kMaxMemory], ss[kMaxMemory], sz[kMaxMemory + 1], sy[kMaxMemory + 1];
     __shared__ double sR[kMaxMemory * (kMaxMemory + 1) / 2];
-    __shared__ double s_flags[4];      // rnorm, solved, breakdown, Hbis
+    __shared__ double s_flags[4];      // rnorm, inconsistent, -, Hbis
     __shared__ double s_seg[32];
 
     GridReduce gr;
-    gr.init(a.barrier, a.partials);
+    gr.init(a.barrier, a.partials, a.poll_depth);
     const int r0 = a.part[blockIdx.x], r1 = a.part[blockIdx.x + 1];
+    SpmvEngine<T, RES> eng(a, r0, r1, dyn_smem);
     const int n = a.n;
     const int mem = a.mem;
-    double *V = a.work;                                  // V[i] = V + i*n, i = 0..mem
-    double *qbuf = a.work + (size_t)(mem + 1) * n;       // two raw buffers for the SpMV gather
+    VecSlices V(a, dyn_smem, a.work, r0);                // V.at(i), i = 0..mem: CTA-local basis rows
+    double *qbuf = a.work + (size_t)(mem + 1) * n;       // two raw buffers for the SpMV gather (global)
     double *x = a.x;
     const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -283,18 +593,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(KrylovArgs a) {
 
     // ---- initial residual: w = b − A x0 ; r0 = M w (raw into qbuf[0]) ; β = ‖r0‖
     int cur = 0;
+    double beta;
     {
         double part = 0.0;
         double *q0 = qbuf;
-        spmv_rows<T>(a, x, r0, r1, [&](int row, double ax) {
+        double *v0 = V.at(0);
+        eng.run(x, [&](int row, double ax) {
             const double v = precond(a, row, a.b[row] - ax);
             q0[row] = v;
+            v0[row] = v;
             part = fma(v, v, part);
         });
-        block_partial_to(part, red, &sm_in[0]);
-        gr.sum(1, sm_in, sm_out);
+        beta = sqrt(grid_sum(gr, part, red, true));
     }
-    double beta = sqrt(sm_out[0]);
     double rnorm = beta;
     const double rnorm0 = beta;
     if (lead && a.hist && nhist < a.hist_cap) a.hist[nhist] = rnorm;
@@ -308,7 +619,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(KrylovArgs a) {
     bool tired = iter >= itmax;
     int npass = 0;
 
-    while (!(solved || tired || breakdown || gr.bar.aborted())) {
+    while (!(solved || tired || breakdown || gr.aborted())) {
         // ---- start of a pass ----
         if (tid < kMaxMemory) { sc[tid] = 0.0; ss[tid] = 0.0; }
         if (tid <= kMaxMemory) sz[tid] = 0.0;
@@ -317,56 +628,52 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(KrylovArgs a) {
             // w = b − A x ; r0 = M w ; β = ‖r0‖   (x was published by the barrier ending the last pass)
             double part = 0.0;
             double *q0 = qbuf + (size_t)cur * n;
-            spmv_rows<T>(a, x, r0, r1, [&](int row, double ax) {
+            double *v0 = V.at(0);
+            eng.run(x, [&](int row, double ax) {
                 const double v = precond(a, row, a.b[row] - ax);
                 q0[row] = v;
+                v0[row] = v;
                 part = fma(v, v, part);
             });
-            block_partial_to(part, red, &sm_in[0]);
-            gr.sum(1, sm_in, sm_out);
-            beta = sqrt(sm_out[0]);
+            beta = sqrt(grid_sum(gr, part, red, true));
         }
         __syncthreads();
         if (tid == 0) sz[0] = beta;
         // V[0] = r0/β on own rows; other CTAs read the raw vector scaled by inv_h
         double inv_h = 1.0 / beta;
         {
-            const double *q0 = qbuf + (size_t)cur * n;
-            for (int row = r0 + tid; row < r1; row += nthr) V[row] = q0[row] * inv_h;
+            double *v0 = V.at(0);
+            for (int row = r0 + tid; row < r1; row += nthr) v0[row] *= inv_h;
         }
         npass++;
         int k = 0;          // inner_iter
         int nr = 0;
         bool inner_tired = false;
-        while (!(solved || inner_tired || breakdown || gr.bar.aborted())) {
+        while (!(solved || inner_tired || breakdown || gr.aborted())) {
             k++;
             // ---- q = M A v_k on own rows (raw v_k gathered from qbuf[cur], scaled by inv_h)
-            double *q = V + (size_t)k * n;               // slot of the next basis vector
+            double *q = V.at(k);                          // slot of the next basis vector
             const double *src = qbuf + (size_t)cur * n;
             double *dst = qbuf + (size_t)(cur ^ 1) * n;
-            spmv_rows<T>(a, src, r0, r1, [&](int row, double av) {
-                q[row] = precond(a, row, av * inv_h);
-            });
+            eng.run(src, [&](int row, double av) { q[row] = precond(a, row, av * inv_h); });
             __syncthreads();
             double hsq = 0.0;                            // ‖q‖² after orthogonalisation
             if (a.orth == NUPGCM_ORTH_MGS) {
                 // h_i = v_i·q ; q −= h_i v_i, sequentially (one grid reduction per i)
                 double hprev = 0.0;
                 for (int i = 0; i < k; ++i) {
-                    const double *vi = V + (size_t)i * n;
-                    const double *vp = V + (size_t)(i > 0 ? i - 1 : 0) * n;
+                    const double *vi = V.at(i);
+                    const double *vp = V.at(i > 0 ? i - 1 : 0);
                     double part = 0.0;
                     for (int row = r0 + tid; row < r1; row += nthr) {
                         double qv = q[row];
                         if (i > 0) { qv = fma(-hprev, vp[row], qv); q[row] = qv; }
                         part = fma(vi[row], qv, part);
                     }
-                    block_partial_to(part, red, &sm_in[0]);
-                    gr.sum(1, sm_in, sm_out);
-                    hprev = sm_out[0];
+                    hprev = grid_sum(gr, part, red, false);
                     if (tid == 0) sR[nr + i] = hprev;
                 }
-                const double *vp = V + (size_t)(k - 1) * n;
+                const double *vp = V.at(k - 1);
                 double part = 0.0;
                 for (int row = r0 + tid; row < r1; row += nthr) {
                     const double qv = fma(-hprev, vp[row], q[row]);
@@ -374,9 +681,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(KrylovArgs a) {
                     dst[row] = qv;
                     part = fma(qv, qv, part);
                 }
-                block_partial_to(part, red, &sm_in[0]);
-                gr.sum(1, sm_in, sm_out);
-                hsq = sm_out[0];
+                hsq = grid_sum(gr, part, red, true);     // publishes dst for the next gather
             } else {
                 // CGS2: all k projections at once, twice; warp w handles basis vector w % k on
                 // row segment w / k.
@@ -387,14 +692,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(KrylovArgs a) {
                     __syncthreads();
                     for (int u = wid; u < k * nseg; u += nwarps) {
                         const int i = u % k, sg = u / k;
-                        const double *vi = V + (size_t)i * n;
+                        const double *vi = V.at(i);
                         const int lo = r0 + sg * seglen, hi = min(r1, lo + seglen);
                         double part = 0.0;
                         for (int row = lo + lane; row < hi; row += 32) part = fma(vi[row], q[row], part);
                         part = warp_sum(part);
-                        if (lane == 0) s_seg[u % 32] = part;   // k*nseg <= 32 when k <= nwarps
-                        __syncwarp();
-                        // segments of one vector are summed in order by the first segment's warp
+                        if (lane == 0) s_seg[u] = part;        // k*nseg <= nwarps <= 32
                     }
                     __syncthreads();
                     if (tid < k) {
@@ -403,21 +706,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(KrylovArgs a) {
                         sm_in[tid] = t;
                     }
                     __syncthreads();
-                    gr.sum(k, sm_in, sm_out);
+                    gr.sumN(k, sm_in, sm_out, false);
                     // q −= Σ h_i v_i  (own rows)
                     double part = 0.0;
                     for (int row = r0 + tid; row < r1; row += nthr) {
                         double qv = q[row];
-                        for (int i = 0; i < k; ++i) qv = fma(-sm_out[i], V[(size_t)i * n + row], qv);
+                        for (int i = 0; i < k; ++i) qv = fma(-sm_out[i], V.at(i)[row], qv);
                         q[row] = qv;
                         if (pass == 1) { dst[row] = qv; part = fma(qv, qv, part); }
                     }
                     if (tid < k) sR[nr + tid] = (pass == 0) ? sm_out[tid] : sR[nr + tid] + sm_out[tid];
-                    if (pass == 1) {
-                        block_partial_to(part, red, &sm_in[0]);
-                        gr.sum(1, sm_in, sm_out);
-                        hsq = sm_out[0];
-                    }
+                    if (pass == 1) hsq = grid_sum(gr, part, red, true);
                 }
             }
             // ---- scalar recurrences, replicated per CTA (thread 0), Krylov.jl order
@@ -477,7 +776,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(KrylovArgs a) {
         if (s_flags[1] != 0.0) inconsistent = true;
         for (int row = r0 + tid; row < r1; row += nthr) {
             double xr = 0.0;
-            for (int i = 0; i < k; ++i) xr = fma(sy[i], V[(size_t)i * n + row], xr);
+            for (int i = 0; i < k; ++i) xr = fma(sy[i], V.at(i)[row], xr);
             x[row] += xr;
         }
         inner_itmax -= k;
@@ -497,13 +796,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(KrylovArgs a) {
         a.result[4] = rnorm;
         a.result[5] = rnorm0;
         a.result[6] = (double)(nhist < a.hist_cap ? nhist : a.hist_cap);
-        a.result[7] = gr.bar.aborted() ? 1.0 : 0.0;
+        a.result[7] = gr.aborted() ? 1.0 : 0.0;
     }
 }
 
 // =============================================================================================
 // host side
 // =============================================================================================
+
+// depth + 16 * replicas of GridReduce (NUPGCM_POLL_DEPTH / NUPGCM_REPLICAS override)
+static int poll_config(int grid) {
+    int depth = 1, rep = grid > 100 ? 2 : 1;   // measured on B200: tools/reduce_cliff.py
+    if (const char *ed = getenv("NUPGCM_POLL_DEPTH")) {
+        const int v = atoi(ed);
+        if (v == 1 || v == 2 || v == 4) depth = v;
+    }
+    if (const char *er = getenv("NUPGCM_REPLICAS")) {
+        const int v = atoi(er);
+        if (v >= 1 && v <= kMaxReplicas) rep = v;
+    }
+    return depth + 16 * rep;
+}
 
 static int pow2floor(int v) {
     int p = 1;
@@ -513,15 +826,15 @@ static int pow2floor(int v) {
 
 // Lanes per row inside the persistent kernels: the row-length choice, narrowed when the CTA has
 // fewer rows than row groups so that all rows of the CTA are processed in one sweep.
-static int persistent_tpr(const nupgcm_csr *A) {
+static int persistent_tpr(const nupgcm_csr *A, bool resident, int grid) {
     const char *env = getenv("NUPGCM_TPR");
     if (env) {
         int v = atoi(env);
         if (v == 2 || v == 4 || v == 8 || v == 16 || v == 32) return v;
     }
-    const int grid = A->ctx->coop_grid;
     const int rows_per_cta = (int)((A->n_rows + grid - 1) / grid);
     int t = A->tpr;
+    if (resident) return std::min(t, 8);       // measured on B200: 4-8 lanes per row are fastest
     if (rows_per_cta > 0 && rows_per_cta * t > kThreads && rows_per_cta <= kThreads / 2)
         t = std::max(2, pow2floor(kThreads / rows_per_cta));
     return std::min(t, 32);
@@ -548,11 +861,35 @@ static int32_t ensure_workspace(nupgcm_ctx *ctx, size_t bytes) {
     return NUPGCM_OK;
 }
 
-template <int T>
-static cudaError_t launch(bool gmres, KrylovArgs &args, nupgcm_ctx *ctx) {
+template <int T, bool RES>
+static cudaError_t launch2(bool gmres, KrylovArgs &args, nupgcm_ctx *ctx, size_t smem, int grid) {
     void *params[] = {&args};
-    const void *fn = gmres ? (const void *)k_gmres<T> : (const void *)k_cg<T>;
-    return cudaLaunchCooperativeKernel(fn, dim3(ctx->coop_grid), dim3(kThreads), params, 0, ctx->stream);
+    const void *fn = gmres ? (const void *)k_gmres<T, RES> : (const void *)k_cg<T, RES>;
+    if (smem > 0) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), params, smem, ctx->stream);
+}
+
+template <int T>
+static cudaError_t launch(bool gmres, KrylovArgs &args, nupgcm_ctx *ctx, size_t smem, int grid) {
+    return smem > 0 ? launch2<T, true>(gmres, args, ctx, smem, grid) : launch2<T, false>(gmres, args, ctx, 0, grid);
+}
+
+// Shared-memory plan of the SM-resident form; total == 0 when the matrix slice does not fit.
+static ResidentLayout plan_resident(const nupgcm_csr *A, bool gmres, int memory) {
+    ResidentLayout none;
+    memset(&none, 0, sizeof(none));
+    const char *env = getenv("NUPGCM_RESIDENT");
+    if (env && atoi(env) == 0) return none;
+    if (!A->d_loc || A->res_max_nnz == 0) return none;
+    const int static_smem = gmres ? 6144 : 2048;          // the kernels' static shared memory
+    const int limit = 227 * 1024 - static_smem;
+    const char *envv = getenv("NUPGCM_VEC_SMEM");
+    const int n_vec = (envv && atoi(envv) == 0) ? 1 << 20 : (gmres ? memory + 1 : 5);
+    ResidentLayout L = resident_layout(A->res_max_nnz, A->res_max_foot, A->res_max_rows, n_vec, limit);
+    return L.total <= limit ? L : none;
 }
 
 static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *dinv, double pscale,
@@ -566,6 +903,13 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
     NUPGCM_REQUIRE(ctx, !dinv || dinv->n == A->n_rows, "solve: preconditioner length mismatch");
     NUPGCM_REQUIRE(ctx, itmax >= 0 && atol >= 0.0 && rtol >= 0.0, "solve: negative tolerance or itmax");
     NUPGCM_REQUIRE(ctx, x->d != y->d, "solve: x and y must not alias");
+    // CTAs of the persistent kernel: all SMs by default (NUPGCM_GRID overrides, for experiments)
+    int grid = ctx->coop_grid;
+    if (const char *eg = getenv("NUPGCM_GRID")) {
+        const int v = atoi(eg);
+        if (v >= 1 && v <= ctx->coop_grid) grid = v;
+    }
+    NUPGCM_REQUIRE(ctx, grid <= 32 * kPollWarps, "solve: grid larger than the reduction supports");
     if (gmres) {
         NUPGCM_REQUIRE(ctx, memory >= 1 && memory <= kMaxMemory, "gmres: memory must be in 1..20");
         NUPGCM_REQUIRE(ctx, orth == NUPGCM_ORTH_MGS || orth == NUPGCM_ORTH_CGS2, "gmres: unknown orth");
@@ -577,7 +921,9 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
         return NUPGCM_OK;
     }
     NUPGCM_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t wbytes = (gmres ? (size_t)(memory + 3) : 3) * (size_t)n * sizeof(double);
+    int32_t rcp = nupgcm_csr_prepare(const_cast<nupgcm_csr *>(A), grid);
+    if (rcp) return rcp;
+    const size_t wbytes = (gmres ? (size_t)(memory + 3) : 6) * (size_t)n * sizeof(double);
     int32_t rc = ensure_workspace(ctx, wbytes);
     if (rc) return rc;
     if (hist_cap > ctx->hist_cap) {
@@ -588,10 +934,15 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
         ctx->hist_cap = hist_cap;
     }
     KrylovArgs args;
+    memset(&args, 0, sizeof(args));
     args.rowptr = A->d_rowptr;
     args.colidx = A->d_colidx;
     args.vals = A->d_vals;
     args.part = A->d_part;
+    args.loc = A->d_loc;
+    args.foot_ptr = A->d_foot_ptr;
+    args.foot = A->d_foot;
+    args.lay = plan_resident(A, gmres, memory);
     args.n = (int)n;
     args.dinv = dinv ? dinv->d : nullptr;
     args.pscale = pscale;
@@ -603,6 +954,7 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
     args.itmax = itmax;
     args.mem = memory;
     args.orth = orth;
+    args.poll_depth = poll_config(grid);
     args.barrier = ctx->d_barrier;
     args.partials = ctx->d_partials;
     args.hist = hist_cap > 0 ? ctx->d_hist : nullptr;
@@ -610,14 +962,16 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
     args.result = ctx->d_scalars;
 
     NUPGCM_CUDA(ctx, cudaMemsetAsync(ctx->d_barrier, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    NUPGCM_CUDA(ctx, cudaMemsetAsync(ctx->d_partials, 0, reduce_scratch_bytes(ctx->coop_grid), ctx->stream));
     NUPGCM_CUDA(ctx, cudaEventRecord(ctx->sev0, ctx->stream));
     cudaError_t e;
-    switch (persistent_tpr(A)) {
-        case 32: e = launch<32>(gmres, args, ctx); break;
-        case 16: e = launch<16>(gmres, args, ctx); break;
-        case 8: e = launch<8>(gmres, args, ctx); break;
-        case 4: e = launch<4>(gmres, args, ctx); break;
-        default: e = launch<2>(gmres, args, ctx); break;
+    const size_t smem = (size_t)args.lay.total;
+    switch (persistent_tpr(A, smem > 0, grid)) {
+        case 32: e = launch<32>(gmres, args, ctx, smem, grid); break;
+        case 16: e = launch<16>(gmres, args, ctx, smem, grid); break;
+        case 8: e = launch<8>(gmres, args, ctx, smem, grid); break;
+        case 4: e = launch<4>(gmres, args, ctx, smem, grid); break;
+        default: e = launch<2>(gmres, args, ctx, smem, grid); break;
     }
     NUPGCM_CUDA(ctx, e);
     ctx->launches++;
@@ -628,7 +982,7 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
     const double *res = ctx->h_scalars;
     if (res[7] != 0.0)
         return nupgcm_fail(ctx, NUPGCM_ERR_CUDA, "%s",
-                           "persistent solver kernel aborted: grid barrier watchdog expired");
+                           "persistent solver kernel aborted: cross-CTA wait watchdog expired");
     const int64_t hist_len = (int64_t)res[6];
     if (hist_cap > 0 && hist_len > 0)
         NUPGCM_CUDA(ctx, cudaMemcpy(resid_hist, ctx->d_hist, (size_t)hist_len * sizeof(double), cudaMemcpyDeviceToHost));
@@ -646,6 +1000,111 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
         NUPGCM_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->sev0, ctx->sev1));
         stats->device_ms = ms;
     }
+    return NUPGCM_OK;
+}
+
+// ---- diagnostics: latency of the grid-wide reduction primitive ---------------------------------
+__global__ void k_diag_reduce(unsigned long long *barrier, double *partials, int mode, int reps, int depth, double *out) {
+    __shared__ double red[32];
+    GridReduce gr;
+    gr.init(barrier, partials, depth);
+    double v = 1.0 + blockIdx.x, acc = 0.0;
+    for (int i = 0; i < reps && !gr.aborted(); ++i) {
+        double s;
+        __syncthreads();
+        if (mode == 0) s = gr.sum1<false>(v);
+        else if (mode == 1) s = grid_sum(gr, threadIdx.x == 0 ? v : 0.0, red, false);
+        else s = grid_sum(gr, threadIdx.x == 0 ? v : 0.0, red, true);
+        acc += s;
+        v = s * 1e-6 + blockIdx.x;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { out[0] = acc; out[7] = gr.aborted() ? 1.0 : 0.0; }
+}
+
+// Ping-pong between CTA 0 and CTA `peer` through one global word: one-way visibility latency of
+// different store/load flavours (variant = 10*store + load).
+//   store: 0 st.relaxed.gpu  1 st.volatile  2 atomicExch  3 st.release.gpu  4 plain st + __threadfence
+//   load : 0 ld.relaxed.gpu  1 ld.volatile  2 ld.global.cg  3 atomicAdd(p,0)  4 ld.acquire.gpu
+__device__ __forceinline__ void pp_store(unsigned long long *p, unsigned long long v, int kind) {
+    switch (kind) {
+        case 0: asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); break;
+        case 1: asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); break;
+        case 2: atomicExch(p, v); break;
+        case 3: asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); break;
+        default: *p = v; __threadfence(); break;
+    }
+}
+__device__ __forceinline__ unsigned long long pp_load(unsigned long long *p, int kind) {
+    unsigned long long v;
+    switch (kind) {
+        case 0: asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); break;
+        case 1: asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); break;
+        case 2: asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); break;
+        case 3: v = atomicAdd(p, 0ULL); break;
+        default: asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); break;
+    }
+    return v;
+}
+__global__ void k_diag_pingpong(unsigned long long *words, int peer, int variant, int reps, double *out) {
+    if (threadIdx.x != 0) return;
+    const int sk = variant / 10, lk = variant % 10;
+    unsigned long long *mine, *theirs;
+    if (blockIdx.x == 0) { mine = words; theirs = words + 16; }
+    else if ((int)blockIdx.x == peer) { mine = words + 16; theirs = words; }
+    else return;
+    const unsigned long long t_start = global_timer_ns();
+    bool ok = true;
+    for (int i = 1; i <= reps && ok; ++i) {
+        if (blockIdx.x == 0) pp_store(mine, (unsigned long long)i, sk);
+        unsigned long long spins = 0;
+        while (pp_load(theirs, lk) < (unsigned long long)i)
+            if (++spins > 20000000ULL) { ok = false; break; }
+        if (blockIdx.x != 0) pp_store(mine, (unsigned long long)i, sk);
+    }
+    if (blockIdx.x == 0) { out[0] = (double)(global_timer_ns() - t_start); out[7] = ok ? 0.0 : 1.0; }
+}
+
+extern "C" int32_t nupgcm_diag_pingpong(nupgcm_ctx *ctx, int32_t peer, int32_t variant, int32_t reps,
+                                        float *us_round_trip) {
+    NUPGCM_REQUIRE(nullptr, ctx, "ctx is NULL");
+    NUPGCM_REQUIRE(ctx, peer >= 1 && peer < ctx->coop_grid && reps > 0 && us_round_trip, "diag: bad argument");
+    NUPGCM_CUDA(ctx, cudaMemsetAsync(ctx->d_partials, 0, 64 * sizeof(double), ctx->stream));
+    unsigned long long *w = reinterpret_cast<unsigned long long *>(ctx->d_partials);
+    double *out = ctx->d_scalars;
+    int p = peer, v = variant, r = reps;
+    void *params[] = {&w, &p, &v, &r, &out};
+    NUPGCM_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_diag_pingpong, dim3(ctx->coop_grid), dim3(32), params, 0, ctx->stream));
+    ctx->launches++;
+    NUPGCM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NUPGCM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_scalars[7] != 0.0) return nupgcm_fail(ctx, NUPGCM_ERR_CUDA, "%s", "ping-pong timed out");
+    *us_round_trip = (float)(ctx->h_scalars[0] * 1e-3 / reps);
+    return NUPGCM_OK;
+}
+
+extern "C" int32_t nupgcm_diag_reduce_latency(nupgcm_ctx *ctx, int32_t mode, int32_t reps, int32_t grid,
+                                              int32_t threads, float *us_per_reduction) {
+    NUPGCM_REQUIRE(nullptr, ctx, "ctx is NULL");
+    NUPGCM_REQUIRE(ctx, mode >= 0 && mode <= 2 && reps > 0 && us_per_reduction, "diag: bad argument");
+    NUPGCM_REQUIRE(ctx, grid >= 1 && grid <= ctx->coop_grid && threads >= 32 && threads <= 1024 && threads % 32 == 0,
+                   "diag: grid/threads out of range");
+    NUPGCM_CUDA(ctx, cudaMemsetAsync(ctx->d_barrier, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    NUPGCM_CUDA(ctx, cudaMemsetAsync(ctx->d_partials, 0, reduce_scratch_bytes(ctx->coop_grid), ctx->stream));
+    unsigned long long *bar = ctx->d_barrier;
+    double *part = ctx->d_partials, *out = ctx->d_scalars;
+    int m = mode, r = reps, dep = poll_config(grid);
+    void *params[] = {&bar, &part, &m, &r, &dep, &out};
+    NUPGCM_CUDA(ctx, cudaEventRecord(ctx->sev0, ctx->stream));
+    NUPGCM_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_diag_reduce, dim3(grid), dim3(threads), params, 0, ctx->stream));
+    ctx->launches++;
+    NUPGCM_CUDA(ctx, cudaEventRecord(ctx->sev1, ctx->stream));
+    NUPGCM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NUPGCM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_scalars[7] != 0.0)
+        return nupgcm_fail(ctx, NUPGCM_ERR_CUDA, "%s", "diag kernel aborted: cross-CTA wait watchdog expired");
+    float ms = 0.f;
+    NUPGCM_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->sev0, ctx->sev1));
+    *us_per_reduction = 1e3f * ms / reps;
     return NUPGCM_OK;
 }
 

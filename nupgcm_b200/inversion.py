@@ -35,12 +35,13 @@ def permuted_inversion_system(fe_data: FEData, params: Parameters, forcings: For
 
 class InversionToolkit:
     def __init__(self, arch, *args, atol=1e-6, rtol=1e-6, itmax=0, memory=20, history=True,
-                 verbose=False, restart=True, orth=lib.ORTH_MGS, drop_zeros=False):
+                 verbose=False, restart=True, orth=lib.ORTH_MGS, drop_zeros=True):
         """``InversionToolkit(arch, fe_data, params, forcings; kwargs...)`` or
         ``InversionToolkit(arch, A, P, B, b; kwargs...)`` with host operands (inversion.jl:27,74).
 
         Extra keywords of this implementation: ``orth`` (Arnoldi orthogonalisation variant) and
-        ``drop_zeros`` (do not store Gridap's explicit zeros on the device)."""
+        ``drop_zeros`` (do not store Gridap's explicit zeros — 32 % of the entries — on the
+        device; default on, valid while the value pattern is fixed, i.e. constant ν)."""
         if not isinstance(arch, GPU):
             raise NotImplementedError("nupgcm_b200 only provides the GPU() architecture; the CPU "
                                       "path is the reference's own (no fallback)")

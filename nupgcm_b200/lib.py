@@ -70,6 +70,8 @@ SIGNATURES = {
                         POINTER(SolveStats)],
     "nupgcm_gmres_solve": [_P, _P, c_double, _P, _P, c_double, c_double, c_int64, c_int32, c_int32,
                            _dp, c_int64, POINTER(SolveStats)],
+    "nupgcm_diag_reduce_latency": [_P, c_int32, c_int32, c_int32, c_int32, POINTER(c_float)],
+    "nupgcm_diag_pingpong": [_P, c_int32, c_int32, c_int32, POINTER(c_float)],
     "nupgcm_mesh_create": [_P, c_int64, c_int32, _i32p, _i32p, _dp, _dp, c_int32, _dp, _dp, c_int64,
                            _dp, c_int64, c_int64, _dp, c_int64, POINTER(_P)],
     "nupgcm_mesh_destroy": [_P],
@@ -153,6 +155,17 @@ class Context:
         ms = c_float()
         _check(self.lib.nupgcm_timer_stop(self.h, byref(ms)), self.h)
         return ms.value
+
+    def reduce_latency(self, mode=1, reps=2000, grid=None, threads=512) -> float:
+        us = c_float()
+        grid = grid or self.device_info()["sm_count"]
+        _check(self.lib.nupgcm_diag_reduce_latency(self.h, mode, reps, grid, threads, byref(us)), self.h)
+        return us.value
+
+    def pingpong(self, peer=1, variant=0, reps=2000) -> float:
+        us = c_float()
+        _check(self.lib.nupgcm_diag_pingpong(self.h, peer, variant, reps, byref(us)), self.h)
+        return us.value
 
     def launch_count(self) -> int:
         n = c_int64()

@@ -116,10 +116,12 @@ def test_gmres_parity_3d_inversion(ctx):
         st, hist = lib.gmres_solve(ctx.csr(A, drop_zeros=drop), ctx.vector(y), x, pscale=ops["pscale"],
                                    atol=1e-6, rtol=1e-6, memory=20, history=1 << 16)
         assert st.solved == so.solved
-        assert abs(st.niter - so.niter) <= 1, (st.niter, so.niter)
-        assert rel(x.download(), xo) < 1e-5
-        n = min(len(hist), len(so.residuals))
-        assert np.allclose(hist[:n:50], np.array(so.residuals)[:n:50], rtol=1e-4)
+        assert abs(st.niter - so.niter) <= GMRES_LONG_RUN_SPREAD * so.niter, (st.niter, so.niter)
+        got = x.download()
+        assert rel(got, xo) < 1e-4
+        assert np.allclose(hist[:300], np.array(so.residuals)[:300], rtol=1e-6)
+        # the stopping measure is ‖M r‖ with M = I/h³: check it directly on the answer
+        assert ops["pscale"] * np.linalg.norm(y - A @ got) <= 1.01 * (1e-6 + 1e-6 * so.residuals[0])
 
 
 def test_gmres_tight_matches_direct(ctx):
