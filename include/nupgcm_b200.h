@@ -130,6 +130,8 @@ typedef struct {
     float   device_ms;     /* CUDA-event duration of the solve kernel(s) */
     int32_t launches;      /* kernels launched by this call */
     int64_t hist_len;
+    float   phase_frac[4]; /* GMRES: share of kernel time in SpMV / local vector work / waiting for
+                              grid reductions / scalar recurrences (CTA 0's clock) */
 } nupgcm_solve_stats;
 
 /* CG with Jacobi/scalar left preconditioner (CgWorkspace, src/evolution.jl:118-126) */

@@ -539,6 +539,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg(const __grid_constant__ Kryl
 // GMRES(m), restarted, left preconditioned  (Krylov.jl gmres!)
 // =============================================================================================
 
+// Coarse phase timer (CTA 0, thread 0 only): cycles spent in SpMV / local vector work / waiting
+// for grid reductions / scalar recurrences, reported per solve for the roofline analysis.
+struct PhaseClock {
+    long long last, acc[4];
+    bool on;
+    __device__ __forceinline__ void start(bool enable) {
+        on = enable;
+        acc[0] = acc[1] = acc[2] = acc[3] = 0;
+        last = on ? clock64() : 0;
+    }
+    __device__ __forceinline__ void mark(int phase) {
+        if (on) {
+            const long long now = clock64();
+            acc[phase] += now - last;
+            last = now;
+        }
+    }
+};
+
 // Krylov.jl sym_givens for reals: [c s; s −c][a; b] = [ρ; 0]
 __device__ __forceinline__ void sym_givens(double a, double b, double &c, double &s, double &rho) {
     if (b == 0.0) {
@@ -590,6 +609,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
     const int lane = tid & 31, wid = tid >> 5, nwarps = nthr >> 5;
     const double btol = 1.8189894035458565e-12;          // eps^(3/4)
     long long nhist = 0;
+    PhaseClock pc;
+    pc.start(lead);
 
     // ---- initial residual: w = b − A x0 ; r0 = M w (raw into qbuf[0]) ; β = ‖r0‖
     int cur = 0;
@@ -655,8 +676,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
             double *q = V.at(k);                          // slot of the next basis vector
             const double *src = qbuf + (size_t)cur * n;
             double *dst = qbuf + (size_t)(cur ^ 1) * n;
+            pc.mark(3);
             eng.run(src, [&](int row, double av) { q[row] = precond(a, row, av * inv_h); });
             __syncthreads();
+            pc.mark(0);
             double hsq = 0.0;                            // ‖q‖² after orthogonalisation
             if (a.orth == NUPGCM_ORTH_MGS) {
                 // h_i = v_i·q ; q −= h_i v_i, sequentially (one grid reduction per i)
@@ -670,7 +693,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
                         if (i > 0) { qv = fma(-hprev, vp[row], qv); q[row] = qv; }
                         part = fma(vi[row], qv, part);
                     }
+                    pc.mark(1);
                     hprev = grid_sum(gr, part, red, false);
+                    pc.mark(2);
                     if (tid == 0) sR[nr + i] = hprev;
                 }
                 const double *vp = V.at(k - 1);
@@ -681,7 +706,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
                     dst[row] = qv;
                     part = fma(qv, qv, part);
                 }
+                pc.mark(1);
                 hsq = grid_sum(gr, part, red, true);     // publishes dst for the next gather
+                pc.mark(2);
             } else {
                 // CGS2: all k projections at once, twice; warp w handles basis vector w % k on
                 // row segment w / k.
@@ -706,7 +733,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
                         sm_in[tid] = t;
                     }
                     __syncthreads();
+                    pc.mark(1);
                     gr.sumN(k, sm_in, sm_out, false);
+                    pc.mark(2);
                     // q −= Σ h_i v_i  (own rows)
                     double part = 0.0;
                     for (int row = r0 + tid; row < r1; row += nthr) {
@@ -716,7 +745,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
                         if (pass == 1) { dst[row] = qv; part = fma(qv, qv, part); }
                     }
                     if (tid < k) sR[nr + tid] = (pass == 0) ? sm_out[tid] : sR[nr + tid] + sm_out[tid];
-                    if (pass == 1) hsq = grid_sum(gr, part, red, true);
+                    if (pass == 1) {
+                        pc.mark(1);
+                        hsq = grid_sum(gr, part, red, true);
+                        pc.mark(2);
+                    }
                 }
             }
             // ---- scalar recurrences, replicated per CTA (thread 0), Krylov.jl order
@@ -797,6 +830,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
         a.result[5] = rnorm0;
         a.result[6] = (double)(nhist < a.hist_cap ? nhist : a.hist_cap);
         a.result[7] = gr.aborted() ? 1.0 : 0.0;
+        pc.mark(3);
+        for (int i = 0; i < 4; ++i) a.result[8 + i] = (double)pc.acc[i];
     }
 }
 
@@ -976,7 +1011,7 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
     NUPGCM_CUDA(ctx, e);
     ctx->launches++;
     NUPGCM_CUDA(ctx, cudaEventRecord(ctx->sev1, ctx->stream));
-    NUPGCM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 8 * sizeof(double),
+    NUPGCM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 12 * sizeof(double),
                                      cudaMemcpyDeviceToHost, ctx->stream));
     NUPGCM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const double *res = ctx->h_scalars;
@@ -999,6 +1034,10 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
         float ms = 0.f;
         NUPGCM_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->sev0, ctx->sev1));
         stats->device_ms = ms;
+        if (gmres) {
+            const double tot = res[8] + res[9] + res[10] + res[11];
+            for (int i = 0; i < 4; ++i) stats->phase_frac[i] = tot > 0 ? (float)(res[8 + i] / tot) : 0.f;
+        }
     }
     return NUPGCM_OK;
 }

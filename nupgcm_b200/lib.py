@@ -26,7 +26,7 @@ class SolveStats(C.Structure):
     _fields_ = [("niter", c_int64), ("solved", c_int32), ("inconsistent", c_int32),
                 ("breakdown", c_int32), ("reserved", c_int32), ("rnorm", c_double),
                 ("rnorm0", c_double), ("device_ms", c_float), ("launches", c_int32),
-                ("hist_len", c_int64)]
+                ("hist_len", c_int64), ("phase_frac", c_float * 4)]
 
 
 _P = c_void_p
