@@ -80,7 +80,8 @@ def cg_bytes(n, nnz, niter):
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons during the timed region."""
+    """nvidia-smi clocks and throttle reasons during the timed region (one nvidia-smi process in
+    loop mode, 50 ms period)."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -89,28 +90,38 @@ class ClockSampler:
     def __init__(self, device):
         self.device = device
         self.samples = []
-        self._stop = threading.Event()
-        self._t = threading.Thread(target=self._run, daemon=True)
+        self.proc = None
+        self._t = None
 
     def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True,
-                                     text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        for line in self.proc.stdout:
+            parts = [s.strip() for s in line.split(",")]
+            if len(parts) >= 6 and parts[0].replace(".", "").isdigit():
+                self.samples.append(parts)
 
     def __enter__(self):
-        self._t.start()
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+            time.sleep(0.15)                      # let the first sample land before timing starts
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        if self.proc is not None:
+            time.sleep(0.06)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            if self._t is not None:
+                self._t.join(timeout=5)
 
     def summary(self):
         if not self.samples:
@@ -166,7 +177,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--h", type=float, default=0.08)
-    ap.add_argument("--orth", default="mgs", choices=["mgs", "cgs2"])
+    ap.add_argument("--orth", default="cgs2", choices=["mgs", "cgs2"],
+                    help="Arnoldi orthogonalisation: cgs2 (3 grid reductions per iteration, default) or "
+                         "mgs (Krylov.jl order, k+1 reductions)")
     ap.add_argument("--keep-zeros", action="store_true", help="store Gridap's explicit zeros too")
     ap.add_argument("--cpu-sample-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -112,6 +112,13 @@ int32_t nupgcm_csr_inv_diag(const nupgcm_csr *A, nupgcm_vec *dinv);
 int32_t nupgcm_spmv(const nupgcm_csr *A, const nupgcm_vec *x, nupgcm_vec *y, double alpha,
                     double beta);
 
+/* Reverse Cuthill-McKee ordering of the symmetrised pattern of a square CSR matrix (host-only;
+ * needs no context).  perm_out[i] = row placed at position i.  The persistent solvers apply this
+ * ordering internally (the caller never sees it); it is exported for hosts that want the same
+ * ordering the reference gets from CuthillMcKee.symrcm (src/dofs.jl:98-100). */
+int32_t nupgcm_rcm_order(int64_t n, const int64_t *rowptr, const int64_t *colidx,
+                         int32_t index_base, int64_t *perm_out);
+
 /* ---- Krylov solvers (replace Krylov.krylov_solve! at src/iterative_solvers.jl:58) ---------
  * x is in/out: its content on entry is the warm start (the reference aliases x to workspace.x,
  * src/iterative_solvers.jl:26-29).  itmax == 0 means 2n (Krylov.jl default).  The stopping
@@ -132,6 +139,8 @@ typedef struct {
     int64_t hist_len;
     float   phase_frac[4]; /* GMRES: share of kernel time in SpMV / local vector work / waiting for
                               grid reductions / scalar recurrences (CTA 0's clock) */
+    float   sm_mhz;        /* GMRES: SM clock the kernel actually ran at (clock64 / globaltimer) */
+    float   reserved2;
 } nupgcm_solve_stats;
 
 /* CG with Jacobi/scalar left preconditioner (CgWorkspace, src/evolution.jl:118-126) */

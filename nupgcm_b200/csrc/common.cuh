@@ -68,6 +68,13 @@ struct nupgcm_csr {
     int res_max_nnz, res_max_foot, res_max_rows;   // maxima over CTAs (0 when unavailable)
     int prepared_grid;             // grid the partition / resident tables were built for
     int32_t *h_rowptr, *h_col;     // host copies of the structure
+    // internally reordered copy used by the persistent solvers (RCM of the whole pattern)
+    int32_t *d_perm;               // [n] internal row i  <->  caller row perm[i]
+    int32_t *d_prow, *d_pcol;      // reordered CSR structure (columns are internal ids)
+    int32_t *d_psrc;               // [nnz] position of each reordered entry in d_vals
+    double *d_pvals;               // [nnz] reordered values, refreshed when vals_version moves
+    int32_t *h_prow, *h_pcol;
+    long long vals_version, pvals_version;
 };
 
 int32_t nupgcm_csr_prepare(nupgcm_csr *A, int grid);

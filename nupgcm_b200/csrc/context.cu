@@ -43,7 +43,7 @@ extern "C" int32_t nupgcm_create(int32_t device, nupgcm_ctx **out) {
     NUPGCM_CUDA(ctx, cudaEventCreate(&ctx->sev1));
     NUPGCM_CUDA(ctx, cudaMalloc(&ctx->d_barrier, 4 * sizeof(unsigned long long)));
     // reduction scratch of the persistent solvers: per-CTA slots + replicated broadcast words
-    NUPGCM_CUDA(ctx, cudaMalloc(&ctx->d_partials, (size_t)kPartialSlots * 2 * 8 * ((ctx->coop_grid + 7) & ~7) * 16));
+    NUPGCM_CUDA(ctx, cudaMalloc(&ctx->d_partials, 2 * ((size_t)(8 + kPartialSlots) * ((ctx->coop_grid + 7) & ~7) + 8 * 32) * 16 + 65536));
     NUPGCM_CUDA(ctx, cudaMalloc(&ctx->d_scalars, 64 * sizeof(double)));
     NUPGCM_CUDA(ctx, cudaMallocHost(&ctx->h_scalars, 64 * sizeof(double)));
     ctx->hist_cap = 1 << 16;

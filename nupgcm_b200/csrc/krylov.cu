@@ -31,7 +31,7 @@
 static const int kThreads = 512;       // 16 warps: up to 128 registers per thread, cheap CTA barriers
 
 struct ResidentLayout {       // byte offsets into dynamic shared memory (all multiples of 16)
-    int vals, cols, xs, rp, bar, vec, total;
+    int vals, cols, xs, foot, rp, bar, vec, total;
     int vec_rows;             // row capacity of one vector slice (0: vectors stay in global memory)
 };
 
@@ -41,8 +41,9 @@ struct KrylovArgs {
     const double *vals;
     const int32_t *part;     // [grid+1] row ranges
     const uint16_t *loc;     // SM-resident tables (see SpmvEngine)
-    const int32_t *foot_ptr;
+    const int32_t *foot_ptr; // [grid][2]: start (multiple of 4) and length of each CTA's footprint
     const int32_t *foot;
+    const int32_t *perm;     // [n] internal row -> caller row (vectors cross the ABI in caller order)
     ResidentLayout lay;
     int n;
     const double *dinv;      // diagonal preconditioner or NULL
@@ -54,7 +55,8 @@ struct KrylovArgs {
     long long itmax;
     int mem;
     int orth;
-    int poll_depth;          // polls kept in flight per awaited word (GridReduce)
+    int poll_depth;          // replicas of the reduction slots (GridReduce)
+    unsigned long long *trace;   // debug: arrival/completion stamps of a window of reductions
     unsigned long long *barrier;
     double *partials;        // LLSlot [2][kPartialSlots][grid]
     double *hist;
@@ -107,147 +109,235 @@ __device__ __forceinline__ void ll_load_raw(const LLSlot *p, unsigned long long 
         asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 
+static const unsigned kTraceStart = 2000, kTraceWindow = 256, kTraceStamps = 6;   // reductions recorded by the debug trace
 static const int kPollWarps = 5;           // 5 x 32 lanes cover grids up to 160 CTAs (B200: 148 SMs)
-static const long long kPollStagger = 160; // cycles between the pipelined polls
+static const int kMaxReplicas = 8;
+static const int kMaxV = 12;       // values one polling lane keeps in flight (largest without spills)
 
-// All-to-all reduction: every CTA stores its partial into its slot and reads all slots, one slot
-// per lane (ceil(grid/32) warps per value), adding them in a fixed order.  Small grids keep
-// several polls of a slot in flight (a new value is then seen one stagger interval, not one L2
-// round trip, after it lands); at full-chip grids that would multiply the 148 x 148 reads hitting
-// the same few cache lines, so the depth drops to one.  Measured on B200 (tools/krylov_microbench):
-// 1.0 us per reduction at 2-16 CTAs, 2.5-3 us at 148.
+// ---- warp specialisation ------------------------------------------------------------------------
+// Warps 0..kMainWarps-1 ("main") run the solver; warps kMainWarps.. ("comm") do nothing but the
+// cross-CTA exchange.  The two roles never share registers at a program point, so the polling
+// code (many 16-byte loads in flight) does not spill the solver's state and vice versa — an
+// earlier single-role version spilled 0.6-2 KB per thread, and every acquire (which invalidates
+// L1) turned the spill reloads into L2 round trips.  Main and comm warps meet at two named
+// barriers (request / response); main warps synchronise among themselves on a third.
+static const int kMainWarps = 11, kCommWarps = 5;
+static const int kMainThreads = 32 * kMainWarps, kCommThreads = 32 * kCommWarps;
+static_assert(kMainThreads + kCommThreads == kThreads, "role split must cover the CTA");
+#define NUPGCM_BAR_MAIN 1
+#define NUPGCM_BAR_REQ 2
+#define NUPGCM_BAR_RSP 3
+#define NUPGCM_BAR_COMM 4
+
+__device__ __forceinline__ void named_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void main_sync() { named_sync(NUPGCM_BAR_MAIN, kMainThreads); }
+
+struct CommMailbox {
+    int count;                       // > 0: values to reduce; 0: barrier only; < 0: exit
+    int from_warps;                  // 1: the single value is the sum of wpart[0..kMainWarps)
+    int publish;                     // release/acquire: also publishes the CTA's global rows
+    int dead;                        // set by the comm warps when the watchdog fired
+    double wpart[kMainWarps];
+    double in[kPartialSlots];
+    double out[kPartialSlots];
+    double part[kPartialSlots][kPollWarps];
+};
+
+// Scratch layout (LLSlot units) of one bank of the exchange area.
+static const int kBcastCopies = 8, kBcastStride = 32;
+__host__ __device__ inline size_t exch_bank_slots(int gpad) {
+    return (size_t)(kMaxReplicas + kPartialSlots) * gpad + (size_t)kBcastCopies * kBcastStride;
+}
+
+// Wait (with watchdog) until the flagged word at p carries `gen`; returns its value.
+template <bool ACQUIRE>
+__device__ __forceinline__ double wait_flagged(const LLSlot *p, unsigned gen, unsigned long long *abort_word, bool &bad) {
+    unsigned long long a, b;
+    unsigned spins = 0;
+    unsigned long long t0 = 0;
+    for (;;) {
+        ll_load_raw<ACQUIRE>(p, a, b);
+        if ((unsigned)(a >> 32) == gen && (unsigned)(b >> 32) == gen)
+            return __longlong_as_double((long long)((a & 0xffffffffULL) | (b << 32)));
+        if ((++spins & 255u) == 0) {
+            unsigned long long fl;
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(fl) : "l"(abort_word) : "memory");
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            if (fl != 0 || now - t0 > kWaitTimeoutNs) {
+                atomicExch(abort_word, 1ULL);
+                bad = true;
+                return 0.0;
+            }
+        }
+    }
+}
+
+// One value per CTA, all-to-all: every CTA stores its partial (nrep replicas) and reads all grid
+// slots, one per comm lane; lanes are combined by an xor-shuffle tree and warps in index order —
+// a fixed summation order, identical in every CTA.  PUBLISH uses release stores / acquire loads so
+// that the global-memory rows written by the CTA before the call are visible to all CTAs after it.
+template <bool PUBLISH>
+__device__ __forceinline__ bool comm_sum1(CommMailbox *mb, LLSlot *bank_base, unsigned long long *abort_word,
+                                          unsigned long long *trow, bool tr, unsigned gen, int grid, int gpad,
+                                          int nrep) {
+    const int ct = threadIdx.x - kMainThreads, cw = ct >> 5, lane = ct & 31;
+    const int bid = blockIdx.x;
+    if (cw == 0) {
+        double val;
+        if (mb->from_warps) {
+            val = lane < kMainWarps ? mb->wpart[lane] : 0.0;
+            val = warp_sum(val);                              // fixed tree over the main warps' partials
+        } else {
+            val = mb->in[0];
+        }
+        if (lane < nrep) ll_store<PUBLISH>(bank_base + (size_t)lane * gpad + bid, val, gen);
+    }
+    if (tr) trow[2 * (size_t)grid] = global_timer_ns();            // own partial stored
+    bool bad = false;
+    const int c = cw * 32 + lane;
+    double v = 0.0;
+    if (c < grid) v = wait_flagged<PUBLISH>(bank_base + (size_t)(bid % nrep) * gpad + c, gen, abort_word, bad);
+    v = warp_sum(v);
+    if (lane == 0) mb->part[0][cw] = v;
+    if (bad) mb->dead = 1;
+    if (tr) trow[3 * (size_t)grid] = global_timer_ns();
+    named_sync(NUPGCM_BAR_COMM, kCommThreads);
+    if (tr) trow[4 * (size_t)grid] = global_timer_ns();
+    if (ct == 0) {
+        const int npw = (grid + 31) >> 5;
+        double total = 0.0;
+        for (int g = 0; g < npw; ++g) total += mb->part[0][g];
+        mb->out[0] = total;
+    }
+    return bad;
+}
+
+// `count` values per CTA (CGS2 projections), gather-broadcast: CTA j is the reducer of value j —
+// it waits for the grid's partials of that value, adds them in the same fixed order as comm_sum1
+// and stores the total into kBcastCopies replicated result blocks; every CTA then waits for the
+// `count` totals of one replica.  An all-to-all of count values would issue grid² x count sector
+// reads per poll round (438 k at 148 CTAs x 20 values) against a few hundred cache lines and was
+// measured at 6-12 us; this form issues (grid + copies) x count.
+__device__ __forceinline__ bool comm_sumN(CommMailbox *mb, LLSlot *bank_base, unsigned long long *abort_word,
+                                          unsigned long long *trow, bool tr, unsigned gen, int grid, int gpad,
+                                          int count) {
+    const int ct = threadIdx.x - kMainThreads, cw = ct >> 5, lane = ct & 31;
+    const int bid = blockIdx.x;
+    LLSlot *vals = bank_base + (size_t)kMaxReplicas * gpad;                 // [kPartialSlots][gpad]
+    LLSlot *res = vals + (size_t)kPartialSlots * gpad;                      // [kBcastCopies][kBcastStride]
+    if (ct < count) ll_store<false>(vals + (size_t)ct * gpad + bid, mb->in[ct], gen);
+    if (tr) trow[2 * (size_t)grid] = global_timer_ns();
+    bool bad = false;
+    if (bid < count) {                                                      // reducer of value `bid`
+        const int c = cw * 32 + lane;
+        double v = 0.0;
+        if (c < grid) v = wait_flagged<false>(vals + (size_t)bid * gpad + c, gen, abort_word, bad);
+        v = warp_sum(v);
+        if (lane == 0) mb->part[0][cw] = v;
+        named_sync(NUPGCM_BAR_COMM, kCommThreads);
+        if (ct < kBcastCopies) {
+            const int npw = (grid + 31) >> 5;
+            double total = 0.0;
+            for (int g = 0; g < npw; ++g) total += mb->part[0][g];
+            ll_store<false>(res + (size_t)ct * kBcastStride + bid, total, gen);
+        }
+    }
+    if (tr) trow[3 * (size_t)grid] = global_timer_ns();
+    if (ct < count)
+        mb->out[ct] = wait_flagged<false>(res + (size_t)(bid % kBcastCopies) * kBcastStride + ct, gen, abort_word, bad);
+    if (bad) mb->dead = 1;
+    if (tr) trow[4 * (size_t)grid] = global_timer_ns();
+    return bad;
+}
+
+// Service loop of the comm warps: one request per grid-wide reduction, until the main warps post
+// the exit request.
+__device__ __forceinline__ void comm_warp_loop(CommMailbox *mb, const KrylovArgs &a, int nrep) {
+    LLSlot *slots = reinterpret_cast<LLSlot *>(a.partials);
+    unsigned long long *abort_word = a.barrier + 1;
+    const int grid = gridDim.x, gpad = (grid + 7) & ~7;
+    const int ct = threadIdx.x - kMainThreads;
+    unsigned gen = 0;
+    bool dead = false;
+    for (;;) {
+        named_sync(NUPGCM_BAR_REQ, kThreads);
+        const int count = mb->count;
+        if (count < 0) break;
+        gen += 1;
+        if (!dead) {
+            const bool tr = a.trace && gen >= kTraceStart && gen < kTraceStart + kTraceWindow && ct == 0;
+            unsigned long long *trow = a.trace + ((size_t)(gen - kTraceStart) * kTraceStamps) * grid + blockIdx.x;
+            if (tr) trow[1 * (size_t)grid] = global_timer_ns();        // request seen by the comm warps
+            LLSlot *bank_base = slots + (size_t)(gen & 1) * exch_bank_slots(gpad);
+            bool bad;
+            if (count > 1) bad = comm_sumN(mb, bank_base, abort_word, trow, tr, gen, grid, gpad, count);
+            else if (mb->publish) bad = comm_sum1<true>(mb, bank_base, abort_word, trow, tr, gen, grid, gpad, nrep);
+            else bad = comm_sum1<false>(mb, bank_base, abort_word, trow, tr, gen, grid, gpad, nrep);
+            dead = __any_sync(0xffffffffu, bad) || mb->dead != 0;
+        }
+        named_arrive(NUPGCM_BAR_RSP, kThreads);
+    }
+}
+
+// Main-warp side of the exchange.
 struct GridReduce {
-    LLSlot *slots;                   // [2][kPartialSlots][replicas][grid_pad]
-    unsigned long long *abort_word;  // raised by the watchdog
+    CommMailbox *mb;
+    unsigned long long *trace;
     unsigned gen;
-    int grid, bid, depth, nrep, gpad;
     bool dead;
-
-    // poll_cfg = depth + 16 * replicas.  Each CTA stores its partial into `replicas` copies of the
-    // slot array and CTA b reads copy b % replicas, which divides the number of readers per cache
-    // line (the contended resource at full-chip grids) by `replicas`.
-    __device__ __forceinline__ void init(unsigned long long *barrier_words, double *p, int poll_cfg) {
-        slots = reinterpret_cast<LLSlot *>(p);
-        abort_word = barrier_words + 1;
+    __device__ __forceinline__ void init(CommMailbox *m, unsigned long long *tr = nullptr) {
+        mb = m;
+        trace = tr;
         gen = 0;
-        grid = gridDim.x;
-        gpad = (grid + 7) & ~7;                   // replicas start on 128-byte lines
-        bid = blockIdx.x;
-        depth = poll_cfg & 15;
-        nrep = poll_cfg >> 4;
-        if (nrep < 1) nrep = 1;
         dead = false;
     }
     __device__ __forceinline__ bool aborted() const { return dead; }
-    __device__ __forceinline__ LLSlot *slot(int bank, int j, int replica) {
-        return slots + ((size_t)((bank * kPartialSlots + j) * nrep + replica)) * gpad;
-    }
-
-    // Wait until the word at p carries `flag` and return its value, with DEPTH polls in flight.
-    template <bool ACQUIRE, int DEPTH>
-    __device__ __noinline__ double wait_word(const LLSlot *p, unsigned flag, bool &bad) {
-        unsigned long long a[DEPTH], b[DEPTH];
-#pragma unroll
-        for (int d = 0; d < DEPTH; ++d) {
-            ll_load_raw<ACQUIRE>(p, a[d], b[d]);
-            if (d + 1 < DEPTH) {
-                const long long c0 = clock64();
-                while (clock64() - c0 < kPollStagger) {}
-            }
-        }
-        unsigned spins = 0;
-        unsigned long long t0 = 0;
-        for (;;) {
-#pragma unroll
-            for (int d = 0; d < DEPTH; ++d) {
-                if ((unsigned)(a[d] >> 32) == flag && (unsigned)(b[d] >> 32) == flag)
-                    return __longlong_as_double((long long)((a[d] & 0xffffffffULL) | (b[d] << 32)));
-                ll_load_raw<ACQUIRE>(p, a[d], b[d]);
-            }
-            if ((++spins & 255u) == 0) {
-                unsigned long long fl;
-                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(fl) : "l"(abort_word) : "memory");
-                const unsigned long long now = global_timer_ns();
-                if (t0 == 0) t0 = now;
-                if (fl != 0 || now - t0 > kWaitTimeoutNs) {
-                    atomicExch(abort_word, 1ULL);
-                    bad = true;
-                    return 0.0;
-                }
-            }
-        }
-    }
-    template <bool ACQUIRE>
-    __device__ __forceinline__ double wait_any(const LLSlot *p, unsigned flag, bool &bad) {
-        if (depth >= 4) return wait_word<ACQUIRE, 4>(p, flag, bad);
-        if (depth == 2) return wait_word<ACQUIRE, 2>(p, flag, bad);
-        return wait_word<ACQUIRE, 1>(p, flag, bad);
-    }
-
-    // Sum of `count` (<= kPartialSlots) values per CTA.  Value j of this CTA must be in sm_in[j]
-    // (visible to all threads).  Results land in sm_out[j], valid for every thread on return.
-    // PUBLISH additionally makes the global-memory rows this CTA wrote before the call visible to
-    // every CTA after the call (release slot stores, acquire polls).
-    template <bool PUBLISH>
-    __device__ __forceinline__ void reduce(int count, const double *sm_in, double *sm_out) {
-        __shared__ double s_partn[kPartialSlots * kPollWarps];
+    __device__ __forceinline__ void round_trip() {
         gen += 1;
-        const int bank = gen & 1;
-        if (dead) return;
-        const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
-        const int npw = (grid + 31) >> 5;          // poll warps per value
-        bool bad = false;
-        for (int u = tid; u < count * nrep; u += blockDim.x)
-            ll_store<PUBLISH>(slot(bank, u / nrep, u % nrep) + bid, sm_in[u / nrep], gen);
-        const int myrep = bid % nrep;
-        for (int u = wid; u < count * npw; u += nw) {
-            const int j = u / npw, w = u % npw, li = w * 32 + lane;
-            double t = li < grid ? wait_any<PUBLISH>(slot(bank, j, myrep) + li, gen, bad) : 0.0;
-            t = warp_sum(t);
-            if (lane == 0) s_partn[j * kPollWarps + w] = t;
-        }
-        dead = __syncthreads_or(bad ? 1 : 0) != 0;
-        if (tid < count) {
-            double total = 0.0;
-            for (int w = 0; w < npw; ++w) total += s_partn[tid * kPollWarps + w];
-            sm_out[tid] = total;
-        }
-        __syncthreads();
+        const bool tr = trace && gen >= kTraceStart && gen < kTraceStart + kTraceWindow && threadIdx.x == 0;
+        unsigned long long *trow = trace + ((size_t)(gen - kTraceStart) * kTraceStamps) * gridDim.x + blockIdx.x;
+        if (tr) trow[0] = global_timer_ns();                          // main warps post the request
+        named_arrive(NUPGCM_BAR_REQ, kThreads);
+        named_sync(NUPGCM_BAR_RSP, kThreads);
+        if (tr) trow[5 * (size_t)gridDim.x] = global_timer_ns();      // main warps resume
+        dead = mb->dead != 0;
     }
-
-    // Sum of one value per CTA.  `v` must be valid in thread 0.  Result valid in every thread.
+    // Sum over the whole grid of a per-thread value (main warps only).  Every main thread gets
+    // the result.  The block-level part is one shuffle tree per warp; the comm warps add the
+    // kMainWarps warp partials.
     template <bool PUBLISH>
-    __device__ __forceinline__ double sum1(double v) {
-        __shared__ double s_in[1], s_out[1];
-        if (threadIdx.x == 0) s_in[0] = v;
-        if (nrep > 1) __syncthreads();         // threads 0..nrep-1 store the replicas
-        reduce<PUBLISH>(1, s_in, s_out);
-        return s_out[0];
+    __device__ __forceinline__ double sum_threads(double v) {
+        v = warp_sum(v);
+        if ((threadIdx.x & 31) == 0) mb->wpart[threadIdx.x >> 5] = v;
+        if (threadIdx.x == 0) { mb->count = 1; mb->from_warps = 1; mb->publish = PUBLISH ? 1 : 0; }
+        round_trip();
+        return mb->out[0];
     }
-
-    __device__ __forceinline__ void sumN(int count, const double *sm_in, double *sm_out, bool publish) {
-        if (publish) reduce<true>(count, sm_in, sm_out);
-        else reduce<false>(count, sm_in, sm_out);
+    // Sum of `count` values per CTA that main threads put into mb->in[0..count) beforehand
+    // (followed by main_sync()).  Results in mb->out[0..count).
+    __device__ __forceinline__ void sumN(int count) {
+        if (threadIdx.x == 0) { mb->count = count; mb->from_warps = 0; mb->publish = 0; }
+        round_trip();
     }
-
-    // Grid barrier that publishes this CTA's vector rows.
+    // Grid barrier that publishes this CTA's global-memory rows.
     __device__ __forceinline__ void barrier() {
-        __syncthreads();
-        (void)sum1<true>(0.0);
+        if (threadIdx.x == 0) { mb->count = 0; mb->from_warps = 0; mb->in[0] = 0.0; mb->publish = 1; }
+        round_trip();
+    }
+    // Tell the comm warps to leave (call once, at the end, by all main threads).
+    __device__ __forceinline__ void finish() {
+        if (threadIdx.x == 0) mb->count = -1;
+        named_arrive(NUPGCM_BAR_REQ, kThreads);
     }
 };
 
-static const int kMaxReplicas = 8;
-static size_t reduce_scratch_bytes(int grid) {
-    return (size_t)2 * kPartialSlots * kMaxReplicas * ((grid + 7) & ~7) * sizeof(LLSlot);
-}
-
-// Block-wide sum then grid-wide sum of one value.  All vector writes made by the CTA before the
-// call are covered by `publish` (block_sum synchronises the CTA before thread 0 stores its slot).
-__device__ __forceinline__ double grid_sum(GridReduce &gr, double v, double *red, bool publish) {
-    v = block_sum(v, red);
-    return publish ? gr.sum1<true>(v) : gr.sum1<false>(v);
-}
+static size_t reduce_scratch_bytes(int grid) { return 2 * exch_bank_slots((grid + 7) & ~7) * sizeof(LLSlot); }
 
 // ---- SpMV over the CTA's rows -----------------------------------------------------------------
 // Two forms, chosen at launch:
@@ -293,6 +383,7 @@ static ResidentLayout resident_layout(int max_nnz, int max_foot, int max_rows, i
     L.vals = off; off += ((max_nnz + 2 + 1) & ~1) * 8;
     L.cols = off; off += (((max_nnz + 8 + 7) & ~7) * 2 + 15) & ~15;
     L.xs = off;   off += ((max_foot + 1) & ~1) * 8;
+    L.foot = off; off += ((max_foot + 3) & ~3) * 4;
     L.rp = off;   off += ((max_rows + 1 + 4 + 3) & ~3) * 4;
     L.bar = off;  off += 16;
     L.vec = off;
@@ -324,8 +415,10 @@ struct SpmvEngine {
             const ResidentLayout &L = a.lay;
             uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.bar);
             const int k0 = a.rowptr[r0], k1 = a.rowptr[r1];
-            const int f0 = a.foot_ptr[blockIdx.x], f1 = a.foot_ptr[blockIdx.x + 1];
+            const int f0 = a.foot_ptr[2 * blockIdx.x];
+            nfoot = a.foot_ptr[2 * blockIdx.x + 1];
             const int ka = k0 & ~1, kc = k0 & ~7, ra = r0 & ~3;
+            const uint32_t bf = (uint32_t)(((nfoot + 3) & ~3) * 4);
             const uint32_t bv = (uint32_t)(((k1 - ka + 1) & ~1) * 8);
             const uint32_t bc = (uint32_t)(((k1 - kc + 7) & ~7) * 2);
             const uint32_t br = (uint32_t)(((r1 + 1 - ra + 3) & ~3) * 4);
@@ -335,7 +428,7 @@ struct SpmvEngine {
             }
             __syncthreads();
             if (threadIdx.x == 0) {
-                mbar_expect_tx(bar, bv + bc + br);
+                mbar_expect_tx(bar, bv + bc + br + bf);
                 uint32_t done = 0;                            // values in <= 32 KB pieces
                 while (done < bv) {
                     const uint32_t piece = min(bv - done, 32768u);
@@ -344,14 +437,14 @@ struct SpmvEngine {
                 }
                 if (bc) bulk_g2s(smem + L.cols, a.loc + kc, bc, bar);
                 bulk_g2s(smem + L.rp, a.rowptr + ra, br, bar);
+                if (bf) bulk_g2s(smem + L.foot, a.foot + f0, bf, bar);
             }
             mbar_wait(bar, 0);
             vs = reinterpret_cast<const double *>(smem + L.vals) - ka;
             cs = reinterpret_cast<const uint16_t *>(smem + L.cols) - kc;
             rp = reinterpret_cast<const int32_t *>(smem + L.rp) - ra;
             xs = reinterpret_cast<double *>(smem + L.xs);
-            foot = a.foot + f0;
-            nfoot = f1 - f0;
+            foot = reinterpret_cast<const int32_t *>(smem + L.foot);
         }
     }
 
@@ -359,11 +452,20 @@ struct SpmvEngine {
     __device__ __forceinline__ void run(const double *xin, F &&f) {
         const int lane = threadIdx.x & (T - 1);
         const int g = threadIdx.x / T;
-        const int G = blockDim.x / T;
+        const int G = kMainThreads / T;
         if constexpr (RES) {
-            __syncthreads();                                 // previous readers of xs are done
-            for (int i = threadIdx.x; i < nfoot; i += blockDim.x) xs[i] = ld_cg(xin + __ldg(foot + i));
-            __syncthreads();
+            main_sync();                                     // previous readers of xs are done
+            {   // stage the footprint of xin: 4 independent L2 gathers in flight per thread
+                const int nt = kMainThreads;
+                int i = threadIdx.x;
+                for (; i + 3 * nt < nfoot; i += 4 * nt) {
+                    const double x0 = ld_cg(xin + foot[i]), x1 = ld_cg(xin + foot[i + nt]);
+                    const double x2 = ld_cg(xin + foot[i + 2 * nt]), x3 = ld_cg(xin + foot[i + 3 * nt]);
+                    xs[i] = x0; xs[i + nt] = x1; xs[i + 2 * nt] = x2; xs[i + 3 * nt] = x3;
+                }
+                for (; i < nfoot; i += nt) xs[i] = ld_cg(xin + foot[i]);
+            }
+            main_sync();
             for (int base = r0; base < r1; base += G) {      // uniform trip count over the CTA
                 const int row = base + g;
                 const bool active = row < r1;
@@ -436,11 +538,17 @@ struct VecSlices {
 template <int T, bool RES>
 __global__ void __launch_bounds__(kThreads, 1) k_cg(const __grid_constant__ KrylovArgs a) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
-    __shared__ double red[32];
-    GridReduce gr;
-    gr.init(a.barrier, a.partials, a.poll_depth);
+    __shared__ CommMailbox mailbox;
+    if (threadIdx.x == 0) mailbox.dead = 0;
     const int r0 = a.part[blockIdx.x], r1 = a.part[blockIdx.x + 1];
-    SpmvEngine<T, RES> eng(a, r0, r1, dyn_smem);
+    SpmvEngine<T, RES> eng(a, r0, r1, dyn_smem);          // all warps take part in the bulk copy
+    __syncthreads();
+    if (threadIdx.x >= kMainThreads) {                     // comm warps: exchange service only
+        comm_warp_loop(&mailbox, a, a.poll_depth);
+        return;
+    }
+    GridReduce gr;
+    gr.init(&mailbox, a.trace);
     const int n = a.n;
     // CTA-local vectors: r, Ap, local copy of p, the iterate, the Jacobi diagonal
     VecSlices loc(a, dyn_smem, a.work + n, r0);       // global fallback: work[n .. 6n)
@@ -448,25 +556,30 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg(const __grid_constant__ Kryl
     double *pg = a.work;                               // p as the other CTAs gather it
     const double eps = 2.220446049250313e-16;
     const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int tid = threadIdx.x, nthr = kMainThreads;
     long long nhist = 0;
 
+    // vectors cross the ABI in caller order; internally rows follow the reordered matrix
+    double *xi = a.work + 6 * (size_t)n;               // Δx in internal order, gathered by all CTAs
     for (int row = r0 + tid; row < r1; row += nthr) {
-        xl[row] = a.x[row];                            // Δx, the warm start
-        dl[row] = a.dinv ? a.dinv[row] : a.pscale;
+        const int src = a.perm[row];
+        const double x0 = a.x[src];                    // Δx, the warm start
+        xl[row] = x0;
+        xi[row] = x0;
+        dl[row] = a.dinv ? a.dinv[src] : a.pscale;
     }
-    __syncthreads();
+    gr.barrier();
     // r = b − A Δx ; z = M r ; p = z ; γ = r·z          (own rows; z is never stored)
     double part = 0.0;
-    eng.run(a.x, [&](int row, double ax) {
-        const double rv = a.b[row] - ax;
+    eng.run(xi, [&](int row, double ax) {
+        const double rv = a.b[a.perm[row]] - ax;
         const double zv = dl[row] * rv;
         r[row] = rv;
         pl[row] = zv;
         pg[row] = zv;
         part = fma(rv, zv, part);
     });
-    double gamma = grid_sum(gr, part, red, true);      // also publishes p for the first SpMV
+    double gamma = gr.sum_threads<true>(part);      // also publishes p for the first SpMV
     double rnorm = sqrt(gamma);
     const double rnorm0 = rnorm;
     if (lead && a.hist && nhist < a.hist_cap) a.hist[nhist] = rnorm;
@@ -488,7 +601,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg(const __grid_constant__ Kryl
             Ap[row] = ap;
             part = fma(pl[row], ap, part);
         });
-        const double pAp = grid_sum(gr, part, red, false);
+        const double pAp = gr.sum_threads<false>(part);
         if (pAp <= eps * pnorm2 && fabs(pAp) <= eps * pnorm2) {
             zero_curv = true;
             continue;
@@ -502,7 +615,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg(const __grid_constant__ Kryl
             r[row] = rv;
             part = fma(rv, dl[row] * rv, part);
         }
-        const double gamma_next = grid_sum(gr, part, red, false);
+        const double gamma_next = gr.sum_threads<false>(part);
         rnorm = sqrt(gamma_next);
         if (lead && a.hist && nhist < a.hist_cap) a.hist[nhist] = rnorm;
         nhist++;
@@ -522,7 +635,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg(const __grid_constant__ Kryl
         iter++;
         tired = iter >= itmax;
     }
-    for (int row = r0 + tid; row < r1; row += nthr) a.x[row] = xl[row];
+    for (int row = r0 + tid; row < r1; row += nthr) a.x[a.perm[row]] = xl[row];
+    gr.finish();
     if (lead) {
         a.result[0] = (double)iter;
         a.result[1] = solved ? 1.0 : 0.0;
@@ -541,13 +655,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg(const __grid_constant__ Kryl
 
 // Coarse phase timer (CTA 0, thread 0 only): cycles spent in SpMV / local vector work / waiting
 // for grid reductions / scalar recurrences, reported per solve for the roofline analysis.
-struct PhaseClock {
-    long long last, acc[4];
+template <bool ENABLED>
+struct PhaseClock;
+template <>
+struct PhaseClock<false> {
+    __device__ __forceinline__ void start(bool) {}
+    __device__ __forceinline__ void mark(int) {}
+    __device__ __forceinline__ void dump(double *) const {}
+};
+template <>
+struct PhaseClock<true> {
+    long long last, acc[4], c0;
+    unsigned long long ns0;
     bool on;
+    __device__ __forceinline__ void dump(double *result) const {
+        if (!on) return;
+        for (int i = 0; i < 4; ++i) result[8 + i] = (double)acc[i];
+        result[12] = mhz();
+    }
     __device__ __forceinline__ void start(bool enable) {
         on = enable;
         acc[0] = acc[1] = acc[2] = acc[3] = 0;
-        last = on ? clock64() : 0;
+        last = c0 = on ? clock64() : 0;
+        ns0 = on ? global_timer_ns() : 0;
+    }
+    // SM clock actually seen by this kernel (cycles per nanosecond -> MHz)
+    __device__ __forceinline__ double mhz() const {
+        const unsigned long long ns = global_timer_ns() - ns0;
+        return ns ? 1e3 * (double)(clock64() - c0) / (double)ns : 0.0;
     }
     __device__ __forceinline__ void mark(int phase) {
         if (on) {
@@ -582,34 +717,43 @@ __device__ __forceinline__ void sym_givens(double a, double b, double &c, double
 }
 
 __device__ __forceinline__ double precond(const KrylovArgs &a, int row, double v) {
-    return a.dinv ? __ldg(a.dinv + row) * v : a.pscale * v;
+    return a.dinv ? __ldg(a.dinv + __ldg(a.perm + row)) * v : a.pscale * v;
 }
 
-template <int T, bool RES>
+template <int T, bool RES, bool PROF>
 __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ KrylovArgs a) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
-    __shared__ double red[32];
-    __shared__ double sm_in[kPartialSlots], sm_out[kPartialSlots];
+    __shared__ CommMailbox mailbox;
     __shared__ double sc[kMaxMemory], ss[kMaxMemory], sz[kMaxMemory + 1], sy[kMaxMemory + 1];
     __shared__ double sR[kMaxMemory * (kMaxMemory + 1) / 2];
     __shared__ double s_flags[4];      // rnorm, inconsistent, -, Hbis
     __shared__ double s_seg[32];
 
-    GridReduce gr;
-    gr.init(a.barrier, a.partials, a.poll_depth);
+    if (threadIdx.x == 0) mailbox.dead = 0;
     const int r0 = a.part[blockIdx.x], r1 = a.part[blockIdx.x + 1];
-    SpmvEngine<T, RES> eng(a, r0, r1, dyn_smem);
+    SpmvEngine<T, RES> eng(a, r0, r1, dyn_smem);          // all warps take part in the bulk copy
+    __syncthreads();
+    if (threadIdx.x >= kMainThreads) {                     // comm warps: exchange service only
+        comm_warp_loop(&mailbox, a, a.poll_depth);
+        return;
+    }
+    GridReduce gr;
+    gr.init(&mailbox, a.trace);
+    double *sm_in = mailbox.in, *sm_out = mailbox.out;
     const int n = a.n;
     const int mem = a.mem;
     VecSlices V(a, dyn_smem, a.work, r0);                // V.at(i), i = 0..mem: CTA-local basis rows
     double *qbuf = a.work + (size_t)(mem + 1) * n;       // two raw buffers for the SpMV gather (global)
-    double *x = a.x;
+    double *x = a.work + (size_t)(mem + 3) * n;          // iterate in internal order (gathered by all CTAs)
     const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int lane = tid & 31, wid = tid >> 5, nwarps = nthr >> 5;
+    const int tid = threadIdx.x, nthr = kMainThreads;
+    const int lane = tid & 31, wid = tid >> 5, nwarps = kMainWarps;
+    // vectors cross the ABI in caller order; internally rows follow the reordered matrix
+    for (int row = r0 + tid; row < r1; row += nthr) x[row] = a.x[a.perm[row]];
+    gr.barrier();
     const double btol = 1.8189894035458565e-12;          // eps^(3/4)
     long long nhist = 0;
-    PhaseClock pc;
+    PhaseClock<PROF> pc;
     pc.start(lead);
 
     // ---- initial residual: w = b − A x0 ; r0 = M w (raw into qbuf[0]) ; β = ‖r0‖
@@ -620,12 +764,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
         double *q0 = qbuf;
         double *v0 = V.at(0);
         eng.run(x, [&](int row, double ax) {
-            const double v = precond(a, row, a.b[row] - ax);
+            const double v = precond(a, row, a.b[a.perm[row]] - ax);
             q0[row] = v;
             v0[row] = v;
             part = fma(v, v, part);
         });
-        beta = sqrt(grid_sum(gr, part, red, true));
+        beta = sqrt(gr.sum_threads<true>(part));
     }
     double rnorm = beta;
     const double rnorm0 = beta;
@@ -651,14 +795,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
             double *q0 = qbuf + (size_t)cur * n;
             double *v0 = V.at(0);
             eng.run(x, [&](int row, double ax) {
-                const double v = precond(a, row, a.b[row] - ax);
+                const double v = precond(a, row, a.b[a.perm[row]] - ax);
                 q0[row] = v;
                 v0[row] = v;
                 part = fma(v, v, part);
             });
-            beta = sqrt(grid_sum(gr, part, red, true));
+            beta = sqrt(gr.sum_threads<true>(part));
         }
-        __syncthreads();
+        main_sync();
         if (tid == 0) sz[0] = beta;
         // V[0] = r0/β on own rows; other CTAs read the raw vector scaled by inv_h
         double inv_h = 1.0 / beta;
@@ -678,7 +822,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
             double *dst = qbuf + (size_t)(cur ^ 1) * n;
             pc.mark(3);
             eng.run(src, [&](int row, double av) { q[row] = precond(a, row, av * inv_h); });
-            __syncthreads();
+            main_sync();
             pc.mark(0);
             double hsq = 0.0;                            // ‖q‖² after orthogonalisation
             if (a.orth == NUPGCM_ORTH_MGS) {
@@ -694,7 +838,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
                         part = fma(vi[row], qv, part);
                     }
                     pc.mark(1);
-                    hprev = grid_sum(gr, part, red, false);
+                    hprev = gr.sum_threads<false>(part);
                     pc.mark(2);
                     if (tid == 0) sR[nr + i] = hprev;
                 }
@@ -707,7 +851,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
                     part = fma(qv, qv, part);
                 }
                 pc.mark(1);
-                hsq = grid_sum(gr, part, red, true);     // publishes dst for the next gather
+                hsq = gr.sum_threads<true>(part);     // publishes dst for the next gather
                 pc.mark(2);
             } else {
                 // CGS2: all k projections at once, twice; warp w handles basis vector w % k on
@@ -716,7 +860,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
                 const int rows = r1 - r0;
                 const int seglen = (rows + nseg - 1) / nseg;
                 for (int pass = 0; pass < 2; ++pass) {
-                    __syncthreads();
+                    main_sync();
                     for (int u = wid; u < k * nseg; u += nwarps) {
                         const int i = u % k, sg = u / k;
                         const double *vi = V.at(i);
@@ -726,15 +870,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
                         part = warp_sum(part);
                         if (lane == 0) s_seg[u] = part;        // k*nseg <= nwarps <= 32
                     }
-                    __syncthreads();
+                    main_sync();
                     if (tid < k) {
                         double t = 0.0;
                         for (int sg = 0; sg < nseg; ++sg) t += s_seg[sg * k + tid];
                         sm_in[tid] = t;
                     }
-                    __syncthreads();
+                    main_sync();
                     pc.mark(1);
-                    gr.sumN(k, sm_in, sm_out, false);
+                    gr.sumN(k);
                     pc.mark(2);
                     // q −= Σ h_i v_i  (own rows)
                     double part = 0.0;
@@ -747,13 +891,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
                     if (tid < k) sR[nr + tid] = (pass == 0) ? sm_out[tid] : sR[nr + tid] + sm_out[tid];
                     if (pass == 1) {
                         pc.mark(1);
-                        hsq = grid_sum(gr, part, red, true);
+                        hsq = gr.sum_threads<true>(part);
                         pc.mark(2);
                     }
                 }
             }
             // ---- scalar recurrences, replicated per CTA (thread 0), Krylov.jl order
-            __syncthreads();
+            main_sync();
             if (tid == 0) {
                 const double Hbis = sqrt(hsq);
                 for (int i = 0; i < k - 1; ++i) {
@@ -772,7 +916,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
                 s_flags[0] = fabs(zeta);
                 s_flags[3] = Hbis;
             }
-            __syncthreads();
+            main_sync();
             rnorm = s_flags[0];
             const double Hbis = s_flags[3];
             if (lead && a.hist && nhist < a.hist_cap) a.hist[nhist] = rnorm;
@@ -790,7 +934,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
             }
         }
         // ---- back substitution R y = z (thread 0), then x += Σ y_i v_i on own rows
-        __syncthreads();
+        main_sync();
         if (tid == 0) {
             bool inc = false;
             for (int i = 0; i < k; ++i) sy[i] = sz[i];
@@ -805,7 +949,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
             }
             s_flags[1] = inc ? 1.0 : 0.0;
         }
-        __syncthreads();
+        main_sync();
         if (s_flags[1] != 0.0) inconsistent = true;
         for (int row = r0 + tid; row < r1; row += nthr) {
             double xr = 0.0;
@@ -821,6 +965,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
             cur = 0;
         }
     }
+    for (int row = r0 + tid; row < r1; row += nthr) a.x[a.perm[row]] = x[row];
+    gr.finish();
     if (lead) {
         a.result[0] = (double)iter;
         a.result[1] = solved ? 1.0 : 0.0;
@@ -831,7 +977,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
         a.result[6] = (double)(nhist < a.hist_cap ? nhist : a.hist_cap);
         a.result[7] = gr.aborted() ? 1.0 : 0.0;
         pc.mark(3);
-        for (int i = 0; i < 4; ++i) a.result[8 + i] = (double)pc.acc[i];
+        pc.dump(a.result);
     }
 }
 
@@ -839,18 +985,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
 // host side
 // =============================================================================================
 
-// depth + 16 * replicas of GridReduce (NUPGCM_POLL_DEPTH / NUPGCM_REPLICAS override)
+// replicas of the reduction slots (NUPGCM_REPLICAS overrides); measured on B200 with
+// tools/reduce_cliff.py
 static int poll_config(int grid) {
-    int depth = 1, rep = grid > 100 ? 2 : 1;   // measured on B200: tools/reduce_cliff.py
-    if (const char *ed = getenv("NUPGCM_POLL_DEPTH")) {
-        const int v = atoi(ed);
-        if (v == 1 || v == 2 || v == 4) depth = v;
-    }
+    int rep = grid > 100 ? 2 : 1;
     if (const char *er = getenv("NUPGCM_REPLICAS")) {
         const int v = atoi(er);
         if (v >= 1 && v <= kMaxReplicas) rep = v;
     }
-    return depth + 16 * rep;
+    return rep;
 }
 
 static int pow2floor(int v) {
@@ -870,8 +1013,8 @@ static int persistent_tpr(const nupgcm_csr *A, bool resident, int grid) {
     const int rows_per_cta = (int)((A->n_rows + grid - 1) / grid);
     int t = A->tpr;
     if (resident) return std::min(t, 8);       // measured on B200: 4-8 lanes per row are fastest
-    if (rows_per_cta > 0 && rows_per_cta * t > kThreads && rows_per_cta <= kThreads / 2)
-        t = std::max(2, pow2floor(kThreads / rows_per_cta));
+    if (rows_per_cta > 0 && rows_per_cta * t > kMainThreads && rows_per_cta <= kMainThreads / 2)
+        t = std::max(2, pow2floor(kMainThreads / rows_per_cta));
     return std::min(t, 32);
 }
 
@@ -899,7 +1042,10 @@ static int32_t ensure_workspace(nupgcm_ctx *ctx, size_t bytes) {
 template <int T, bool RES>
 static cudaError_t launch2(bool gmres, KrylovArgs &args, nupgcm_ctx *ctx, size_t smem, int grid) {
     void *params[] = {&args};
-    const void *fn = gmres ? (const void *)k_gmres<T, RES> : (const void *)k_cg<T, RES>;
+    const char *ep = getenv("NUPGCM_PROFILE");
+    const bool prof = ep && atoi(ep) != 0;
+    const void *fn = gmres ? (prof ? (const void *)k_gmres<T, RES, true> : (const void *)k_gmres<T, RES, false>)
+                           : (const void *)k_cg<T, RES>;
     if (smem > 0) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -958,7 +1104,7 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
     NUPGCM_CUDA(ctx, cudaSetDevice(ctx->device));
     int32_t rcp = nupgcm_csr_prepare(const_cast<nupgcm_csr *>(A), grid);
     if (rcp) return rcp;
-    const size_t wbytes = (gmres ? (size_t)(memory + 3) : 6) * (size_t)n * sizeof(double);
+    const size_t wbytes = (gmres ? (size_t)(memory + 4) : 7) * (size_t)n * sizeof(double);
     int32_t rc = ensure_workspace(ctx, wbytes);
     if (rc) return rc;
     if (hist_cap > ctx->hist_cap) {
@@ -970,9 +1116,10 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
     }
     KrylovArgs args;
     memset(&args, 0, sizeof(args));
-    args.rowptr = A->d_rowptr;
-    args.colidx = A->d_colidx;
-    args.vals = A->d_vals;
+    args.rowptr = A->d_prow;
+    args.colidx = A->d_pcol;
+    args.vals = A->d_pvals;
+    args.perm = A->d_perm;
     args.part = A->d_part;
     args.loc = A->d_loc;
     args.foot_ptr = A->d_foot_ptr;
@@ -998,6 +1145,14 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
 
     NUPGCM_CUDA(ctx, cudaMemsetAsync(ctx->d_barrier, 0, 4 * sizeof(unsigned long long), ctx->stream));
     NUPGCM_CUDA(ctx, cudaMemsetAsync(ctx->d_partials, 0, reduce_scratch_bytes(ctx->coop_grid), ctx->stream));
+    const char *trace_path = getenv("NUPGCM_TRACE_FILE");       // debug only
+    unsigned long long *d_trace = nullptr;
+    const size_t trace_words = (size_t)kTraceWindow * kTraceStamps * grid;
+    if (trace_path && gmres) {
+        NUPGCM_CUDA(ctx, cudaMalloc(&d_trace, trace_words * sizeof(unsigned long long)));
+        NUPGCM_CUDA(ctx, cudaMemsetAsync(d_trace, 0, trace_words * sizeof(unsigned long long), ctx->stream));
+    }
+    args.trace = d_trace;
     NUPGCM_CUDA(ctx, cudaEventRecord(ctx->sev0, ctx->stream));
     cudaError_t e;
     const size_t smem = (size_t)args.lay.total;
@@ -1011,10 +1166,22 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
     NUPGCM_CUDA(ctx, e);
     ctx->launches++;
     NUPGCM_CUDA(ctx, cudaEventRecord(ctx->sev1, ctx->stream));
-    NUPGCM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 12 * sizeof(double),
+    NUPGCM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 13 * sizeof(double),
                                      cudaMemcpyDeviceToHost, ctx->stream));
     NUPGCM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const double *res = ctx->h_scalars;
+    if (d_trace) {
+        unsigned long long *h = (unsigned long long *)malloc(trace_words * sizeof(unsigned long long));
+        cudaMemcpy(h, d_trace, trace_words * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+        if (FILE *f = fopen(trace_path, "wb")) {
+            const int hdr[4] = {grid, (int)kTraceWindow, (int)kTraceStamps, 0};
+            fwrite(hdr, sizeof(int), 4, f);
+            fwrite(h, sizeof(unsigned long long), trace_words, f);
+            fclose(f);
+        }
+        free(h);
+        cudaFree(d_trace);
+    }
     if (res[7] != 0.0)
         return nupgcm_fail(ctx, NUPGCM_ERR_CUDA, "%s",
                            "persistent solver kernel aborted: cross-CTA wait watchdog expired");
@@ -1034,29 +1201,35 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
         float ms = 0.f;
         NUPGCM_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->sev0, ctx->sev1));
         stats->device_ms = ms;
-        if (gmres) {
+        const char *ep = getenv("NUPGCM_PROFILE");
+        if (gmres && ep && atoi(ep) != 0) {
             const double tot = res[8] + res[9] + res[10] + res[11];
             for (int i = 0; i < 4; ++i) stats->phase_frac[i] = tot > 0 ? (float)(res[8 + i] / tot) : 0.f;
+            stats->sm_mhz = (float)res[12];
         }
     }
     return NUPGCM_OK;
 }
 
 // ---- diagnostics: latency of the grid-wide reduction primitive ---------------------------------
-__global__ void k_diag_reduce(unsigned long long *barrier, double *partials, int mode, int reps, int depth, double *out) {
-    __shared__ double red[32];
+__global__ void __launch_bounds__(kThreads, 1) k_diag_reduce(const __grid_constant__ KrylovArgs a, int mode, int reps, double *out) {
+    __shared__ CommMailbox mailbox;
+    if (threadIdx.x == 0) mailbox.dead = 0;
+    __syncthreads();
+    if (threadIdx.x >= kMainThreads) {
+        comm_warp_loop(&mailbox, a, a.poll_depth);
+        return;
+    }
     GridReduce gr;
-    gr.init(barrier, partials, depth);
+    gr.init(&mailbox);
     double v = 1.0 + blockIdx.x, acc = 0.0;
     for (int i = 0; i < reps && !gr.aborted(); ++i) {
-        double s;
-        __syncthreads();
-        if (mode == 0) s = gr.sum1<false>(v);
-        else if (mode == 1) s = grid_sum(gr, threadIdx.x == 0 ? v : 0.0, red, false);
-        else s = grid_sum(gr, threadIdx.x == 0 ? v : 0.0, red, true);
+        const double mine = threadIdx.x == 0 ? v : 0.0;
+        const double s = mode == 2 ? gr.sum_threads<true>(mine) : gr.sum_threads<false>(mine);
         acc += s;
         v = s * 1e-6 + blockIdx.x;
     }
+    gr.finish();
     if (blockIdx.x == 0 && threadIdx.x == 0) { out[0] = acc; out[7] = gr.aborted() ? 1.0 : 0.0; }
 }
 
@@ -1125,16 +1298,20 @@ extern "C" int32_t nupgcm_diag_reduce_latency(nupgcm_ctx *ctx, int32_t mode, int
                                               int32_t threads, float *us_per_reduction) {
     NUPGCM_REQUIRE(nullptr, ctx, "ctx is NULL");
     NUPGCM_REQUIRE(ctx, mode >= 0 && mode <= 2 && reps > 0 && us_per_reduction, "diag: bad argument");
-    NUPGCM_REQUIRE(ctx, grid >= 1 && grid <= ctx->coop_grid && threads >= 32 && threads <= 1024 && threads % 32 == 0,
-                   "diag: grid/threads out of range");
+    NUPGCM_REQUIRE(ctx, grid >= 1 && grid <= ctx->coop_grid, "diag: grid out of range");
+    (void)threads;                                      // the kernels always run kThreads per CTA
     NUPGCM_CUDA(ctx, cudaMemsetAsync(ctx->d_barrier, 0, 4 * sizeof(unsigned long long), ctx->stream));
     NUPGCM_CUDA(ctx, cudaMemsetAsync(ctx->d_partials, 0, reduce_scratch_bytes(ctx->coop_grid), ctx->stream));
-    unsigned long long *bar = ctx->d_barrier;
-    double *part = ctx->d_partials, *out = ctx->d_scalars;
-    int m = mode, r = reps, dep = poll_config(grid);
-    void *params[] = {&bar, &part, &m, &r, &dep, &out};
+    KrylovArgs args;
+    memset(&args, 0, sizeof(args));
+    args.barrier = ctx->d_barrier;
+    args.partials = ctx->d_partials;
+    args.poll_depth = poll_config(grid);
+    double *out = ctx->d_scalars;
+    int m = mode, r = reps;
+    void *params[] = {&args, &m, &r, &out};
     NUPGCM_CUDA(ctx, cudaEventRecord(ctx->sev0, ctx->stream));
-    NUPGCM_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_diag_reduce, dim3(grid), dim3(threads), params, 0, ctx->stream));
+    NUPGCM_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_diag_reduce, dim3(grid), dim3(kThreads), params, 0, ctx->stream));
     ctx->launches++;
     NUPGCM_CUDA(ctx, cudaEventRecord(ctx->sev1, ctx->stream));
     NUPGCM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -26,7 +26,8 @@ class SolveStats(C.Structure):
     _fields_ = [("niter", c_int64), ("solved", c_int32), ("inconsistent", c_int32),
                 ("breakdown", c_int32), ("reserved", c_int32), ("rnorm", c_double),
                 ("rnorm0", c_double), ("device_ms", c_float), ("launches", c_int32),
-                ("hist_len", c_int64), ("phase_frac", c_float * 4)]
+                ("hist_len", c_int64), ("phase_frac", c_float * 4),
+                ("sm_mhz", c_float), ("reserved2", c_float)]
 
 
 _P = c_void_p
@@ -65,6 +66,7 @@ SIGNATURES = {
     "nupgcm_csr_update_values": [_P, _dp, c_int64],
     "nupgcm_csr_combine": [_P, _P, _P, _P, c_double],
     "nupgcm_csr_inv_diag": [_P, _P],
+    "nupgcm_rcm_order": [c_int64, _ip, _ip, c_int32, _ip],
     "nupgcm_spmv": [_P, _P, _P, c_double, c_double],
     "nupgcm_cg_solve": [_P, _P, c_double, _P, _P, c_double, c_double, c_int64, _dp, c_int64,
                         POINTER(SolveStats)],
@@ -322,6 +324,17 @@ class CsrMatrix:
     def spmv(self, x: Vector, y: Vector, alpha=1.0, beta=0.0):
         _check(self.lib.nupgcm_spmv(self.h, x.h, y.h, float(alpha), float(beta)), self.ctx.h)
         return y
+
+
+def rcm_order(mat):
+    """RCM ordering of a SciPy sparse matrix's symmetrised pattern (host-only utility)."""
+    import scipy.sparse as sp
+    m = sp.csr_matrix(mat)
+    rowptr = np.ascontiguousarray(m.indptr, dtype=np.int64)
+    col = np.ascontiguousarray(m.indices, dtype=np.int64)
+    out = np.empty(m.shape[0], dtype=np.int64)
+    _check(load().nupgcm_rcm_order(m.shape[0], _ptr(rowptr, _ip), _ptr(col, _ip), 0, _ptr(out, _ip)))
+    return out
 
 
 def _solve(fn, A, dinv, pscale, y, x, atol, rtol, itmax, extra, history):

@@ -17,4 +17,4 @@ for drop in (True, False):
             st, _ = lib.gmres_solve(dA, dy, x, pscale=ops["pscale"], atol=0, rtol=1e-30, itmax=1000, orth=orth)
             us = 1e3 * st.device_ms / st.niter
             pf = list(st.phase_frac)
-            print(f"drop={int(drop)} grid={grid} {name:4s}: {us:6.2f} us/iter  spmv {us*pf[0]:5.2f}  local {us*pf[1]:5.2f}  reduce {us*pf[2]:5.2f}  scalar {us*pf[3]:5.2f}", flush=True)
+            print(f"drop={int(drop)} grid={grid} {name:4s}: {us:6.2f} us/iter  spmv {us*pf[0]:5.2f}  local {us*pf[1]:5.2f}  reduce {us*pf[2]:5.2f}  scalar {us*pf[3]:5.2f}  SM {st.sm_mhz:.0f} MHz", flush=True)
