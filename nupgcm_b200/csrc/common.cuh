@@ -75,6 +75,10 @@ struct nupgcm_csr {
     double *d_pvals;               // [nnz] reordered values, refreshed when vals_version moves
     int32_t *h_prow, *h_pcol;
     long long vals_version, pvals_version;
+    // streaming form: per-CTA chunk tables (built by nupgcm_csr_prepare for the current grid)
+    int32_t *d_chunk_ptr;          // [grid+1]
+    int32_t *d_chunk_rowend;       // per chunk: first row starting at or after the chunk's end
+    int str_max_rows, str_max_chunks;
 };
 
 int32_t nupgcm_csr_prepare(nupgcm_csr *A, int grid);
@@ -97,6 +101,7 @@ struct nupgcm_mesh {
     double *d_w;                   // [nq]
 };
 
+static const int kStreamChunk = 4096;  // matrix entries per TMA pipeline stage of the streaming SpMV
 static const int kPartialSlots = 24;   // >= memory+2 of GMRES
 static const int kMaxMemory = 20;
 

@@ -182,15 +182,19 @@ static int32_t build_internal_order(nupgcm_csr *A) {
     NUPGCM_CUDA(ctx, cudaMalloc(&A->d_prow, (size_t)(n + 1 + 8) * sizeof(int32_t)));
     NUPGCM_CUDA(ctx, cudaMemset(A->d_prow, 0, (size_t)(n + 1 + 8) * sizeof(int32_t)));
     NUPGCM_CUDA(ctx, cudaMemcpy(A->d_prow, prow.data(), (size_t)(n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
-    NUPGCM_CUDA(ctx, cudaMalloc(&A->d_pcol, nz * sizeof(int32_t)));
+    // values / columns are padded to whole streaming chunks (+1) so that bulk copies never run out
+    const size_t nzpad = ((nz + kStreamChunk - 1) / kStreamChunk + 1) * (size_t)kStreamChunk;
+    NUPGCM_CUDA(ctx, cudaMalloc(&A->d_pcol, nzpad * sizeof(int32_t)));
+    NUPGCM_CUDA(ctx, cudaMemset(A->d_pcol, 0, nzpad * sizeof(int32_t)));
     NUPGCM_CUDA(ctx, cudaMalloc(&A->d_psrc, nz * sizeof(int32_t)));
     if (nnz) {
         NUPGCM_CUDA(ctx, cudaMemcpy(A->d_pcol, pcol.data(), (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice));
         NUPGCM_CUDA(ctx, cudaMemcpy(A->d_psrc, psrc.data(), (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice));
     }
-    NUPGCM_CUDA(ctx, cudaMalloc(&A->d_pvals, (nz + 4) * sizeof(double)));
-    NUPGCM_CUDA(ctx, cudaMemset(A->d_pvals, 0, (nz + 4) * sizeof(double)));
+    NUPGCM_CUDA(ctx, cudaMalloc(&A->d_pvals, nzpad * sizeof(double)));
+    NUPGCM_CUDA(ctx, cudaMemset(A->d_pvals, 0, nzpad * sizeof(double)));
     A->pvals_version = -1;
+    NUPGCM_CUDA(ctx, cudaDeviceSynchronize());   // set-up copies ran on the default stream
     return NUPGCM_OK;
 }
 
@@ -220,7 +224,40 @@ int32_t nupgcm_csr_prepare(nupgcm_csr *A, int grid) {
     build_partition(h_rowptr, n_rows, grid, part);
     NUPGCM_CUDA(ctx, cudaMalloc(&A->d_part, part.size() * sizeof(int32_t)));
     NUPGCM_CUDA(ctx, cudaMemcpy(A->d_part, part.data(), part.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    if (A->n_rows == A->n_cols && kept > 0) {
+    {   // streaming chunk tables
+        cudaFree(A->d_chunk_ptr); A->d_chunk_ptr = nullptr;
+        cudaFree(A->d_chunk_rowend); A->d_chunk_rowend = nullptr;
+        std::vector<int32_t> cptr(grid + 1, 0), rowend;
+        int max_rows = 0, max_chunks = 0;
+        for (int p = 0; p < grid; ++p) {
+            const int32_t ra = part[p], rb = part[p + 1];
+            const int64_t k0 = h_rowptr[ra], k1 = h_rowptr[rb];
+            const int64_t kbase = (k0 / kStreamChunk) * kStreamChunk;
+            const int nch = k1 > k0 ? (int)((k1 - kbase + kStreamChunk - 1) / kStreamChunk) : 0;
+            while (rowend.size() % 4) rowend.push_back(0);      // 16-byte aligned bulk copies
+            cptr[p] = (int32_t)rowend.size();
+            int32_t row = ra;
+            for (int ci = 0; ci < nch; ++ci) {
+                const int64_t c1 = kbase + (int64_t)(ci + 1) * kStreamChunk;
+                while (row < rb && h_rowptr[row] < c1) ++row;
+                rowend.push_back(row);
+            }
+            max_rows = std::max(max_rows, (int)(rb - ra));
+            max_chunks = std::max(max_chunks, nch);
+        }
+        cptr[grid] = (int32_t)rowend.size();
+        NUPGCM_CUDA(ctx, cudaMalloc(&A->d_chunk_ptr, cptr.size() * sizeof(int32_t)));
+        NUPGCM_CUDA(ctx, cudaMemcpy(A->d_chunk_ptr, cptr.data(), cptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        NUPGCM_CUDA(ctx, cudaMalloc(&A->d_chunk_rowend, (rowend.size() + 8) * sizeof(int32_t)));
+        NUPGCM_CUDA(ctx, cudaMemset(A->d_chunk_rowend, 0, (rowend.size() + 8) * sizeof(int32_t)));
+        if (!rowend.empty())
+            NUPGCM_CUDA(ctx, cudaMemcpy(A->d_chunk_rowend, rowend.data(), rowend.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        A->str_max_rows = max_rows;
+        A->str_max_chunks = max_chunks;
+    }
+    // SM-resident tables: only worth building when a CTA's slice can possibly fit on chip
+    const int64_t slice_bytes = kept * 10 / (grid > 0 ? grid : 1);
+    if (A->n_rows == A->n_cols && kept > 0 && slice_bytes < 230 * 1024) {
         const int32_t *h_col = A->h_pcol;
         std::vector<uint16_t> loc(kept);
         std::vector<int32_t> foot_ptr(grid + 1, 0), foot_len(grid, 0), foot, tmp;
@@ -261,6 +298,7 @@ int32_t nupgcm_csr_prepare(nupgcm_csr *A, int grid) {
         }
     }
     A->prepared_grid = grid;
+    NUPGCM_CUDA(ctx, cudaDeviceSynchronize());   // set-up copies ran on the default stream
     return NUPGCM_OK;
 }
 
@@ -359,6 +397,7 @@ extern "C" int32_t nupgcm_csr_create(nupgcm_ctx *ctx, int64_t n_rows, int64_t n_
     memcpy(A->h_rowptr, h_rowptr.data(), (size_t)(n_rows + 1) * sizeof(int32_t));
     if (kept) memcpy(A->h_col, h_col.data(), (size_t)kept * sizeof(int32_t));
     A->prepared_grid = 0;
+    NUPGCM_CUDA(ctx, cudaDeviceSynchronize());   // set-up copies ran on the default stream
     *out = A;
     return NUPGCM_OK;
 }
@@ -380,6 +419,8 @@ extern "C" int32_t nupgcm_csr_destroy(nupgcm_csr *A) {
     cudaFree(A->d_pcol);
     cudaFree(A->d_psrc);
     cudaFree(A->d_pvals);
+    cudaFree(A->d_chunk_ptr);
+    cudaFree(A->d_chunk_rowend);
     free(A->h_rowptr);
     free(A->h_col);
     free(A->h_prow);

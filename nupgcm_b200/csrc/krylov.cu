@@ -33,7 +33,12 @@ static const int kThreads = 512;       // 16 warps: up to 128 registers per thre
 struct ResidentLayout {       // byte offsets into dynamic shared memory (all multiples of 16)
     int vals, cols, xs, foot, rp, bar, vec, total;
     int vec_rows;             // row capacity of one vector slice (0: vectors stay in global memory)
+    // streaming form (matrix does not fit on chip): kStreamStages buffers of kStreamChunk entries
+    int st_vals, st_cols, st_info, st_misc;
+    int streaming;            // 1: SpmvEngine<T,false> uses the TMA pipeline described by st_*
 };
+
+static const int kStreamStages = 3;        // kStreamChunk (common.cuh) entries per stage: 32 KB values + 16 KB columns
 
 struct KrylovArgs {
     const int32_t *rowptr;
@@ -44,6 +49,8 @@ struct KrylovArgs {
     const int32_t *foot_ptr; // [grid][2]: start (multiple of 4) and length of each CTA's footprint
     const int32_t *foot;
     const int32_t *perm;     // [n] internal row -> caller row (vectors cross the ABI in caller order)
+    const int32_t *chunk_ptr;    // streaming form: [grid+1] offsets into chunk_rowend
+    const int32_t *chunk_rowend; // per chunk: first row that starts at or after the chunk's end
     ResidentLayout lay;
     int n;
     const double *dinv;      // diagonal preconditioner or NULL
@@ -359,15 +366,15 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
 }
 // 1-D TMA bulk copy global -> shared; bytes % 16 == 0, both addresses 16-byte aligned
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
@@ -427,19 +434,25 @@ struct SpmvEngine {
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             }
             __syncthreads();
-            if (threadIdx.x == 0) {
-                mbar_expect_tx(bar, bv + bc + br + bf);
-                uint32_t done = 0;                            // values in <= 32 KB pieces
-                while (done < bv) {
-                    const uint32_t piece = min(bv - done, 32768u);
-                    bulk_g2s(smem + L.vals + done, reinterpret_cast<const unsigned char *>(a.vals + ka) + done, piece, bar);
-                    done += piece;
+            // One bulk copy per barrier phase: with several copies outstanding on one mbarrier the
+            // streaming kernels faulted on B200 ("unspecified launch failure", round-1 notes in
+            // DESIGN.md), so each piece is issued, awaited, then the next one.  Once per solve.
+            uint32_t parity = 0;
+            auto copy_piece = [&](void *dst, const void *src, uint32_t bytes) {
+                if (bytes == 0) return;                                  // uniform over the CTA
+                if (threadIdx.x == 0) {
+                    mbar_expect_tx(bar, bytes);
+                    bulk_g2s(dst, src, bytes, bar);
                 }
-                if (bc) bulk_g2s(smem + L.cols, a.loc + kc, bc, bar);
-                bulk_g2s(smem + L.rp, a.rowptr + ra, br, bar);
-                if (bf) bulk_g2s(smem + L.foot, a.foot + f0, bf, bar);
-            }
-            mbar_wait(bar, 0);
+                mbar_wait(bar, parity);
+                parity ^= 1u;
+            };
+            for (uint32_t done = 0; done < bv; done += 32768u)
+                copy_piece(smem + L.vals + done, reinterpret_cast<const unsigned char *>(a.vals + ka) + done,
+                           min(bv - done, 32768u));
+            copy_piece(smem + L.cols, a.loc + kc, bc);
+            copy_piece(smem + L.rp, a.rowptr + ra, br);
+            copy_piece(smem + L.foot, a.foot + f0, bf);
             vs = reinterpret_cast<const double *>(smem + L.vals) - ka;
             cs = reinterpret_cast<const uint16_t *>(smem + L.cols) - kc;
             rp = reinterpret_cast<const int32_t *>(smem + L.rp) - ra;
@@ -512,6 +525,187 @@ struct SpmvEngine {
                 if (active && lane == 0) f(row, acc);
             }
         }
+    }
+};
+
+
+// Streaming form: the CTA's slice of the (reordered) matrix is pulled through shared memory in
+// chunks of kStreamChunk entries by TMA bulk copies (cp.async.bulk + mbarrier), kStreamStages deep,
+// so the HBM/L2 latency of the matrix stream is hidden by the copy engine instead of by registers.
+// Per chunk: (A) every main thread multiplies its entries by the gathered vector entries (all of a
+// thread's ~12 ld.cg gathers are in flight together) and stores the products in place; (B) groups
+// of T lanes add up the products row by row; a row cut by the chunk boundary carries its partial
+// sum into the next chunk.  Chunks are aligned to multiples of kStreamChunk in the global entry
+// index, so neighbouring CTAs' chunks overlap harmlessly at the ends of their row ranges.
+template <int T>
+struct SpmvEngine<T, false> {
+    const KrylovArgs &a;
+    int r0, r1;
+    const int32_t *rp;            // CTA's row pointers in shared memory, biased by the global row id
+    double *svals;                // [stages][chunk]
+    int32_t *scols;               // [stages][chunk]
+    const int32_t *rowend;        // per chunk (shared memory copy)
+    uint64_t *bars;               // [stages] full barriers
+    double *carry;                // 2 doubles
+    int kbase, nch;
+    unsigned phases;              // expected parity of each stage's barrier (persists across run() calls)
+    bool legacy;
+
+    __device__ __forceinline__ SpmvEngine(const KrylovArgs &args, int r0_, int r1_, unsigned char *smem)
+        : a(args), r0(r0_), r1(r1_) {
+        legacy = a.lay.streaming == 0;
+        phases = 0;
+        if (legacy) return;
+        const ResidentLayout &L = a.lay;
+        svals = reinterpret_cast<double *>(smem + L.st_vals);
+        scols = reinterpret_cast<int32_t *>(smem + L.st_cols);
+        bars = reinterpret_cast<uint64_t *>(smem + L.st_misc);
+        carry = reinterpret_cast<double *>(smem + L.st_misc + 64);
+        const int k0 = a.rowptr[r0], k1 = a.rowptr[r1];
+        kbase = (k0 / kStreamChunk) * kStreamChunk;
+        nch = k1 > k0 ? (k1 - kbase + kStreamChunk - 1) / kStreamChunk : 0;
+        const int ra = r0 & ~3;
+        const uint32_t br = (uint32_t)(((r1 + 1 - ra + 3) & ~3) * 4);
+        const int cp0 = a.chunk_ptr[blockIdx.x];
+        const int ca = cp0 & ~3;
+        const uint32_t bi = (uint32_t)(((cp0 + nch - ca + 3) & ~3) * 4);
+        uint64_t *setup_bar = bars + 2 * kStreamStages;
+        if (threadIdx.x == 0) {
+            for (int s = 0; s <= 2 * kStreamStages; ++s) mbar_init(bars + s, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        // row pointers by TMA, chunk table by plain loads (a few dozen ints)
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(setup_bar, br);
+            bulk_g2s(smem + L.rp, a.rowptr + ra, br, setup_bar);
+        }
+        {
+            int32_t *d1 = reinterpret_cast<int32_t *>(smem + L.st_info);
+            for (int i = threadIdx.x; i < (int)(bi / 4); i += blockDim.x) d1[i] = a.chunk_rowend[ca + i];
+        }
+        mbar_wait(setup_bar, 0);
+        __syncthreads();
+        rp = reinterpret_cast<const int32_t *>(smem + L.rp) - ra;
+        rowend = reinterpret_cast<const int32_t *>(smem + L.st_info) + (cp0 - ca);
+    }
+
+    __device__ __forceinline__ void issue(int ci) {          // one thread
+        const int st = ci % kStreamStages;
+        const size_t k = (size_t)kbase + (size_t)ci * kStreamChunk;
+        // one bulk copy per barrier (values: bars[st], columns: bars[stages + st])
+        mbar_expect_tx(bars + st, kStreamChunk * 8);
+        bulk_g2s(svals + (size_t)st * kStreamChunk, a.vals + k, kStreamChunk * 8, bars + st);
+        mbar_expect_tx(bars + kStreamStages + st, kStreamChunk * 4);
+        bulk_g2s(scols + (size_t)st * kStreamChunk, a.colidx + k, kStreamChunk * 4, bars + kStreamStages + st);
+    }
+
+    template <class F>
+    __device__ __forceinline__ void run(const double *xin, F &&f) {
+        const int lane = threadIdx.x & (T - 1);
+        const int g = threadIdx.x / T;
+        const int G = kMainThreads / T;
+        if (!legacy && a.lay.streaming == 3) {               // debug: exercise the pipeline only
+            main_sync();
+            if (threadIdx.x == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                for (int ci = 0; ci < nch && ci < kStreamStages; ++ci) issue(ci);
+            }
+            for (int ci = 0; ci < nch; ++ci) {
+                const int st = ci % kStreamStages;
+                mbar_wait(bars + st, (phases >> st) & 1u);
+                mbar_wait(bars + kStreamStages + st, (phases >> st) & 1u);
+                phases ^= 1u << st;
+                main_sync();
+                if (threadIdx.x == 0 && ci + kStreamStages < nch) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(ci + kStreamStages);
+                }
+            }
+        }
+        if (legacy || a.lay.streaming >= 2) {
+            for (int base = r0; base < r1; base += G) {      // uniform trip count over the CTA
+                const int row = base + g;
+                const bool active = row < r1;
+                double acc = 0.0;
+                if (active) {
+                    const int32_t beg = __ldg(a.rowptr + row), end = __ldg(a.rowptr + row + 1);
+                    for (int32_t k = beg + lane; k < end; k += T)
+                        acc = fma(__ldg(a.vals + k), ld_cg(xin + __ldg(a.colidx + k)), acc);
+                }
+                acc = group_sum<T>(acc);
+                if (active && lane == 0) f(row, acc);
+            }
+            return;
+        }
+        main_sync();                                         // previous run() is completely finished
+        if (threadIdx.x == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            for (int ci = 0; ci < nch && ci < kStreamStages; ++ci) issue(ci);
+        }
+        int cursor = r0;
+        double carry_in = 0.0;
+        for (int ci = 0; ci < nch; ++ci) {
+            const int st = ci % kStreamStages;
+            double *pv = svals + (size_t)st * kStreamChunk;
+            const int32_t *pc = scols + (size_t)st * kStreamChunk;
+            mbar_wait(bars + st, (phases >> st) & 1u);
+            mbar_wait(bars + kStreamStages + st, (phases >> st) & 1u);
+            phases ^= 1u << st;
+            // (A) products, in place
+            {
+                constexpr int PER = (kStreamChunk + kMainThreads - 1) / kMainThreads;
+                double xv[PER];
+#pragma unroll
+                for (int i = 0; i < PER; ++i) {
+                    const int e = threadIdx.x + i * kMainThreads;
+                    xv[i] = e < kStreamChunk ? ld_cg(xin + pc[e]) : 0.0;
+                }
+#pragma unroll
+                for (int i = 0; i < PER; ++i) {
+                    const int e = threadIdx.x + i * kMainThreads;
+                    if (e < kStreamChunk) pv[e] *= xv[i];
+                }
+            }
+            main_sync();
+            // (B) row sums
+            const int c0 = kbase + ci * kStreamChunk, c1 = c0 + kStreamChunk;
+            int rend = rowend[ci];
+            if (rend > r1) rend = r1;
+            for (int base = cursor; base < rend; base += G) {
+                const int row = base + g;
+                const bool active = row < rend;
+                double acc = 0.0;
+                int rbeg = 0, rfin = 0;
+                if (active) {
+                    rbeg = rp[row];
+                    rfin = rp[row + 1];
+                    const int beg = max(rbeg, c0) - c0, end = min(rfin, c1) - c0;
+                    for (int k = beg + lane; k < end; k += T) acc += pv[k];
+                }
+                acc = group_sum<T>(acc);
+                if (active && lane == 0) {
+                    if (row == cursor) acc += carry_in;
+                    if (rfin <= c1) f(row, acc);
+                    else carry[ci & 1] = acc;                 // row continues in the next chunk
+                }
+            }
+            main_sync();
+            // rows [cursor, rend) were touched; the last one may be unfinished
+            if (rend > cursor && rp[rend] > c1) {
+                cursor = rend - 1;
+                carry_in = carry[ci & 1];
+            } else {
+                cursor = rend;
+                carry_in = 0.0;
+            }
+            if (threadIdx.x == 0 && ci + kStreamStages < nch) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(ci + kStreamStages);
+            }
+        }
+        // rows that start exactly at the end of the last chunk (only empty rows can)
+        for (int row = cursor + threadIdx.x; row < r1; row += kMainThreads) f(row, row == cursor ? carry_in : 0.0);
     }
 };
 
@@ -1054,8 +1248,8 @@ static cudaError_t launch2(bool gmres, KrylovArgs &args, nupgcm_ctx *ctx, size_t
 }
 
 template <int T>
-static cudaError_t launch(bool gmres, KrylovArgs &args, nupgcm_ctx *ctx, size_t smem, int grid) {
-    return smem > 0 ? launch2<T, true>(gmres, args, ctx, smem, grid) : launch2<T, false>(gmres, args, ctx, 0, grid);
+static cudaError_t launch(bool gmres, KrylovArgs &args, nupgcm_ctx *ctx, size_t smem, int grid, bool resident) {
+    return resident ? launch2<T, true>(gmres, args, ctx, smem, grid) : launch2<T, false>(gmres, args, ctx, smem, grid);
 }
 
 // Shared-memory plan of the SM-resident form; total == 0 when the matrix slice does not fit.
@@ -1071,6 +1265,35 @@ static ResidentLayout plan_resident(const nupgcm_csr *A, bool gmres, int memory)
     const int n_vec = (envv && atoi(envv) == 0) ? 1 << 20 : (gmres ? memory + 1 : 5);
     ResidentLayout L = resident_layout(A->res_max_nnz, A->res_max_foot, A->res_max_rows, n_vec, limit);
     return L.total <= limit ? L : none;
+}
+
+// Shared-memory plan of the streaming form (TMA pipeline); total == 0 if even that does not fit
+// (then the legacy direct-load loop runs).
+static ResidentLayout plan_streaming(const nupgcm_csr *A, bool gmres, int memory) {
+    ResidentLayout L;
+    memset(&L, 0, sizeof(L));
+    const char *env = getenv("NUPGCM_STREAM_TMA");
+    if (env && atoi(env) == 0) return L;
+    if (!A->d_chunk_ptr) return L;
+    const int static_smem = gmres ? 6144 : 2048;
+    const int limit = 227 * 1024 - static_smem;
+    int off = 0;
+    L.st_vals = off; off += kStreamStages * kStreamChunk * 8;
+    L.st_cols = off; off += kStreamStages * kStreamChunk * 4;
+    L.rp = off;      off += ((A->str_max_rows + 1 + 4 + 3) & ~3) * 4;
+    L.st_info = off; off += ((A->str_max_chunks + 4 + 3) & ~3) * 4;
+    L.st_misc = off; off += 128;
+    L.vec = off;
+    const long long vec_bytes = (long long)(gmres ? memory + 1 : 5) * ((A->str_max_rows + 1) & ~1) * 8;
+    if (off + vec_bytes <= limit) {
+        L.vec_rows = (A->str_max_rows + 1) & ~1;
+        off += (int)vec_bytes;
+    }
+    L.total = off;
+    L.streaming = 1;
+    if (const char *ed = getenv("NUPGCM_STREAM_DEBUG")) L.streaming = atoi(ed);   // 2: set-up only, 3: + pipeline
+    if (L.total > limit) memset(&L, 0, sizeof(L));
+    return L;
 }
 
 static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *dinv, double pscale,
@@ -1125,6 +1348,10 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
     args.foot_ptr = A->d_foot_ptr;
     args.foot = A->d_foot;
     args.lay = plan_resident(A, gmres, memory);
+    const bool resident = args.lay.total > 0;
+    if (!resident) args.lay = plan_streaming(A, gmres, memory);
+    args.chunk_ptr = A->d_chunk_ptr;
+    args.chunk_rowend = A->d_chunk_rowend;
     args.n = (int)n;
     args.dinv = dinv ? dinv->d : nullptr;
     args.pscale = pscale;
@@ -1156,12 +1383,12 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
     NUPGCM_CUDA(ctx, cudaEventRecord(ctx->sev0, ctx->stream));
     cudaError_t e;
     const size_t smem = (size_t)args.lay.total;
-    switch (persistent_tpr(A, smem > 0, grid)) {
-        case 32: e = launch<32>(gmres, args, ctx, smem, grid); break;
-        case 16: e = launch<16>(gmres, args, ctx, smem, grid); break;
-        case 8: e = launch<8>(gmres, args, ctx, smem, grid); break;
-        case 4: e = launch<4>(gmres, args, ctx, smem, grid); break;
-        default: e = launch<2>(gmres, args, ctx, smem, grid); break;
+    switch (persistent_tpr(A, resident || args.lay.streaming, grid)) {
+        case 32: e = launch<32>(gmres, args, ctx, smem, grid, resident); break;
+        case 16: e = launch<16>(gmres, args, ctx, smem, grid, resident); break;
+        case 8: e = launch<8>(gmres, args, ctx, smem, grid, resident); break;
+        case 4: e = launch<4>(gmres, args, ctx, smem, grid, resident); break;
+        default: e = launch<2>(gmres, args, ctx, smem, grid, resident); break;
     }
     NUPGCM_CUDA(ctx, e);
     ctx->launches++;

@@ -205,6 +205,7 @@ extern "C" int32_t nupgcm_mesh_create(nupgcm_ctx *ctx, int64_t n_cells, int32_t 
     NUPGCM_CUDA(ctx, upload(&m->d_phi, std::vector<double>(bary, bary + (size_t)nq * nv)));   // bary
     NUPGCM_CUDA(ctx, upload(&m->d_w, std::vector<double>(w, w + nq)));
     NUPGCM_CUDA(ctx, cudaMalloc(&m->d_elem, (size_t)n_cells * n_loc * sizeof(double)));
+    NUPGCM_CUDA(ctx, cudaDeviceSynchronize());   // set-up copies ran on the default stream
     *out = m;
     return NUPGCM_OK;
 }

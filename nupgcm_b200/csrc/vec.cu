@@ -263,6 +263,7 @@ extern "C" int32_t nupgcm_index_create(nupgcm_ctx *ctx, const int64_t *idx, int6
     if (e == cudaSuccess)
         e = cudaMemcpy(ix->d, h, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice);
     free(h);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();   // set-up copy ran on the default stream
     if (e != cudaSuccess) {
         free(ix);
         return nupgcm_fail(ctx, NUPGCM_ERR_CUDA, "CUDA error: %s at %s", cudaGetErrorString(e), "index_create");

@@ -1,7 +1,8 @@
 """Host-side stand-in for the parts of Gridap / GridapGmsh that nuPGCM calls at set-up time."""
 from .mshio import RawMesh, read_msh
+from .refine import bowl_projection, refine
 from .fem import (CellIntegrator, DiscreteModel, FacetIntegrator, LagrangeSpace, restrict,
                   restrict_vector)
 
-__all__ = ["RawMesh", "read_msh", "CellIntegrator", "DiscreteModel", "FacetIntegrator",
+__all__ = ["RawMesh", "read_msh", "refine", "bowl_projection", "CellIntegrator", "DiscreteModel", "FacetIntegrator",
            "LagrangeSpace", "restrict", "restrict_vector"]

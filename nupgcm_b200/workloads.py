@@ -109,6 +109,17 @@ def bowl_surface_flux() -> Workload:
                     dict(t_start=0.0, t_stop=50 * 1e-1, Δt=1e-1), lambda x: x[:, 2] / α)
 
 
+def refined_bowl(levels: int = 1, h0: float = 0.08, α: float = 0.5):
+    """bowl3D mesh refined `levels` times from the shipped h0 mesh (h0/2, h0/4, ...), boundary
+    nodes projected onto the bowl: stands in for the gmsh-generated meshes of BASELINE configs
+    3 (h = 0.04) and 5 (h = 0.02)."""
+    from .gridap_lite import RawMesh, bowl_projection, refine
+    raw = RawMesh.load_npz(mesh_path(3, h0))
+    for _ in range(levels):
+        raw = refine(raw, project=bowl_projection(α))
+    return raw
+
+
 def bowl_example(h: float = 0.08, mesh=None, n_steps: int | None = None) -> Workload:
     ε, α, μϱ = 2e-1, 0.5, 1.0
     H = _H(α)
