@@ -45,6 +45,7 @@ typedef struct nupgcm_vec nupgcm_vec;
 typedef struct nupgcm_index nupgcm_index;
 typedef struct nupgcm_csr nupgcm_csr;
 typedef struct nupgcm_mesh nupgcm_mesh;
+typedef struct nupgcm_comm nupgcm_comm;
 
 int32_t nupgcm_version(void);
 const char *nupgcm_last_error(const nupgcm_ctx *ctx);
@@ -64,6 +65,51 @@ int32_t nupgcm_timer_start(nupgcm_ctx *ctx);
 int32_t nupgcm_timer_stop(nupgcm_ctx *ctx, float *ms);
 /* number of kernels this context has launched since creation */
 int32_t nupgcm_launch_count(nupgcm_ctx *ctx, int64_t *count);
+
+/* Restrict the persistent solver kernels of this context to `grid` CTAs (1..SM count; default:
+ * one per SM).  Lets several contexts share one device, each with a slice of the SMs. */
+int32_t nupgcm_set_grid(nupgcm_ctx *ctx, int32_t grid);
+
+/* ---- multi-GPU: row-block sharded solves -------------------------------------------------
+ * The reference runs on one GPU; BASELINE.json's north_star shards the Krylov solves over the
+ * GPUs of one NVLink/NVSwitch box.  One rank per GPU (normally one process per rank, launched by
+ * torchrun).  Every rank builds the same operands; nupgcm_csr_shard then makes the persistent
+ * solvers on that matrix collective: rank r's CTAs own the r-th contiguous block of rows of the
+ * (internally RCM-ordered) system, push the rows a peer's SpMV gathers straight into the peer's
+ * memory over NVLink, and combine dot products through flagged words in peer memory — no host
+ * round trip and no separate collective launch per iteration.  Right-hand side and solution
+ * vectors stay full-length and replicated: each rank reads its rows of y and the warm start, and
+ * the solve ends with an all-gather so x is complete on every rank.
+ *
+ * Set-up protocol: nupgcm_comm_create on every rank; exchange the 64-byte handles from
+ * nupgcm_comm_ipc_handle with any host transport (torch.distributed / MPI all-gather) and pass
+ * all of them, ordered by rank, to nupgcm_comm_connect_ipc; or, for ranks living in one process,
+ * pass the communicator objects to nupgcm_comm_connect_local.  Sharded solves must be called by
+ * all ranks with identical arguments, in the same order. */
+#define NUPGCM_MAX_RANKS 8
+#define NUPGCM_IPC_HANDLE_BYTES 64
+/* max_n: largest system (rows) that will be solved over this communicator */
+int32_t nupgcm_comm_create(nupgcm_ctx *ctx, int32_t rank, int32_t nranks, int64_t max_n,
+                           nupgcm_comm **out);
+int32_t nupgcm_comm_destroy(nupgcm_comm *comm);
+int32_t nupgcm_comm_ipc_handle(nupgcm_comm *comm, void *handle_out /* 64 bytes */);
+int32_t nupgcm_comm_connect_ipc(nupgcm_comm *comm, const void *handles /* nranks x 64 bytes */);
+int32_t nupgcm_comm_connect_local(nupgcm_comm *comm, nupgcm_comm *const *all /* nranks */);
+/* make the persistent solvers on A collective over comm (NULL: back to single-GPU) */
+int32_t nupgcm_csr_shard(nupgcm_csr *A, nupgcm_comm *comm);
+/* rows [*row_begin, *row_end) of the internally ordered system owned by `rank`, and the number
+ * of halo rows it receives per SpMV (valid after the first sharded solve or nupgcm_csr_shard) */
+int32_t nupgcm_csr_shard_info(nupgcm_csr *A, int32_t rank, int64_t *row_begin, int64_t *row_end,
+                              int64_t *nnz_owned, int64_t *halo_rows);
+
+/* Host-only (no context): the layout a sharded solve uses for a square matrix over `nranks`
+ * ranks of `grid_per_rank` CTAs.  perm_out[n]: internal row i = caller row perm_out[i];
+ * row_begin[nranks+1]: rank r owns internal rows [row_begin[r], row_begin[r+1]);
+ * halo_lo/hi[dst*nranks + src]: range of src's rows pushed to dst before each SpMV (0,0: none).
+ * Output pointers may be NULL. */
+int32_t nupgcm_shard_plan(int64_t n, const int64_t *rowptr, const int64_t *colidx, int32_t index_base,
+                          int32_t nranks, int32_t grid_per_rank, int64_t *perm_out,
+                          int64_t *row_begin, int64_t *halo_lo, int64_t *halo_hi);
 
 /* ---- vectors (replace CuVector{Float64}: ext/nuPGCMCUDAExt.jl:24-26,32) ------------------ */
 int32_t nupgcm_vec_create(nupgcm_ctx *ctx, int64_t n, nupgcm_vec **out); /* zero-filled */

@@ -29,15 +29,23 @@ class CPU(AbstractArchitecture):
 
 
 class GPU(AbstractArchitecture):
-    """B200 architecture; carries the library context (created lazily, one per device)."""
+    """B200 architecture; carries the library context (created lazily, one per device).
+
+    ``comm`` (a ``lib.Comm``) turns the Krylov solves of toolkits built on this architecture into
+    row-block sharded, collective solves over the communicator's ranks (one rank per GPU);
+    ``ctx`` supplies an explicit context (several ranks sharing one device)."""
 
     _contexts: dict = {}
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, comm=None, ctx=None):
         self.device = device
+        self.comm = comm
+        self._ctx = ctx if ctx is not None else (comm.ctx if comm is not None else None)
 
     @property
     def ctx(self) -> lib.Context:
+        if self._ctx is not None:
+            return self._ctx
         c = GPU._contexts.get(self.device)
         if c is None:
             c = lib.Context(self.device)        # raises if no B200 / no library: no fallback

@@ -30,7 +30,33 @@ struct nupgcm_ctx {
     double *d_hist;                // residual history
     int64_t hist_cap;
     int coop_grid;                 // CTAs of the persistent solver kernels
+    double *d_ws;                  // workspace of the persistent solvers (grown on demand)
+    size_t ws_bytes;
     char err[512];
+};
+
+// Communicator of the sharded solves: one per rank (= one GPU, normally one process).  Each rank
+// owns an "arena" in its device memory that every other rank can write into (CUDA IPC mapping
+// between processes, plain pointers inside one process):
+//   [0, 128)                    abort word (sticky: a rank whose watchdog fired raises it everywhere)
+//   [kArenaXrOffset, +24 KB)    inter-rank reduction slots  LLSlot[2 banks][kPartialSlots][kXRep][kMaxRanks]
+//   [kArenaVecOffset, ...)      exchange vectors, 3 x max_n doubles: the rows of the multiplied
+//                               vector / iterate that the rank's SpMV gathers (own rows + halo)
+static const int kMaxRanks = NUPGCM_MAX_RANKS;
+static const int kXRep = 4;                  // replicas of the all-reader inter-rank slots
+static const size_t kArenaXrOffset = 128, kArenaVecOffset = 32768;
+
+struct nupgcm_comm {
+    nupgcm_ctx *ctx;
+    int rank, nranks;
+    int64_t max_n;
+    char *arena;                   // this rank's arena
+    size_t arena_bytes;
+    char *peer[kMaxRanks];         // every rank's arena as mapped here (peer[rank] == arena)
+    int ipc_mapped[kMaxRanks];
+    int connected;
+    int broken;                    // a sharded solve aborted: the sequence numbers are undefined
+    unsigned xgen;                 // sequence number of the inter-rank reductions (never reset)
 };
 
 struct nupgcm_vec {
@@ -79,6 +105,11 @@ struct nupgcm_csr {
     int32_t *d_chunk_ptr;          // [grid+1]
     int32_t *d_chunk_rowend;       // per chunk: first row starting at or after the chunk's end
     int str_max_rows, str_max_chunks;
+    // sharded solves: the communicator, and for every peer the range of THIS rank's rows that the
+    // peer's SpMV gathers (bounding range of the peer's column footprint inside this rank's block)
+    nupgcm_comm *comm;
+    int prepared_ranks;
+    int push_lo[kMaxRanks], push_hi[kMaxRanks];
 };
 
 int32_t nupgcm_csr_prepare(nupgcm_csr *A, int grid);

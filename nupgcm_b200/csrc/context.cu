@@ -61,12 +61,20 @@ extern "C" int32_t nupgcm_destroy(nupgcm_ctx *ctx) {
     cudaFree(ctx->d_scalars);
     cudaFreeHost(ctx->h_scalars);
     cudaFree(ctx->d_hist);
+    cudaFree(ctx->d_ws);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->sev0);
     cudaEventDestroy(ctx->sev1);
     cudaStreamDestroy(ctx->stream);
     free(ctx);
+    return NUPGCM_OK;
+}
+
+extern "C" int32_t nupgcm_set_grid(nupgcm_ctx *ctx, int32_t grid) {
+    NUPGCM_REQUIRE(nullptr, ctx, "ctx is NULL");
+    NUPGCM_REQUIRE(ctx, grid >= 1 && grid <= ctx->sm_count, "set_grid: grid must be in 1..SM count");
+    ctx->coop_grid = grid;
     return NUPGCM_OK;
 }
 

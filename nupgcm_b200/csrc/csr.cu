@@ -86,6 +86,22 @@ static void build_partition(const std::vector<int32_t> &rowptr, int64_t n_rows, 
     for (int p = 1; p <= parts; ++p) part[p] = std::max(part[p], part[p - 1]);
 }
 
+// Sharded solves: bounding range [lo, hi) of the rows owned by rank `src` that the rows of rank
+// `dst` reference (dst's halo inside src's block); lo = hi = 0 when there are none.  `part` is the
+// partition over all ranks' CTAs (rank r owns parts [r*gpr, (r+1)*gpr)).
+static void halo_range(const int32_t *rowptr, const int32_t *col, const std::vector<int32_t> &part, int gpr,
+                       int dst, int src, int &lo_out, int &hi_out) {
+    const int32_t s0 = part[(size_t)src * gpr], s1 = part[(size_t)(src + 1) * gpr];
+    const int32_t q0 = part[(size_t)dst * gpr], q1 = part[(size_t)(dst + 1) * gpr];
+    int32_t lo = INT32_MAX, hi = -1;
+    for (int32_t k = rowptr[q0]; k < rowptr[q1]; ++k) {
+        const int32_t c = col[k];
+        if (c >= s0 && c < s1) { lo = std::min(lo, c); hi = std::max(hi, c); }
+    }
+    lo_out = hi >= lo ? lo : 0;
+    hi_out = hi >= lo ? hi + 1 : 0;
+}
+
 // Reverse Cuthill-McKee ordering of the symmetrised pattern (A + Aᵀ).  The persistent solvers
 // work on an internally reordered copy of the matrix: the reference orders the inversion system
 // as [u DOFs (RCM) ; p DOFs (RCM)] (src/dofs.jl:38), which puts every pressure row far from the
@@ -145,6 +161,28 @@ static void rcm_order(int64_t n, const int32_t *rowptr, const int32_t *col, std:
     std::reverse(perm.begin(), perm.end());
 }
 
+// Structure of P A Pᵀ for the ordering `perm` (internal row i = caller row perm[i]); psrc[k] is the
+// position of reordered entry k in the caller-order arrays.
+static void permute_structure(int64_t n, const int32_t *rowptr, const int32_t *col, const std::vector<int32_t> &perm,
+                              std::vector<int32_t> &prow, std::vector<int32_t> &pcol, std::vector<int32_t> &psrc) {
+    const int64_t nnz = rowptr[n];
+    std::vector<int32_t> inv(n);
+    for (int64_t i = 0; i < n; ++i) inv[perm[i]] = (int32_t)i;
+    prow.assign(n + 1, 0);
+    pcol.resize(nnz);
+    psrc.resize(nnz);
+    std::vector<std::pair<int32_t, int32_t>> rowbuf;
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t r = perm[i];
+        rowbuf.clear();
+        for (int32_t k = rowptr[r]; k < rowptr[r + 1]; ++k) rowbuf.emplace_back(inv[col[k]], k);
+        std::sort(rowbuf.begin(), rowbuf.end());
+        int32_t o = prow[i];
+        for (auto &e : rowbuf) { pcol[o] = e.first; psrc[o] = e.second; ++o; }
+        prow[i + 1] = o;
+    }
+}
+
 // Internal (reordered) copy of the structure: built once per matrix.
 static int32_t build_internal_order(nupgcm_csr *A) {
     nupgcm_ctx *ctx = A->ctx;
@@ -158,19 +196,8 @@ static int32_t build_internal_order(nupgcm_csr *A) {
     } else {
         rcm_order(n, A->h_rowptr, A->h_col, perm);
     }
-    std::vector<int32_t> inv(n);
-    for (int64_t i = 0; i < n; ++i) inv[perm[i]] = (int32_t)i;
-    std::vector<int32_t> prow(n + 1, 0), pcol(nnz), psrc(nnz);
-    std::vector<std::pair<int32_t, int32_t>> rowbuf;
-    for (int64_t i = 0; i < n; ++i) {
-        const int32_t r = perm[i];
-        rowbuf.clear();
-        for (int32_t k = A->h_rowptr[r]; k < A->h_rowptr[r + 1]; ++k) rowbuf.emplace_back(inv[A->h_col[k]], k);
-        std::sort(rowbuf.begin(), rowbuf.end());
-        int32_t o = prow[i];
-        for (auto &e : rowbuf) { pcol[o] = e.first; psrc[o] = e.second; ++o; }
-        prow[i + 1] = o;
-    }
+    std::vector<int32_t> prow, pcol, psrc;
+    permute_structure(n, A->h_rowptr, A->h_col, perm, prow, pcol, psrc);
     A->h_prow = (int32_t *)malloc((size_t)(n + 1) * sizeof(int32_t));
     A->h_pcol = (int32_t *)malloc((size_t)(nnz > 0 ? nnz : 1) * sizeof(int32_t));
     if (!A->h_prow || !A->h_pcol) return nupgcm_fail(ctx, NUPGCM_ERR_ALLOC, "%s", "host allocation failed");
@@ -201,8 +228,12 @@ static int32_t build_internal_order(nupgcm_csr *A) {
 // Row partition and SM-resident tables of the persistent solvers for a grid of `grid` CTAs, on
 // the internally reordered structure.  Cached in the handle; rebuilt only when a solve asks for
 // a different grid.  Also refreshes the reordered values when the caller-order values changed.
-int32_t nupgcm_csr_prepare(nupgcm_csr *A, int grid) {
+int32_t nupgcm_csr_prepare(nupgcm_csr *A, int grid_per_rank) {
     nupgcm_ctx *ctx = A->ctx;
+    // sharded solves: the partition covers the CTAs of all ranks (rank r's CTA b is part r*grid+b);
+    // every rank builds the same tables from the same host structure
+    const int nranks = A->comm ? A->comm->nranks : 1;
+    const int grid = grid_per_rank * nranks;
     int32_t rc = build_internal_order(A);
     if (rc) return rc;
     if (A->pvals_version != A->vals_version && A->nnz > 0) {
@@ -212,7 +243,7 @@ int32_t nupgcm_csr_prepare(nupgcm_csr *A, int grid) {
         NUPGCM_CUDA(ctx, cudaGetLastError());
         A->pvals_version = A->vals_version;
     }
-    if (A->prepared_grid == grid) return NUPGCM_OK;
+    if (A->prepared_grid == grid && A->prepared_ranks == nranks) return NUPGCM_OK;
     NUPGCM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(A->d_part); A->d_part = nullptr;
     cudaFree(A->d_loc); A->d_loc = nullptr;
@@ -297,8 +328,56 @@ int32_t nupgcm_csr_prepare(nupgcm_csr *A, int grid) {
             A->res_max_rows = max_rows;
         }
     }
+    // halo push ranges: for every peer, the bounding range of this rank's rows it gathers
+    for (int p = 0; p < kMaxRanks; ++p) A->push_lo[p] = A->push_hi[p] = 0;
+    if (nranks > 1) {
+        const int me = A->comm->rank;
+        for (int p = 0; p < nranks; ++p)
+            if (p != me) halo_range(h_rowptr.data(), A->h_pcol, part, grid_per_rank, p, me, A->push_lo[p], A->push_hi[p]);
+    }
     A->prepared_grid = grid;
+    A->prepared_ranks = nranks;
     NUPGCM_CUDA(ctx, cudaDeviceSynchronize());   // set-up copies ran on the default stream
+    return NUPGCM_OK;
+}
+
+extern "C" int32_t nupgcm_csr_shard(nupgcm_csr *A, nupgcm_comm *comm) {
+    NUPGCM_REQUIRE(nullptr, A, "csr is NULL");
+    nupgcm_ctx *ctx = A->ctx;
+    if (comm) {
+        NUPGCM_REQUIRE(ctx, comm->ctx == ctx, "csr_shard: matrix and communicator belong to different contexts");
+        NUPGCM_REQUIRE(ctx, comm->connected, "csr_shard: communicator is not connected");
+        NUPGCM_REQUIRE(ctx, A->n_rows == A->n_cols && A->n_rows <= comm->max_n,
+                       "csr_shard: matrix must be square with n <= the communicator's max_n");
+    }
+    A->comm = (comm && comm->nranks > 1) ? comm : nullptr;
+    return nupgcm_csr_prepare(A, ctx->coop_grid);
+}
+
+extern "C" int32_t nupgcm_csr_shard_info(nupgcm_csr *A, int32_t rank, int64_t *row_begin, int64_t *row_end,
+                                         int64_t *nnz_owned, int64_t *halo_rows) {
+    NUPGCM_REQUIRE(nullptr, A, "csr is NULL");
+    nupgcm_ctx *ctx = A->ctx;
+    const int nranks = A->comm ? A->comm->nranks : 1;
+    NUPGCM_REQUIRE(ctx, rank >= 0 && rank < nranks, "csr_shard_info: rank out of range");
+    NUPGCM_REQUIRE(ctx, A->prepared_grid > 0 && A->prepared_ranks == nranks, "csr_shard_info: matrix not prepared");
+    const int gpr = A->prepared_grid / nranks;
+    std::vector<int32_t> h_rowptr(A->h_prow, A->h_prow + A->n_rows + 1), part;
+    build_partition(h_rowptr, A->n_rows, A->prepared_grid, part);
+    const int32_t q0 = part[(size_t)rank * gpr], q1 = part[(size_t)(rank + 1) * gpr];
+    if (row_begin) *row_begin = q0;
+    if (row_end) *row_end = q1;
+    if (nnz_owned) *nnz_owned = h_rowptr[q1] - h_rowptr[q0];
+    if (halo_rows) {
+        // distinct columns outside the rank's own block
+        std::vector<int32_t> cols;
+        for (int32_t k = h_rowptr[q0]; k < h_rowptr[q1]; ++k) {
+            const int32_t c = A->h_pcol[k];
+            if (c < q0 || c >= q1) cols.push_back(c);
+        }
+        std::sort(cols.begin(), cols.end());
+        *halo_rows = (int64_t)(std::unique(cols.begin(), cols.end()) - cols.begin());
+    }
     return NUPGCM_OK;
 }
 
@@ -322,6 +401,41 @@ extern "C" int32_t nupgcm_rcm_order(int64_t n, const int64_t *rowptr, const int6
     }
     rcm_order(n, rp.data(), col.data(), perm);
     for (int64_t i = 0; i < n; ++i) perm_out[i] = perm[i] + index_base;
+    return NUPGCM_OK;
+}
+
+// Host-only: how a sharded solve lays a matrix out over `nranks` ranks of `grid_per_rank` CTAs —
+// the internal ordering, the row block of every rank and every (dst, src) halo range.  The solvers
+// derive exactly this plan internally; it is exported so that hosts (and the CPU tests) can reason
+// about ownership and halo sizes without a device.
+extern "C" int32_t nupgcm_shard_plan(int64_t n, const int64_t *rowptr, const int64_t *colidx, int32_t index_base,
+                                     int32_t nranks, int32_t grid_per_rank, int64_t *perm_out,
+                                     int64_t *row_begin, int64_t *halo_lo, int64_t *halo_hi) {
+    if (n < 1 || !rowptr || !colidx || (index_base != 0 && index_base != 1) || n >= INT32_MAX ||
+        nranks < 1 || nranks > kMaxRanks || grid_per_rank < 1)
+        return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "invalid argument: %s", "shard_plan");
+    const int64_t nnz = rowptr[n] - index_base;
+    if (nnz < 0 || nnz >= INT32_MAX)
+        return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "invalid argument: %s", "shard_plan: bad nnz");
+    std::vector<int32_t> rp(n + 1), col(nnz > 0 ? nnz : 1), perm, prow, pcol, psrc, part;
+    for (int64_t i = 0; i <= n; ++i) rp[i] = (int32_t)(rowptr[i] - index_base);
+    for (int64_t k = 0; k < nnz; ++k) {
+        const int64_t c = colidx[k] - index_base;
+        if (c < 0 || c >= n) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "invalid argument: %s", "shard_plan: column out of range");
+        col[k] = (int32_t)c;
+    }
+    rcm_order(n, rp.data(), col.data(), perm);
+    permute_structure(n, rp.data(), col.data(), perm, prow, pcol, psrc);
+    build_partition(prow, n, nranks * grid_per_rank, part);
+    if (perm_out) for (int64_t i = 0; i < n; ++i) perm_out[i] = perm[i] + index_base;
+    if (row_begin) for (int r = 0; r <= nranks; ++r) row_begin[r] = part[(size_t)r * grid_per_rank];
+    for (int d = 0; d < nranks; ++d)
+        for (int s_ = 0; s_ < nranks; ++s_) {
+            int lo = 0, hi = 0;
+            if (d != s_) halo_range(prow.data(), pcol.data(), part, grid_per_rank, d, s_, lo, hi);
+            if (halo_lo) halo_lo[d * nranks + s_] = lo;
+            if (halo_hi) halo_hi[d * nranks + s_] = hi;
+        }
     return NUPGCM_OK;
 }
 

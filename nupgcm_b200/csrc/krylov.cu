@@ -69,6 +69,11 @@ struct KrylovArgs {
     double *hist;
     long long hist_cap;
     double *result;          // niter, solved, inconsistent, breakdown, rnorm, rnorm0, hist_len, aborted
+    // sharded solves (nranks > 1): this rank's CTA b is part `rank * gridDim.x + b` of the partition
+    int rank, nranks;
+    unsigned xgen_base;      // sequence number of the communicator's inter-rank reductions so far
+    char *arena[kMaxRanks];  // exchange arenas of all ranks as mapped here (common.cuh: nupgcm_comm)
+    int push_lo[kMaxRanks], push_hi[kMaxRanks];   // rows of this rank that peer p's SpMV gathers
 };
 
 // Watchdog of every cross-CTA wait: a CTA that waits longer than this raises the abort word and
@@ -97,23 +102,38 @@ struct LLSlot {
     unsigned long long a, b;
 };
 
-template <bool RELEASE>
+// SYS = true: system scope — the word lives in (or is read by) another GPU's memory over NVLink.
+template <bool RELEASE, bool SYS = false>
 __device__ __forceinline__ void ll_store(LLSlot *p, double v, unsigned flag) {
     const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
     const unsigned long long a = (bits & 0xffffffffULL) | ((unsigned long long)flag << 32);
     const unsigned long long b = (bits >> 32) | ((unsigned long long)flag << 32);
-    if (RELEASE)
-        asm volatile("st.release.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
-    else
-        asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+    if (SYS) {
+        if (RELEASE)
+            asm volatile("st.release.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+        else
+            asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+    } else {
+        if (RELEASE)
+            asm volatile("st.release.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+        else
+            asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+    }
 }
 
-template <bool ACQUIRE>
+template <bool ACQUIRE, bool SYS = false>
 __device__ __forceinline__ void ll_load_raw(const LLSlot *p, unsigned long long &a, unsigned long long &b) {
-    if (ACQUIRE)
-        asm volatile("ld.acquire.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
-    else
-        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+    if (SYS) {
+        if (ACQUIRE)
+            asm volatile("ld.acquire.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+        else
+            asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+    } else {
+        if (ACQUIRE)
+            asm volatile("ld.acquire.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+        else
+            asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+    }
 }
 
 static const unsigned kTraceStart = 2000, kTraceWindow = 256, kTraceStamps = 6;   // reductions recorded by the debug trace
@@ -162,18 +182,18 @@ __host__ __device__ inline size_t exch_bank_slots(int gpad) {
 }
 
 // Wait (with watchdog) until the flagged word at p carries `gen`; returns its value.
-template <bool ACQUIRE>
+template <bool ACQUIRE, bool SYS = false>
 __device__ __forceinline__ double wait_flagged(const LLSlot *p, unsigned gen, unsigned long long *abort_word, bool &bad) {
     unsigned long long a, b;
     unsigned spins = 0;
     unsigned long long t0 = 0;
     for (;;) {
-        ll_load_raw<ACQUIRE>(p, a, b);
+        ll_load_raw<ACQUIRE, SYS>(p, a, b);
         if ((unsigned)(a >> 32) == gen && (unsigned)(b >> 32) == gen)
             return __longlong_as_double((long long)((a & 0xffffffffULL) | (b << 32)));
         if ((++spins & 255u) == 0) {
             unsigned long long fl;
-            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(fl) : "l"(abort_word) : "memory");
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(fl) : "l"(abort_word) : "memory");
             const unsigned long long now = global_timer_ns();
             if (t0 == 0) t0 = now;
             if (fl != 0 || now - t0 > kWaitTimeoutNs) {
@@ -189,8 +209,21 @@ __device__ __forceinline__ double wait_flagged(const LLSlot *p, unsigned gen, un
 // slots, one per comm lane; lanes are combined by an xor-shuffle tree and warps in index order —
 // a fixed summation order, identical in every CTA.  PUBLISH uses release stores / acquire loads so
 // that the global-memory rows written by the CTA before the call are visible to all CTAs after it.
-template <bool PUBLISH>
-__device__ __forceinline__ bool comm_sum1(CommMailbox *mb, LLSlot *bank_base, unsigned long long *abort_word,
+// Inter-rank slot of the exchange arena (common.cuh): value `val`, replica `rep`, written by `rank`.
+__device__ __forceinline__ LLSlot *xr_slot(char *arena, unsigned bank, int val, int rep, int rank) {
+    return reinterpret_cast<LLSlot *>(arena + kArenaXrOffset) +
+           (((size_t)bank * kPartialSlots + val) * kXRep + rep) * kMaxRanks + rank;
+}
+
+// MR (multi-rank, sharded solves): the all-to-all below yields the sum over THIS rank's CTAs in
+// every CTA; CTA 0 then stores it into every rank's arena (kXRep replicas, one remote 16-byte store
+// per comm lane — over NVLink for the peers) and every CTA adds the nranks words of its own arena in
+// rank order.  All CTAs of all ranks obtain bit-identical totals, so the ranks' scalar recurrences
+// and branches stay in lockstep without any further synchronisation.  Flags of the inter-rank
+// words are xgen = (communicator sequence number) + gen: these words are never zeroed between
+// solves (a peer may already be writing the next solve's first word), and their bank is xgen & 1.
+template <bool PUBLISH, bool MR>
+__device__ __forceinline__ bool comm_sum1(CommMailbox *mb, const KrylovArgs &a, LLSlot *bank_base, unsigned long long *abort_word,
                                           unsigned long long *trow, bool tr, unsigned gen, int grid, int gpad,
                                           int nrep) {
     const int ct = threadIdx.x - kMainThreads, cw = ct >> 5, lane = ct & 31;
@@ -216,11 +249,31 @@ __device__ __forceinline__ bool comm_sum1(CommMailbox *mb, LLSlot *bank_base, un
     if (tr) trow[3 * (size_t)grid] = global_timer_ns();
     named_sync(NUPGCM_BAR_COMM, kCommThreads);
     if (tr) trow[4 * (size_t)grid] = global_timer_ns();
-    if (ct == 0) {
-        const int npw = (grid + 31) >> 5;
-        double total = 0.0;
-        for (int g = 0; g < npw; ++g) total += mb->part[0][g];
-        mb->out[0] = total;
+    const int npw = (grid + 31) >> 5;
+    if constexpr (MR) {
+        const unsigned xgen = a.xgen_base + gen, xbank = xgen & 1u;
+        if (bid == 0 && ct < a.nranks * kXRep) {
+            double total = 0.0;
+            for (int g = 0; g < npw; ++g) total += mb->part[0][g];
+            ll_store<PUBLISH, true>(xr_slot(a.arena[ct % a.nranks], xbank, kPartialSlots - 1, ct / a.nranks, a.rank), total, xgen);
+        }
+        if (cw == 0) {
+            bool xbad = false;
+            double xv = 0.0;
+            if (lane < a.nranks)
+                xv = wait_flagged<PUBLISH, true>(xr_slot(a.arena[a.rank], xbank, kPartialSlots - 1, bid % kXRep, lane), xgen, abort_word, xbad);
+            double total = 0.0;
+            for (int r = 0; r < a.nranks; ++r) total += __shfl_sync(0xffffffffu, xv, r);
+            if (lane == 0) mb->out[0] = total;
+            if (xbad) mb->dead = 1;
+            bad = bad || xbad;
+        }
+    } else {
+        if (ct == 0) {
+            double total = 0.0;
+            for (int g = 0; g < npw; ++g) total += mb->part[0][g];
+            mb->out[0] = total;
+        }
     }
     return bad;
 }
@@ -231,7 +284,10 @@ __device__ __forceinline__ bool comm_sum1(CommMailbox *mb, LLSlot *bank_base, un
 // `count` totals of one replica.  An all-to-all of count values would issue grid² x count sector
 // reads per poll round (438 k at 148 CTAs x 20 values) against a few hundred cache lines and was
 // measured at 6-12 us; this form issues (grid + copies) x count.
-__device__ __forceinline__ bool comm_sumN(CommMailbox *mb, LLSlot *bank_base, unsigned long long *abort_word,
+// MR: the reducer CTA of value j exchanges its rank's total with the reducer CTAs of value j on the
+// other ranks (one remote store per peer), adds the nranks totals in rank order and broadcasts.
+template <bool MR>
+__device__ __forceinline__ bool comm_sumN(CommMailbox *mb, const KrylovArgs &a, LLSlot *bank_base, unsigned long long *abort_word,
                                           unsigned long long *trow, bool tr, unsigned gen, int grid, int gpad,
                                           int count) {
     const int ct = threadIdx.x - kMainThreads, cw = ct >> 5, lane = ct & 31;
@@ -248,8 +304,21 @@ __device__ __forceinline__ bool comm_sumN(CommMailbox *mb, LLSlot *bank_base, un
         v = warp_sum(v);
         if (lane == 0) mb->part[0][cw] = v;
         named_sync(NUPGCM_BAR_COMM, kCommThreads);
-        if (ct < kBcastCopies) {
-            const int npw = (grid + 31) >> 5;
+        const int npw = (grid + 31) >> 5;
+        if constexpr (MR) {
+            const unsigned xgen = a.xgen_base + gen, xbank = xgen & 1u;
+            if (ct < a.nranks) {
+                double mine = 0.0;
+                for (int g = 0; g < npw; ++g) mine += mb->part[0][g];
+                ll_store<false, true>(xr_slot(a.arena[ct], xbank, bid, 0, a.rank), mine, xgen);
+            }
+            if (ct < kBcastCopies) {
+                double total = 0.0;
+                for (int r = 0; r < a.nranks; ++r)
+                    total += wait_flagged<false, true>(xr_slot(a.arena[a.rank], xbank, bid, 0, r), xgen, abort_word, bad);
+                ll_store<false>(res + (size_t)ct * kBcastStride + bid, total, gen);
+            }
+        } else if (ct < kBcastCopies) {
             double total = 0.0;
             for (int g = 0; g < npw; ++g) total += mb->part[0][g];
             ll_store<false>(res + (size_t)ct * kBcastStride + bid, total, gen);
@@ -265,9 +334,11 @@ __device__ __forceinline__ bool comm_sumN(CommMailbox *mb, LLSlot *bank_base, un
 
 // Service loop of the comm warps: one request per grid-wide reduction, until the main warps post
 // the exit request.
+template <bool MR = false>
 __device__ __forceinline__ void comm_warp_loop(CommMailbox *mb, const KrylovArgs &a, int nrep) {
     LLSlot *slots = reinterpret_cast<LLSlot *>(a.partials);
-    unsigned long long *abort_word = a.barrier + 1;
+    // sharded solves watch the arena's abort word, which every rank can raise
+    unsigned long long *abort_word = MR ? reinterpret_cast<unsigned long long *>(a.arena[a.rank]) : a.barrier + 1;
     const int grid = gridDim.x, gpad = (grid + 7) & ~7;
     const int ct = threadIdx.x - kMainThreads;
     unsigned gen = 0;
@@ -283,10 +354,15 @@ __device__ __forceinline__ void comm_warp_loop(CommMailbox *mb, const KrylovArgs
             if (tr) trow[1 * (size_t)grid] = global_timer_ns();        // request seen by the comm warps
             LLSlot *bank_base = slots + (size_t)(gen & 1) * exch_bank_slots(gpad);
             bool bad;
-            if (count > 1) bad = comm_sumN(mb, bank_base, abort_word, trow, tr, gen, grid, gpad, count);
-            else if (mb->publish) bad = comm_sum1<true>(mb, bank_base, abort_word, trow, tr, gen, grid, gpad, nrep);
-            else bad = comm_sum1<false>(mb, bank_base, abort_word, trow, tr, gen, grid, gpad, nrep);
+            if (count > 1) bad = comm_sumN<MR>(mb, a, bank_base, abort_word, trow, tr, gen, grid, gpad, count);
+            else if (mb->publish) bad = comm_sum1<true, MR>(mb, a, bank_base, abort_word, trow, tr, gen, grid, gpad, nrep);
+            else bad = comm_sum1<false, MR>(mb, a, bank_base, abort_word, trow, tr, gen, grid, gpad, nrep);
             dead = __any_sync(0xffffffffu, bad) || mb->dead != 0;
+            if (MR && dead && (ct & 31) == 0) {
+                // take the other ranks down too: their waits poll their own arena's abort word
+                for (int r = 0; r < a.nranks; ++r)
+                    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(a.arena[r]), "l"(1ULL) : "memory");
+            }
         }
         named_arrive(NUPGCM_BAR_RSP, kThreads);
     }
@@ -298,11 +374,13 @@ struct GridReduce {
     unsigned long long *trace;
     unsigned gen;
     bool dead;
-    __device__ __forceinline__ void init(CommMailbox *m, unsigned long long *tr = nullptr) {
+    bool mr;                         // sharded solve: rows were also stored into peer GPUs' memory
+    __device__ __forceinline__ void init(CommMailbox *m, unsigned long long *tr = nullptr, bool multi_rank = false) {
         mb = m;
         trace = tr;
         gen = 0;
         dead = false;
+        mr = multi_rank;
     }
     __device__ __forceinline__ bool aborted() const { return dead; }
     __device__ __forceinline__ void round_trip() {
@@ -320,6 +398,8 @@ struct GridReduce {
     // kMainWarps warp partials.
     template <bool PUBLISH>
     __device__ __forceinline__ double sum_threads(double v) {
+        // remote (NVLink) row stores of this thread must be performed before the flag chain starts
+        if (PUBLISH && mr) __threadfence_system();
         v = warp_sum(v);
         if ((threadIdx.x & 31) == 0) mb->wpart[threadIdx.x >> 5] = v;
         if (threadIdx.x == 0) { mb->count = 1; mb->from_warps = 1; mb->publish = PUBLISH ? 1 : 0; }
@@ -334,6 +414,7 @@ struct GridReduce {
     }
     // Grid barrier that publishes this CTA's global-memory rows.
     __device__ __forceinline__ void barrier() {
+        if (mr) __threadfence_system();
         if (threadIdx.x == 0) { mb->count = 0; mb->from_warps = 0; mb->in[0] = 0.0; mb->publish = 1; }
         round_trip();
     }
@@ -422,8 +503,9 @@ struct SpmvEngine {
             const ResidentLayout &L = a.lay;
             uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L.bar);
             const int k0 = a.rowptr[r0], k1 = a.rowptr[r1];
-            const int f0 = a.foot_ptr[2 * blockIdx.x];
-            nfoot = a.foot_ptr[2 * blockIdx.x + 1];
+            const int lb = a.rank * gridDim.x + blockIdx.x;   // position in the partition (all ranks)
+            const int f0 = a.foot_ptr[2 * lb];
+            nfoot = a.foot_ptr[2 * lb + 1];
             const int ka = k0 & ~1, kc = k0 & ~7, ra = r0 & ~3;
             const uint32_t bf = (uint32_t)(((nfoot + 3) & ~3) * 4);
             const uint32_t bv = (uint32_t)(((k1 - ka + 1) & ~1) * 8);
@@ -566,7 +648,7 @@ struct SpmvEngine<T, false> {
         nch = k1 > k0 ? (k1 - kbase + kStreamChunk - 1) / kStreamChunk : 0;
         const int ra = r0 & ~3;
         const uint32_t br = (uint32_t)(((r1 + 1 - ra + 3) & ~3) * 4);
-        const int cp0 = a.chunk_ptr[blockIdx.x];
+        const int cp0 = a.chunk_ptr[a.rank * gridDim.x + blockIdx.x];
         const int ca = cp0 & ~3;
         const uint32_t bi = (uint32_t)(((cp0 + nch - ca + 3) & ~3) * 4);
         uint64_t *setup_bar = bars + 2 * kStreamStages;
@@ -726,40 +808,108 @@ struct VecSlices {
     __device__ __forceinline__ double *at(int i) const { return base + (size_t)i * stride; }
 };
 
+// ---- halo push (sharded solves) ----------------------------------------------------------------
+// Vectors that other CTAs gather from (the raw Krylov vector, CG's p, the iterate) live in the
+// rank's exchange arena.  A rank's SpMV also gathers rows owned by other ranks (its halo); those are
+// PUSHED by their owner: whenever a CTA stores row i of such a vector it also stores it, over
+// NVLink, at the same arena offset in every peer whose halo range contains i.  The data is in the
+// reader's own memory before the flag of the next publishing reduction arrives, so no gather ever
+// crosses the link (remote loads would put ~2 us of latency into every SpMV).
+template <bool MR>
+struct HaloPush;
+template <>
+struct HaloPush<false> {
+    __device__ __forceinline__ void init(const KrylovArgs &, int, int, int *, char **) {}
+    __device__ __forceinline__ void put_all(const double *, double) const {}
+};
+template <>
+struct HaloPush<true> {
+    const int *range;       // shared: [2*j], [2*j+1] row range of active peer j (intersected with the CTA's rows)
+    char *const *dest;      // shared: arena of active peer j
+    const char *local;
+    char *const *all;       // arenas of all ranks
+    int np, rank, nranks, row_bias;
+    // `sh_range` (2*kMaxRanks ints) and `sh_dest` (kMaxRanks pointers) are shared-memory scratch;
+    // call from all threads, followed by a CTA barrier before the first put().
+    __device__ __forceinline__ void init(const KrylovArgs &a, int r0, int r1, int *sh_range, char **sh_dest) {
+        int cnt = 0;
+        for (int p = 0; p < a.nranks; ++p) {
+            if (p == a.rank) continue;
+            const int lo = max(r0, a.push_lo[p]), hi = min(r1, a.push_hi[p]);
+            if (lo < hi) {
+                if (threadIdx.x == 0) { sh_range[2 * cnt] = lo; sh_range[2 * cnt + 1] = hi; sh_dest[cnt] = a.arena[p]; }
+                cnt++;
+            }
+        }
+        np = cnt;
+        range = sh_range;
+        dest = sh_dest;
+        local = a.arena[a.rank];
+        all = a.arena;
+        rank = a.rank;
+        nranks = a.nranks;
+    }
+    // p_local = address of the row's entry in the LOCAL arena; row = p_local's row index is
+    // recovered from the vector base by the caller: pass the row explicitly.
+    __device__ __forceinline__ void put_row(const double *p_local, int row, double v) const {
+        for (int j = 0; j < np; ++j)
+            if (row >= range[2 * j] && row < range[2 * j + 1])
+                *reinterpret_cast<double *>(dest[j] + (reinterpret_cast<const char *>(p_local) - local)) = v;
+    }
+    // store to every peer (the all-gather that ends a solve)
+    __device__ __forceinline__ void put_all(const double *p_local, double v) const {
+        for (int p = 0; p < nranks; ++p)
+            if (p != rank)
+                *reinterpret_cast<double *>(all[p] + (reinterpret_cast<const char *>(p_local) - local)) = v;
+    }
+};
+template <bool MR>
+__device__ __forceinline__ void halo_put(const HaloPush<MR> &hp, const double *p_local, int row, double v) {
+    if constexpr (MR) hp.put_row(p_local, row, v);
+}
+
 // =============================================================================================
 // CG  (Krylov.jl cg!)
 // =============================================================================================
-template <int T, bool RES>
+template <int T, bool RES, bool MR>
 __global__ void __launch_bounds__(kThreads, 1) k_cg(const __grid_constant__ KrylovArgs a) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ CommMailbox mailbox;
+    __shared__ int s_prange[2 * kMaxRanks];
+    __shared__ char *s_pdest[kMaxRanks];
     if (threadIdx.x == 0) mailbox.dead = 0;
-    const int r0 = a.part[blockIdx.x], r1 = a.part[blockIdx.x + 1];
+    const int lb = a.rank * gridDim.x + blockIdx.x;       // position in the partition (all ranks)
+    const int r0 = a.part[lb], r1 = a.part[lb + 1];
     SpmvEngine<T, RES> eng(a, r0, r1, dyn_smem);          // all warps take part in the bulk copy
+    HaloPush<MR> hp;
+    hp.init(a, r0, r1, s_prange, s_pdest);
     __syncthreads();
     if (threadIdx.x >= kMainThreads) {                     // comm warps: exchange service only
-        comm_warp_loop(&mailbox, a, a.poll_depth);
+        comm_warp_loop<MR>(&mailbox, a, a.poll_depth);
         return;
     }
     GridReduce gr;
-    gr.init(&mailbox, a.trace);
+    gr.init(&mailbox, a.trace, MR);
     const int n = a.n;
     // CTA-local vectors: r, Ap, local copy of p, the iterate, the Jacobi diagonal
     VecSlices loc(a, dyn_smem, a.work + n, r0);       // global fallback: work[n .. 6n)
     double *r = loc.at(0), *Ap = loc.at(1), *pl = loc.at(2), *xl = loc.at(3), *dl = loc.at(4);
-    double *pg = a.work;                               // p as the other CTAs gather it
+    // vectors the other CTAs gather: in the exchange arena when the solve is sharded
+    double *xbase = MR ? reinterpret_cast<double *>(a.arena[a.rank] + kArenaVecOffset) : nullptr;
+    double *pg = MR ? xbase : a.work;                  // p as the other CTAs gather it
     const double eps = 2.220446049250313e-16;
     const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
     const int tid = threadIdx.x, nthr = kMainThreads;
     long long nhist = 0;
 
     // vectors cross the ABI in caller order; internally rows follow the reordered matrix
-    double *xi = a.work + 6 * (size_t)n;               // Δx in internal order, gathered by all CTAs
+    double *xi = MR ? xbase + n : a.work + 6 * (size_t)n;   // Δx in internal order, gathered by all CTAs
     for (int row = r0 + tid; row < r1; row += nthr) {
         const int src = a.perm[row];
         const double x0 = a.x[src];                    // Δx, the warm start
         xl[row] = x0;
         xi[row] = x0;
+        halo_put(hp, xi + row, row, x0);
         dl[row] = a.dinv ? a.dinv[src] : a.pscale;
     }
     gr.barrier();
@@ -771,6 +921,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg(const __grid_constant__ Kryl
         r[row] = rv;
         pl[row] = zv;
         pg[row] = zv;
+        halo_put(hp, pg + row, row, zv);
         part = fma(rv, zv, part);
     });
     double gamma = gr.sum_threads<true>(part);      // also publishes p for the first SpMV
@@ -823,13 +974,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg(const __grid_constant__ Kryl
                 const double pv = fma(beta, pl[row], dl[row] * r[row]);
                 pl[row] = pv;
                 pg[row] = pv;
+                halo_put(hp, pg + row, row, pv);
             }
             gr.barrier();
         }
         iter++;
         tired = iter >= itmax;
     }
-    for (int row = r0 + tid; row < r1; row += nthr) a.x[a.perm[row]] = xl[row];
+    if constexpr (MR) {
+        // all-gather of the solution: every rank receives every row, then scatters all rows to
+        // caller order, so x is complete (replicated) on every rank when the solve returns
+        for (int row = r0 + tid; row < r1; row += nthr) {
+            const double xv = xl[row];
+            xi[row] = xv;
+            hp.put_all(xi + row, xv);
+        }
+        gr.barrier();
+        for (int row = blockIdx.x * nthr + tid; row < n; row += gridDim.x * nthr) a.x[a.perm[row]] = ld_cg(xi + row);
+        gr.barrier();      // no rank leaves (and lets the next solve reuse the arena) before all have read it
+    } else {
+        for (int row = r0 + tid; row < r1; row += nthr) a.x[a.perm[row]] = xl[row];
+    }
+    if (lead) a.result[13] = (double)gr.gen;
     gr.finish();
     if (lead) {
         a.result[0] = (double)iter;
@@ -914,7 +1080,7 @@ __device__ __forceinline__ double precond(const KrylovArgs &a, int row, double v
     return a.dinv ? __ldg(a.dinv + __ldg(a.perm + row)) * v : a.pscale * v;
 }
 
-template <int T, bool RES, bool PROF>
+template <int T, bool RES, bool PROF, bool MR>
 __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ KrylovArgs a) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ CommMailbox mailbox;
@@ -922,28 +1088,39 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
     __shared__ double sR[kMaxMemory * (kMaxMemory + 1) / 2];
     __shared__ double s_flags[4];      // rnorm, inconsistent, -, Hbis
     __shared__ double s_seg[32];
+    __shared__ int s_prange[2 * kMaxRanks];
+    __shared__ char *s_pdest[kMaxRanks];
 
     if (threadIdx.x == 0) mailbox.dead = 0;
-    const int r0 = a.part[blockIdx.x], r1 = a.part[blockIdx.x + 1];
+    const int lb = a.rank * gridDim.x + blockIdx.x;       // position in the partition (all ranks)
+    const int r0 = a.part[lb], r1 = a.part[lb + 1];
     SpmvEngine<T, RES> eng(a, r0, r1, dyn_smem);          // all warps take part in the bulk copy
+    HaloPush<MR> hp;
+    hp.init(a, r0, r1, s_prange, s_pdest);
     __syncthreads();
     if (threadIdx.x >= kMainThreads) {                     // comm warps: exchange service only
-        comm_warp_loop(&mailbox, a, a.poll_depth);
+        comm_warp_loop<MR>(&mailbox, a, a.poll_depth);
         return;
     }
     GridReduce gr;
-    gr.init(&mailbox, a.trace);
+    gr.init(&mailbox, a.trace, MR);
     double *sm_in = mailbox.in, *sm_out = mailbox.out;
     const int n = a.n;
     const int mem = a.mem;
     VecSlices V(a, dyn_smem, a.work, r0);                // V.at(i), i = 0..mem: CTA-local basis rows
-    double *qbuf = a.work + (size_t)(mem + 1) * n;       // two raw buffers for the SpMV gather (global)
-    double *x = a.work + (size_t)(mem + 3) * n;          // iterate in internal order (gathered by all CTAs)
+    // vectors the other CTAs gather: in the exchange arena when the solve is sharded
+    double *xbase = MR ? reinterpret_cast<double *>(a.arena[a.rank] + kArenaVecOffset) : a.work + (size_t)(mem + 1) * n;
+    double *qbuf = xbase;                                // two raw buffers for the SpMV gather (global)
+    double *x = xbase + 2 * (size_t)n;                   // iterate in internal order (gathered by all CTAs)
     const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
     const int tid = threadIdx.x, nthr = kMainThreads;
     const int lane = tid & 31, wid = tid >> 5, nwarps = kMainWarps;
     // vectors cross the ABI in caller order; internally rows follow the reordered matrix
-    for (int row = r0 + tid; row < r1; row += nthr) x[row] = a.x[a.perm[row]];
+    for (int row = r0 + tid; row < r1; row += nthr) {
+        const double xv = a.x[a.perm[row]];
+        x[row] = xv;
+        halo_put(hp, x + row, row, xv);
+    }
     gr.barrier();
     const double btol = 1.8189894035458565e-12;          // eps^(3/4)
     long long nhist = 0;
@@ -960,6 +1137,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
         eng.run(x, [&](int row, double ax) {
             const double v = precond(a, row, a.b[a.perm[row]] - ax);
             q0[row] = v;
+            halo_put(hp, q0 + row, row, v);
             v0[row] = v;
             part = fma(v, v, part);
         });
@@ -991,6 +1169,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
             eng.run(x, [&](int row, double ax) {
                 const double v = precond(a, row, a.b[a.perm[row]] - ax);
                 q0[row] = v;
+                halo_put(hp, q0 + row, row, v);
                 v0[row] = v;
                 part = fma(v, v, part);
             });
@@ -1042,6 +1221,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
                     const double qv = fma(-hprev, vp[row], q[row]);
                     q[row] = qv;
                     dst[row] = qv;
+                    halo_put(hp, dst + row, row, qv);
                     part = fma(qv, qv, part);
                 }
                 pc.mark(1);
@@ -1080,7 +1260,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
                         double qv = q[row];
                         for (int i = 0; i < k; ++i) qv = fma(-sm_out[i], V.at(i)[row], qv);
                         q[row] = qv;
-                        if (pass == 1) { dst[row] = qv; part = fma(qv, qv, part); }
+                        if (pass == 1) { dst[row] = qv; halo_put(hp, dst + row, row, qv); part = fma(qv, qv, part); }
                     }
                     if (tid < k) sR[nr + tid] = (pass == 0) ? sm_out[tid] : sR[nr + tid] + sm_out[tid];
                     if (pass == 1) {
@@ -1148,7 +1328,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
         for (int row = r0 + tid; row < r1; row += nthr) {
             double xr = 0.0;
             for (int i = 0; i < k; ++i) xr = fma(sy[i], V.at(i)[row], xr);
-            x[row] += xr;
+            const double xv = x[row] + xr;
+            x[row] = xv;
+            halo_put(hp, x + row, row, xv);
         }
         inner_itmax -= k;
         iter += k;
@@ -1159,7 +1341,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
             cur = 0;
         }
     }
-    for (int row = r0 + tid; row < r1; row += nthr) a.x[a.perm[row]] = x[row];
+    if constexpr (MR) {
+        // all-gather of the solution (see k_cg)
+        for (int row = r0 + tid; row < r1; row += nthr) hp.put_all(x + row, x[row]);
+        gr.barrier();
+        for (int row = blockIdx.x * nthr + tid; row < n; row += gridDim.x * nthr) a.x[a.perm[row]] = ld_cg(x + row);
+        gr.barrier();
+    } else {
+        for (int row = r0 + tid; row < r1; row += nthr) a.x[a.perm[row]] = x[row];
+    }
+    if (lead) a.result[13] = (double)gr.gen;
     gr.finish();
     if (lead) {
         a.result[0] = (double)iter;
@@ -1212,24 +1403,18 @@ static int persistent_tpr(const nupgcm_csr *A, bool resident, int grid) {
     return std::min(t, 32);
 }
 
-struct Workspace {
-    double *d;
-    size_t bytes;
-};
-static Workspace g_ws = {nullptr, 0};   // grown on demand, one per process (contexts are serialised)
-
 static int32_t ensure_workspace(nupgcm_ctx *ctx, size_t bytes) {
-    if (g_ws.bytes >= bytes) return NUPGCM_OK;
-    if (g_ws.d) {
+    if (ctx->ws_bytes >= bytes) return NUPGCM_OK;
+    if (ctx->d_ws) {
         NUPGCM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        cudaFree(g_ws.d);
-        g_ws.d = nullptr;
-        g_ws.bytes = 0;
+        cudaFree(ctx->d_ws);
+        ctx->d_ws = nullptr;
+        ctx->ws_bytes = 0;
     }
-    cudaError_t e = cudaMalloc(&g_ws.d, bytes);
+    cudaError_t e = cudaMalloc(&ctx->d_ws, bytes);
     if (e != cudaSuccess)
         return nupgcm_fail(ctx, NUPGCM_ERR_ALLOC, "device allocation failed: %s", cudaGetErrorString(e));
-    g_ws.bytes = bytes;
+    ctx->ws_bytes = bytes;
     return NUPGCM_OK;
 }
 
@@ -1238,12 +1423,22 @@ static cudaError_t launch2(bool gmres, KrylovArgs &args, nupgcm_ctx *ctx, size_t
     void *params[] = {&args};
     const char *ep = getenv("NUPGCM_PROFILE");
     const bool prof = ep && atoi(ep) != 0;
-    const void *fn = gmres ? (prof ? (const void *)k_gmres<T, RES, true> : (const void *)k_gmres<T, RES, false>)
-                           : (const void *)k_cg<T, RES>;
+    const bool mr = args.nranks > 1;
+    const void *fn;
+    if (gmres) {
+        if (mr) fn = (const void *)k_gmres<T, RES, false, true>;
+        else fn = prof ? (const void *)k_gmres<T, RES, true, false> : (const void *)k_gmres<T, RES, false, false>;
+    } else {
+        fn = mr ? (const void *)k_cg<T, RES, true> : (const void *)k_cg<T, RES, false>;
+    }
     if (smem > 0) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
+    // cooperative launch = co-residency guarantee (the kernels never call grid.sync()); NUPGCM_COOP=0
+    // uses a plain launch, for experiments with several contexts sharing a device
+    const char *ec = getenv("NUPGCM_COOP");
+    if (ec && atoi(ec) == 0) return cudaLaunchKernel(fn, dim3(grid), dim3(kThreads), params, smem, ctx->stream);
     return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), params, smem, ctx->stream);
 }
 
@@ -1324,6 +1519,15 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
         if (stats) { memset(stats, 0, sizeof(*stats)); stats->solved = 1; }
         return NUPGCM_OK;
     }
+    nupgcm_comm *comm = A->comm;
+    const int nranks = comm ? comm->nranks : 1;
+    if (comm) {
+        NUPGCM_REQUIRE(ctx, comm->connected, "solve: communicator is not connected");
+        NUPGCM_REQUIRE(ctx, !comm->broken, "solve: communicator is unusable after an aborted sharded solve");
+        NUPGCM_REQUIRE(ctx, n <= comm->max_n, "solve: system larger than the communicator's max_n");
+    }
+    if (gmres && orth == NUPGCM_ORTH_CGS2)
+        NUPGCM_REQUIRE(ctx, grid >= memory, "gmres: CGS2 needs at least `memory` CTAs (one reducer per projection)");
     NUPGCM_CUDA(ctx, cudaSetDevice(ctx->device));
     int32_t rcp = nupgcm_csr_prepare(const_cast<nupgcm_csr *>(A), grid);
     if (rcp) return rcp;
@@ -1357,7 +1561,15 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
     args.pscale = pscale;
     args.b = y->d;
     args.x = x->d;
-    args.work = g_ws.d;
+    args.work = ctx->d_ws;
+    args.rank = comm ? comm->rank : 0;
+    args.nranks = nranks;
+    args.xgen_base = comm ? comm->xgen : 0;
+    for (int p = 0; p < nranks && comm; ++p) {
+        args.arena[p] = comm->peer[p];
+        args.push_lo[p] = A->push_lo[p];
+        args.push_hi[p] = A->push_hi[p];
+    }
     args.atol = atol;
     args.rtol = rtol;
     args.itmax = itmax;
@@ -1383,7 +1595,7 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
     NUPGCM_CUDA(ctx, cudaEventRecord(ctx->sev0, ctx->stream));
     cudaError_t e;
     const size_t smem = (size_t)args.lay.total;
-    switch (persistent_tpr(A, resident || args.lay.streaming, grid)) {
+    switch (persistent_tpr(A, resident || args.lay.streaming, grid * nranks)) {
         case 32: e = launch<32>(gmres, args, ctx, smem, grid, resident); break;
         case 16: e = launch<16>(gmres, args, ctx, smem, grid, resident); break;
         case 8: e = launch<8>(gmres, args, ctx, smem, grid, resident); break;
@@ -1393,10 +1605,21 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
     NUPGCM_CUDA(ctx, e);
     ctx->launches++;
     NUPGCM_CUDA(ctx, cudaEventRecord(ctx->sev1, ctx->stream));
-    NUPGCM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 13 * sizeof(double),
+    NUPGCM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 14 * sizeof(double),
                                      cudaMemcpyDeviceToHost, ctx->stream));
-    NUPGCM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    {
+        cudaError_t es = cudaStreamSynchronize(ctx->stream);
+        if (es != cudaSuccess) {
+            if (comm) comm->broken = 1;
+            NUPGCM_CUDA(ctx, es);
+        }
+    }
     const double *res = ctx->h_scalars;
+    if (comm) {
+        // all ranks executed the same reductions: the communicator's sequence number advances in step
+        if (res[7] != 0.0) comm->broken = 1;
+        else comm->xgen += (unsigned)res[13];
+    }
     if (d_trace) {
         unsigned long long *h = (unsigned long long *)malloc(trace_words * sizeof(unsigned long long));
         cudaMemcpy(h, d_trace, trace_words * sizeof(unsigned long long), cudaMemcpyDeviceToHost);

@@ -52,6 +52,8 @@ class EvolutionToolkit:
         nb = ops["M"].shape[0]
         # LHS storage with the shared pattern; values filled by collect_evolution_LHS_
         self._A = on_architecture(arch, ops["M"])
+        if getattr(arch, "comm", None) is not None:
+            self._A.shard(arch.comm)                            # CG becomes collective over the ranks
         self._dinv = arch.ctx.vector(nb)
         y = arch.ctx.vector(nb)
         x = arch.ctx.vector(nb)

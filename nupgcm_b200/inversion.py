@@ -55,6 +55,8 @@ class InversionToolkit:
         self.B = on_architecture(arch, B, drop_zeros=True)      # zeros of B never change
         self.b = on_architecture(arch, b)
         A_dev = on_architecture(arch, A, drop_zeros=drop_zeros)
+        if getattr(arch, "comm", None) is not None:
+            A_dev.shard(arch.comm)                              # GMRES becomes collective over the ranks
         N = A.shape[0]
         y = arch.ctx.vector(N)
         x = arch.ctx.vector(N)                                  # workspace.x .= 0 (inversion.jl:85)

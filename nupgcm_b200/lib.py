@@ -40,6 +40,14 @@ SIGNATURES = {
     "nupgcm_create": [c_int32, POINTER(_P)],
     "nupgcm_destroy": [_P],
     "nupgcm_synchronize": [_P],
+    "nupgcm_set_grid": [_P, c_int32],
+    "nupgcm_comm_create": [_P, c_int32, c_int32, c_int64, POINTER(_P)],
+    "nupgcm_comm_destroy": [_P],
+    "nupgcm_comm_ipc_handle": [_P, c_void_p],
+    "nupgcm_comm_connect_ipc": [_P, c_void_p],
+    "nupgcm_comm_connect_local": [_P, POINTER(_P)],
+    "nupgcm_csr_shard": [_P, _P],
+    "nupgcm_csr_shard_info": [_P, c_int32, _ip, _ip, _ip, _ip],
     "nupgcm_mem_status": [_P, POINTER(c_size_t), POINTER(c_size_t)],
     "nupgcm_device_info": [_P, _i32p, _i32p, _i32p, c_char_p],
     "nupgcm_timer_start": [_P],
@@ -67,6 +75,7 @@ SIGNATURES = {
     "nupgcm_csr_combine": [_P, _P, _P, _P, c_double],
     "nupgcm_csr_inv_diag": [_P, _P],
     "nupgcm_rcm_order": [c_int64, _ip, _ip, c_int32, _ip],
+    "nupgcm_shard_plan": [c_int64, _ip, _ip, c_int32, c_int32, c_int32, _ip, _ip, _ip, _ip],
     "nupgcm_spmv": [_P, _P, _P, c_double, c_double],
     "nupgcm_cg_solve": [_P, _P, c_double, _P, _P, c_double, c_double, c_int64, _dp, c_int64,
                         POINTER(SolveStats)],
@@ -139,6 +148,11 @@ class Context:
     def synchronize(self):
         _check(self.lib.nupgcm_synchronize(self.h), self.h)
 
+    def set_grid(self, grid: int):
+        """Restrict the persistent solver kernels to ``grid`` CTAs (several contexts on one device)."""
+        _check(self.lib.nupgcm_set_grid(self.h, int(grid)), self.h)
+        return self
+
     def mem_status(self):
         f, t = c_size_t(), c_size_t()
         _check(self.lib.nupgcm_mem_status(self.h, byref(f), byref(t)), self.h)
@@ -183,6 +197,61 @@ class Context:
 
     def csr(self, mat, drop_zeros=False):
         return CsrMatrix(self, mat, drop_zeros)
+
+
+IPC_HANDLE_BYTES = 64
+
+
+class Comm:
+    """One rank of a sharded-solve communicator (``nupgcm_comm_*``): a device arena the other
+    ranks store halo rows and reduction words into.  ``connect_ipc`` takes the 64-byte handles of
+    all ranks (exchanged by the caller, e.g. ``torch.distributed.all_gather_object``);
+    ``Comm.connect_local`` wires up ranks that live in one process."""
+
+    def __init__(self, ctx: Context, rank: int, nranks: int, max_n: int):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.rank, self.nranks, self.max_n = int(rank), int(nranks), int(max_n)
+        h = _P()
+        _check(self.lib.nupgcm_comm_create(ctx.h, self.rank, self.nranks, self.max_n, byref(h)), ctx.h)
+        self.h = h
+
+    def close(self):
+        if self.h and self.ctx.h:
+            self.lib.nupgcm_comm_destroy(self.h)
+        self.h = None
+
+    def ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+        _check(self.lib.nupgcm_comm_ipc_handle(self.h, buf), self.ctx.h)
+        return buf.raw
+
+    def connect_ipc(self, handles):
+        blob = b"".join(handles)
+        if len(blob) != IPC_HANDLE_BYTES * self.nranks:
+            raise ValueError("connect_ipc needs one 64-byte handle per rank, ordered by rank")
+        _check(self.lib.nupgcm_comm_connect_ipc(self.h, C.c_char_p(blob)), self.ctx.h)
+        return self
+
+    @staticmethod
+    def connect_local(comms):
+        arr = (_P * len(comms))(*[c.h for c in comms])
+        for c in comms:
+            _check(c.lib.nupgcm_comm_connect_local(c.h, arr), c.ctx.h)
+        return comms
+
+    @staticmethod
+    def from_torch_distributed(ctx: Context, max_n: int, group=None):
+        """One rank per process: exchange the IPC handles over ``torch.distributed``."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        c = Comm(ctx, rank, world, max_n)
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, c.ipc_handle(), group=group)
+            c.connect_ipc(handles)
+            dist.barrier(group)                 # every arena is mapped before anyone stores into one
+        return c
 
 
 class Vector:
@@ -305,6 +374,18 @@ class CsrMatrix:
         except Exception:
             pass
 
+    def shard(self, comm: "Comm | None"):
+        """Make the persistent solvers on this matrix collective over ``comm`` (row-block sharded)."""
+        _check(self.lib.nupgcm_csr_shard(self.h, comm.h if comm is not None else None), self.ctx.h)
+        self.comm = comm
+        return self
+
+    def shard_info(self, rank: int):
+        a, b, c, d = c_int64(), c_int64(), c_int64(), c_int64()
+        _check(self.lib.nupgcm_csr_shard_info(self.h, int(rank), byref(a), byref(b), byref(c), byref(d)),
+               self.ctx.h)
+        return {"row_begin": a.value, "row_end": b.value, "nnz_owned": c.value, "halo_rows": d.value}
+
     def info(self):
         a, b, c, d = c_int64(), c_int64(), c_int64(), c_int64()
         _check(self.lib.nupgcm_csr_info(self.h, byref(a), byref(b), byref(c), byref(d)), self.ctx.h)
@@ -335,6 +416,25 @@ def rcm_order(mat):
     out = np.empty(m.shape[0], dtype=np.int64)
     _check(load().nupgcm_rcm_order(m.shape[0], _ptr(rowptr, _ip), _ptr(col, _ip), 0, _ptr(out, _ip)))
     return out
+
+
+def shard_plan(mat, nranks: int, grid_per_rank: int = 148):
+    """Host-only: internal ordering, row blocks and halo ranges of a sharded solve
+    (``nupgcm_shard_plan``).  Returns ``perm``, ``row_begin[nranks+1]``,
+    ``halo_lo/hi[dst, src]`` (rows of ``src`` pushed to ``dst``; internal row ids)."""
+    import scipy.sparse as sp
+    m = sp.csr_matrix(mat)
+    rowptr = np.ascontiguousarray(m.indptr, dtype=np.int64)
+    col = np.ascontiguousarray(m.indices, dtype=np.int64)
+    n = m.shape[0]
+    perm = np.empty(n, dtype=np.int64)
+    rb = np.empty(nranks + 1, dtype=np.int64)
+    lo = np.empty((nranks, nranks), dtype=np.int64)
+    hi = np.empty((nranks, nranks), dtype=np.int64)
+    _check(load().nupgcm_shard_plan(n, _ptr(rowptr, _ip), _ptr(col, _ip), 0, int(nranks),
+                                    int(grid_per_rank), _ptr(perm, _ip), _ptr(rb, _ip),
+                                    _ptr(lo, _ip), _ptr(hi, _ip)))
+    return {"perm": perm, "row_begin": rb, "halo_lo": lo, "halo_hi": hi}
 
 
 def _solve(fn, A, dinv, pscale, y, x, atol, rtol, itmax, extra, history):

@@ -1,0 +1,187 @@
+"""Row-block sharded solves (multi-GPU path) on ONE GPU: the ranks live in this process and share
+cuda:0's SMs (74 CTAs each for two ranks), so the whole inter-rank protocol — halo rows pushed into
+the peer's arena, flagged-word reductions across ranks, the closing all-gather — runs exactly as
+it does over NVLink, only with local "peer" pointers.  Checked against the single-rank solver
+(same kernels, nranks = 1), the CPU oracle and SciPy direct solves.  The one-process-per-GPU
+variant over CUDA IPC is exercised by test_two_processes_over_ipc when the box has >= 2 GPUs."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+from conftest import ROOT, workload
+from nupgcm_b200 import lib
+from nupgcm_b200.sharding import local_ranks, run_collective
+from oracle import krylov
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def _evol(ops, θ=0.05):
+    return (ops["M"] + θ * (ops["Kh"] + ops["Kv"])).tocsr()
+
+
+def _sharded(nranks, A, solve, drop_zeros=False):
+    """Run `solve(ctx, dA)` collectively on `nranks` ranks sharing cuda:0; returns per-rank results."""
+    comms = local_ranks(nranks, A.shape[0])
+    mats = [c.ctx.csr(A, drop_zeros=drop_zeros).shard(c) for c in comms]
+    try:
+        return run_collective([lambda c=c, m=m: solve(c.ctx, m) for c, m in zip(comms, mats)]), mats, comms
+    finally:
+        pass
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_cg_sharded_matches_single_rank(ctx, nranks):
+    _, ops = workload("bowl_mixing")
+    A = _evol(ops)
+    rng = np.random.default_rng(0)
+    b = rng.uniform(-1, 1, A.shape[0])
+    x0 = rng.uniform(-1, 1, A.shape[0])
+    dinv = 1.0 / A.diagonal()
+
+    def solve(c, dA):
+        x = c.vector(x0)
+        st, hist = lib.cg_solve(dA, c.vector(b), x, dinv=c.vector(dinv), atol=1e-6, rtol=1e-6, history=4096)
+        return st.niter, bool(st.solved), hist, x.download()
+
+    ref = solve(ctx, ctx.csr(A))
+    res, mats, comms = _sharded(nranks, A, solve)
+    xo, so = krylov.cg(A, b, x0=x0, M=dinv, atol=1e-6, rtol=1e-6)
+    for r, (niter, solved, hist, x) in enumerate(res):
+        assert solved
+        assert abs(niter - ref[0]) <= 1 and abs(niter - so.niter) <= 1
+        n = min(len(hist), len(ref[2]))
+        assert np.allclose(hist[:n], ref[2][:n], rtol=1e-8)
+        assert rel(x, ref[3]) < 1e-9
+        assert np.array_equal(x, res[0][3]), "the solution must be bit-identical on every rank"
+        assert np.array_equal(hist, res[0][2]), "all ranks must see the same scalars"
+    info = [mats[0].shard_info(r) for r in range(nranks)]
+    assert info[0]["row_begin"] == 0 and info[-1]["row_end"] == A.shape[0]
+    assert all(info[r]["row_end"] == info[r + 1]["row_begin"] for r in range(nranks - 1))
+
+
+@pytest.mark.parametrize("orth", [lib.ORTH_MGS, lib.ORTH_CGS2])
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_gmres_sharded_short_run_parity(ctx, nranks, orth):
+    """2-D inversion, fixed itmax: iteration counts and residual histories against the oracle and
+    the single-rank kernel."""
+    _, ops = workload("bowl_mixing", dim=2)
+    A = ops["A"].tocsr()
+    rng = np.random.default_rng(2)
+    b = rng.uniform(-1, 1, A.shape[0])
+    ps = ops["pscale"]
+
+    def solve(c, dA):
+        x = c.vector(A.shape[0])
+        st, hist = lib.gmres_solve(dA, c.vector(b), x, pscale=ps, atol=1e-6, rtol=1e-6, itmax=130,
+                                   memory=20, orth=orth, history=4096)
+        return st.niter, bool(st.solved), hist, x.download()
+
+    ref = solve(ctx, ctx.csr(A, drop_zeros=True))
+    res, _, _ = _sharded(nranks, A, solve, drop_zeros=True)
+    xo, so = krylov.gmres(A, b, x0=np.zeros(b.size), M=ps, atol=1e-6, rtol=1e-6, itmax=130, memory=20)
+    for niter, solved, hist, x in res:
+        assert niter == ref[0] and abs(niter - so.niter) <= 1
+        n = min(len(hist), len(ref[2]), 100)
+        assert np.allclose(hist[:n], ref[2][:n], rtol=1e-6)
+        assert rel(x, ref[3]) < 1e-6
+        assert np.array_equal(x, res[0][3])
+
+
+def test_gmres_sharded_tight_matches_direct(ctx):
+    """3-D evolution-sized SPD system solved by sharded GMRES to 1e-12: residual <= 1e-10, solution
+    within 1e-8 of SuperLU; consecutive solves on one communicator (sequence numbers carry over)."""
+    _, ops = workload("bowl_mixing")
+    A = _evol(ops)
+    rng = np.random.default_rng(3)
+    bs = [rng.uniform(-1, 1, A.shape[0]) for _ in range(3)]
+    dinv = 1.0 / A.diagonal()
+    lu = spla.splu(A.tocsc())
+
+    def solve(c, dA):
+        out = []
+        x = c.vector(A.shape[0])
+        for b in bs:                              # warm-started from the previous answer
+            st, _ = lib.gmres_solve(dA, c.vector(b), x, dinv=c.vector(dinv), atol=0.0, rtol=1e-12,
+                                    memory=20, orth=lib.ORTH_CGS2)
+            out.append((bool(st.solved), x.download()))
+        return out
+
+    res, _, _ = _sharded(2, A, solve)
+    for rank_out in res:
+        for (solved, x), b in zip(rank_out, bs):
+            assert solved
+            assert np.linalg.norm(A @ x - b) / np.linalg.norm(b) < 1e-10
+            assert rel(x, lu.solve(b)) < 1e-8
+
+
+def test_inversion_3d_sharded_first_iterations(ctx):
+    """3-D inversion matrix (SM-resident form, RCM reorder, dropped zeros) on 2 ranks: history equal
+    to the single-rank kernel over a bounded run."""
+    _, ops = workload("bowl_mixing")
+    A = ops["A"].tocsr()
+    y = ops["B"] @ ops["b_init"] + ops["b0"] if "b_init" in ops else None
+    rng = np.random.default_rng(4)
+    b = rng.uniform(-1, 1, A.shape[0]) if y is None or not np.any(y) else y
+    ps = ops["pscale"]
+
+    def solve(c, dA):
+        x = c.vector(A.shape[0])
+        st, hist = lib.gmres_solve(dA, c.vector(b), x, pscale=ps, atol=1e-6, rtol=1e-6, itmax=400,
+                                   memory=20, orth=lib.ORTH_CGS2, history=4096)
+        return st.niter, hist, x.download(), st.device_ms
+
+    ref = solve(ctx, ctx.csr(A, drop_zeros=True))
+    res, _, _ = _sharded(2, A, solve, drop_zeros=True)
+    for niter, hist, x, ms in res:
+        assert niter == ref[0]
+        assert np.allclose(hist[:300], ref[1][:300], rtol=1e-6)
+        assert rel(x, ref[2]) < 1e-6
+
+
+def test_model_steps_sharded_match_single_rank(ctx):
+    """Three timesteps of the 2-D bowl with both solves sharded over 2 ranks (state replicated,
+    element RHS replicated) against the single-GPU model."""
+    import nupgcm_b200 as npg
+    w, ops = workload("bowl_mixing", dim=2)
+
+    def make(arch):
+        inv = npg.InversionToolkit(arch, ops["A"], ops["pscale"], ops["B"], ops["b0"])
+        ts = w.timestepper()
+        evo = npg.EvolutionToolkit(arch, ops, w.params, w.forcings, ts)
+        m = npg.Model(arch, w.params, w.forcings, w.fe_data(), inv, evo, ts, tables=ops["tables"])
+        m.xb.upload(ops["b_init"])
+        return m
+
+    single = make(npg.GPU(0))
+    npg.run_(single, n_steps=3)
+    comms = local_ranks(2, ops["A"].shape[0])
+    models = [make(npg.GPU(0, comm=c)) for c in comms]
+    run_collective([lambda m=m: npg.run_(m, n_steps=3) for m in models])
+    for m in models:
+        for a, b in zip(m.step_log, single.step_log):
+            assert abs(a["gmres_iters"] - b["gmres_iters"]) <= 1 and abs(a["cg_iters"] - b["cg_iters"]) <= 1
+        assert rel(m.xb.download(), single.xb.download()) < 1e-8
+        assert rel(m.inversion.solver.x.download(), single.inversion.solver.x.download()) < 1e-6
+    assert np.array_equal(models[0].xb.download(), models[1].xb.download())
+
+
+def test_two_processes_over_ipc():
+    """One process per GPU (torchrun, world size 2): CUDA IPC arenas, NVLink pushes."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29531",
+           os.path.join(ROOT, "tools", "sharded_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "sharded_check ok" in out.stdout
