@@ -21,8 +21,13 @@ Lines printed (rank 0, one JSON line):
             step + NumPy element RHS) timed on a bounded sample of the same workload
 `--impl reference` times that CPU path alone with the same metric/config.
 
-For N > 1 each rank currently steps an independent replica of the workload (row-block sharding of
-one mesh across GPUs is designed in DESIGN.md but not built yet), so scaling is "weak".
+For N > 1 (launched by torchrun, one rank per GPU) the SAME workload is stepped once, with both
+Krylov solves row-block sharded over the N GPUs (halo rows and dot-product words travel through
+peer memory over NVLink inside the persistent kernels; element RHS and the small vector kernels
+are replicated), so scaling is "strong".  The h=0.08 system (N=31 395) fits in the shared memory of
+ONE B200 and is bound by reduction latency, so it cannot speed up across GPUs; the `refined` object
+of the same JSON line therefore also times BASELINE configs[2] — the inversion-only GMRES(20)
+solve on the refined h=0.04 mesh (N=263 159) — at the same N, which is where sharding pays.
 """
 from __future__ import annotations
 
@@ -169,6 +174,49 @@ def reference_arm(args):
     }))
 
 
+def refined_leg(args, arch, ctx, orth, world, barrier, dist):
+    """BASELINE configs[2]: inversion-only GMRES(20) solve on the refined bowl3D mesh (h=0.04, one
+    refinement of the shipped h=0.08 mesh, N=263 159), cold start, bounded to --refined-iters
+    iterations; sharded over the ranks when world > 1."""
+    import nupgcm_b200 as npg
+    from nupgcm_b200 import lib
+    from nupgcm_b200 import workloads as W
+    w = W.bowl_example(mesh=W.refined_bowl(1))
+    fe = w.fe_data()
+    from nupgcm_b200.inversion import permuted_inversion_system
+    A, B, b0, pscale = permuted_inversion_system(fe, w.params, w.forcings)
+    b_init = fe.spaces.B.interpolate(w.b0)[0][fe.dofs.p_b]
+    inv = npg.InversionToolkit(arch, A, pscale, B, b0, orth=orth, drop_zeros=True,
+                               itmax=args.refined_iters, history=False)
+    xb = ctx.vector(b_init)
+    n = A.shape[0]
+    nnz = inv.solver.A.info()["nnz_stored"]
+    ms, its = [], []
+    for rep in range(3):                       # first pass warms up (set-up of the sharded tables)
+        inv.solver.x.fill(0.0)
+        barrier()
+        npg.inversion.invert_(inv, xb)
+        ms.append(inv.solver.stats.timer * 1e3)
+        its.append(inv.solver.stats.niter)
+    t_ms, it = float(np.min(ms[1:])), int(its[-1])
+    if dist is not None:
+        import torch
+        t = torch.tensor([t_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_ms = float(t[0])
+    peak, _ = peaks()
+    gbs = gmres_bytes(n, nnz, it) / (t_ms * 1e-3) / 1e9
+    info = inv.solver.A.shard_info(0) if world > 1 else None
+    return {"workload": "bowl3D h=0.04 (h=0.08 mesh refined once), inversion-only GMRES(20) solve, cold start, "
+                        f"bounded to {args.refined_iters} iterations (BASELINE configs[2])",
+            "N": n, "nnz": nnz, "n_gpus": world, "iterations": it, "ms": t_ms,
+            "us_per_iter": 1e3 * t_ms / max(it, 1), "solves_per_s": 1e3 / t_ms,
+            "rnorm_over_rnorm0": float(inv.solver.stats.rnorm / max(inv.solver.stats.rnorm0, 1e-300)),
+            "algorithmic_gbs": gbs, "frac_of_hbm_peak_all_gpus": gbs / (peak * world),
+            "rank0_rows": None if info is None else [info["row_begin"], info["row_end"]],
+            "rank0_halo_rows": None if info is None else info["halo_rows"]}
+
+
 # ---------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -183,6 +231,8 @@ def main():
     ap.add_argument("--keep-zeros", action="store_true", help="store Gridap's explicit zeros too")
     ap.add_argument("--cpu-sample-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-refined", action="store_true", help="skip the h=0.04 inversion-only leg")
+    ap.add_argument("--refined-iters", type=int, default=2000)
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -204,7 +254,12 @@ def main():
 
     w = W.bowl_example(h=args.h)
     ops = W.host_operands(w)
-    arch = npg.GPU(local)
+    comm = None
+    if world > 1:
+        from nupgcm_b200.sharding import torch_comm
+        arch, comm = torch_comm(max_n=300000)        # largest system solved below: h=0.04, N=263 159
+    else:
+        arch = npg.GPU(local)
     ctx = arch.ctx
     orth = lib.ORTH_MGS if args.orth == "mgs" else lib.ORTH_CGS2
 
@@ -266,8 +321,8 @@ def main():
         t = torch.tensor([total_ms, e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_s = float(t[0]), float(t[1])
-    value = world * args.steps / (total_ms * 1e-3)
-    e2e = world * args.steps / e2e_s
+    value = args.steps / (total_ms * 1e-3)          # one simulation, sharded over `world` GPUs
+    e2e = args.steps / e2e_s
 
     # ---------------- roofline of the dominant kernel (persistent GMRES) ---------------------
     infoA = m.inversion.solver.A.info()
@@ -279,7 +334,10 @@ def main():
     peak, peak_src = peaks()
     g_bytes = float(np.mean([gmres_bytes(n, nnz, k) for k in g_iters]))
     achieved = g_bytes / (float(np.mean(g_ms)) * 1e-3) / 1e9 if g_ms.mean() > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_gmres (persistent GMRES(20), one launch per invert!)",
+    peak_src += "" if world == 1 else f" x {world} GPUs"
+    peak *= world
+    roofline = {"bound": "hbm", "kernel": "k_gmres (persistent GMRES(20), one launch per invert!"
+                                          + (f", sharded over {world} GPUs)" if world > 1 else ")"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": g_bytes, "ms_per_launch": float(g_ms.mean()),
@@ -288,10 +346,12 @@ def main():
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": dict(workload_config(args.h), N=n, nnz=nnz, nb=d.nb, orth=args.orth,
                        drop_zeros=not args.keep_zeros,
-                       parallelism="single GPU" if world == 1 else f"{world} independent replicas"),
+                       parallelism="single GPU" if world == 1 else
+                       f"CG and GMRES row-block sharded over {world} GPUs (peer-memory halo pushes and "
+                       "reductions inside the persistent kernels); element RHS and vector kernels replicated"),
         "iterations": {"gmres_per_step_mean": float(g_iters.mean()), "gmres_per_step_min": float(g_iters.min()),
                        "gmres_per_step_max": float(g_iters.max()), "cg_per_step_mean": float(c_iters.mean()),
                        "gmres_us_per_iter": float(1e3 * g_ms.sum() / max(g_iters.sum(), 1)),
@@ -311,6 +371,9 @@ def main():
                                "sample": f"{args.cpu_sample_steps} timesteps of the same workload "
                                          f"({secs:.1f} s) after LU factorisation; SciPy SuperLU direct "
                                          "solves + NumPy element RHS, single-threaded"}
+    if not args.no_refined:
+        del m, m2
+        out["refined"] = refined_leg(args, arch, ctx, orth, world, barrier, dist)
     if rank == 0:
         print(json.dumps(out))
     if dist is not None:
