@@ -215,6 +215,11 @@ int32_t nupgcm_diag_reduce_latency(nupgcm_ctx *ctx, int32_t mode, int32_t reps, 
 int32_t nupgcm_diag_pingpong(nupgcm_ctx *ctx, int32_t peer, int32_t variant, int32_t reps,
                              float *us_round_trip);
 
+/* diagnostics: one-way latency (µs) of a flag crossing NVLink between two ranks' arenas
+ * (variant 0 relaxed.sys, 1 release/acquire.sys, 2 fence.sys + relaxed).  Call on every rank. */
+int32_t nupgcm_diag_xping(nupgcm_comm *comm, int32_t rank_a, int32_t rank_b, int32_t variant,
+                          int32_t reps, float *us_one_way);
+
 /* ---- per-step element right-hand side (replaces the CPU Gridap assemble_vector of
  *      src/model.jl:269-275 and the broadcast of :278) -----------------------------------
  * P2 tetrahedra (n_loc = 10) or P2 triangles (n_loc = 6).

@@ -57,6 +57,7 @@ struct nupgcm_comm {
     int connected;
     int broken;                    // a sharded solve aborted: the sequence numbers are undefined
     unsigned xgen;                 // sequence number of the inter-rank reductions (never reset)
+    unsigned long long ping_seq;   // nupgcm_diag_xping
 };
 
 struct nupgcm_vec {
@@ -113,6 +114,7 @@ struct nupgcm_csr {
 };
 
 int32_t nupgcm_csr_prepare(nupgcm_csr *A, int grid);
+int32_t nupgcm_reserve_solver_workspace(nupgcm_ctx *ctx, int64_t max_n);
 
 struct nupgcm_mesh {
     nupgcm_ctx *ctx;

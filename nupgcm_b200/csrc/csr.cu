@@ -351,6 +351,10 @@ extern "C" int32_t nupgcm_csr_shard(nupgcm_csr *A, nupgcm_comm *comm) {
                        "csr_shard: matrix must be square with n <= the communicator's max_n");
     }
     A->comm = (comm && comm->nranks > 1) ? comm : nullptr;
+    if (A->comm) {
+        int32_t rc = nupgcm_reserve_solver_workspace(ctx, comm->max_n);
+        if (rc) return rc;
+    }
     return nupgcm_csr_prepare(A, ctx->coop_grid);
 }
 

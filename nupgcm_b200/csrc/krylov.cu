@@ -63,6 +63,8 @@ struct KrylovArgs {
     int mem;
     int orth;
     int poll_depth;          // replicas of the reduction slots (GridReduce)
+    int xmode;               // sharded solves: 1 = gather / multi-rank broadcast reductions, 0 = two-level
+    int xfence;              // 1: release.sys / acquire.sys on the inter-rank flags of publishing reductions
     unsigned long long *trace;   // debug: arrival/completion stamps of a window of reductions
     unsigned long long *barrier;
     double *partials;        // LLSlot [2][kPartialSlots][grid]
@@ -173,6 +175,7 @@ struct CommMailbox {
     double in[kPartialSlots];
     double out[kPartialSlots];
     double part[kPartialSlots][kPollWarps];
+    double xpart[kPartialSlots][kMaxRanks];   // sharded solves: per-rank totals of each value
 };
 
 // Scratch layout (LLSlot units) of one bank of the exchange area.
@@ -332,6 +335,69 @@ __device__ __forceinline__ bool comm_sumN(CommMailbox *mb, const KrylovArgs &a, 
     return bad;
 }
 
+// Sharded solves, xmode 1: every reduction (1..20 values, or a bare barrier) takes two hops.
+//   hop 1 (inside the GPU)  every CTA stores its partials into flagged slots; CTA j — the reducer
+//                           of value j on its rank — adds the rank's partials in CTA order;
+//   hop 2 (over NVLink)     the reducer stores the rank's total into EVERY rank's arena (kXRep
+//                           replicas each: nranks x kXRep 16-byte stores, one per comm lane), and
+//                           every CTA of every rank polls the nranks words of each value in its own
+//                           arena and adds them in rank order.
+// All CTAs of all ranks obtain bit-identical totals.  PUBLISH carries release/acquire along the
+// chain (gpu scope inside the GPU, sys scope across), after the main threads' system fence.
+template <bool PUBLISH>
+__device__ __forceinline__ bool comm_mr(CommMailbox *mb, const KrylovArgs &a, LLSlot *bank_base,
+                                        unsigned long long *abort_word, unsigned gen, int grid, int gpad, int count) {
+    const int ct = threadIdx.x - kMainThreads, cw = ct >> 5, lane = ct & 31;
+    const int bid = blockIdx.x, P = a.nranks;
+    LLSlot *vals = bank_base + (size_t)kMaxReplicas * gpad;                 // [kPartialSlots][gpad]
+    const unsigned xgen = a.xgen_base + gen, xbank = xgen & 1u;
+    if (count == 1 && mb->from_warps) {
+        if (cw == 0) {
+            double val = lane < kMainWarps ? mb->wpart[lane] : 0.0;
+            val = warp_sum(val);
+            if (lane == 0) ll_store<PUBLISH>(vals + bid, val, gen);
+        }
+    } else if (ct < count) {
+        ll_store<PUBLISH>(vals + (size_t)ct * gpad + bid, mb->in[ct], gen);
+    }
+    bool bad = false;
+    if (bid < count) {                                                      // reducer of value `bid` on this rank
+        const int c = cw * 32 + lane;
+        double v = 0.0;
+        if (c < grid) v = wait_flagged<PUBLISH>(vals + (size_t)bid * gpad + c, gen, abort_word, bad);
+        v = warp_sum(v);
+        if (lane == 0) mb->part[0][cw] = v;
+        named_sync(NUPGCM_BAR_COMM, kCommThreads);
+        if (ct < P * kXRep) {
+            const int npw = (grid + 31) >> 5;
+            double total = 0.0;
+            for (int g = 0; g < npw; ++g) total += mb->part[0][g];
+            // Publishing reductions: the rows pushed to the peers were fenced at system scope by the
+            // threads that stored them (GridReduce), and this reducer has acquired every CTA's slot, so
+            // they are performed at the peers before this flag is even issued — a relaxed store is
+            // enough (the NCCL pattern: writers fence, then the flag).  xfence = 1 uses formal
+            // release.sys / acquire.sys instead, at +1.6 us per hop (tools/xrank_latency.py).
+            LLSlot *dst = xr_slot(a.arena[ct % P], xbank, bid, ct / P, a.rank);
+            if (PUBLISH && a.xfence) ll_store<true, true>(dst, total, xgen);
+            else ll_store<false, true>(dst, total, xgen);
+        }
+    }
+    if (ct < count * P) {
+        const int j = ct / P, r = ct % P;
+        const LLSlot *src = xr_slot(a.arena[a.rank], xbank, j, bid % kXRep, r);
+        mb->xpart[j][r] = (PUBLISH && a.xfence) ? wait_flagged<true, true>(src, xgen, abort_word, bad)
+                                                : wait_flagged<false, true>(src, xgen, abort_word, bad);
+    }
+    if (bad) mb->dead = 1;
+    named_sync(NUPGCM_BAR_COMM, kCommThreads);
+    if (ct < count) {
+        double t = 0.0;
+        for (int r = 0; r < P; ++r) t += mb->xpart[ct][r];
+        mb->out[ct] = t;
+    }
+    return bad;
+}
+
 // Service loop of the comm warps: one request per grid-wide reduction, until the main warps post
 // the exit request.
 template <bool MR = false>
@@ -354,7 +420,11 @@ __device__ __forceinline__ void comm_warp_loop(CommMailbox *mb, const KrylovArgs
             if (tr) trow[1 * (size_t)grid] = global_timer_ns();        // request seen by the comm warps
             LLSlot *bank_base = slots + (size_t)(gen & 1) * exch_bank_slots(gpad);
             bool bad;
-            if (count > 1) bad = comm_sumN<MR>(mb, a, bank_base, abort_word, trow, tr, gen, grid, gpad, count);
+            if (MR && a.xmode == 1) {
+                const int cnt = count > 0 ? count : 1;           // a bare barrier sums one zero
+                bad = mb->publish ? comm_mr<true>(mb, a, bank_base, abort_word, gen, grid, gpad, cnt)
+                                  : comm_mr<false>(mb, a, bank_base, abort_word, gen, grid, gpad, cnt);
+            } else if (count > 1) bad = comm_sumN<MR>(mb, a, bank_base, abort_word, trow, tr, gen, grid, gpad, count);
             else if (mb->publish) bad = comm_sum1<true, MR>(mb, a, bank_base, abort_word, trow, tr, gen, grid, gpad, nrep);
             else bad = comm_sum1<false, MR>(mb, a, bank_base, abort_word, trow, tr, gen, grid, gpad, nrep);
             dead = __any_sync(0xffffffffu, bad) || mb->dead != 0;
@@ -1403,6 +1473,15 @@ static int persistent_tpr(const nupgcm_csr *A, bool resident, int grid) {
     return std::min(t, 32);
 }
 
+static int32_t ensure_workspace(nupgcm_ctx *ctx, size_t bytes);
+
+// Sharded solves must not meet a device-wide synchronisation (cudaFree of a grown workspace)
+// between the launches of two ranks: reserve the largest workspace any solve over the
+// communicator can need when a matrix is sharded.
+int32_t nupgcm_reserve_solver_workspace(nupgcm_ctx *ctx, int64_t max_n) {
+    return ensure_workspace(ctx, (size_t)(kMaxMemory + 4) * (size_t)max_n * sizeof(double));
+}
+
 static int32_t ensure_workspace(nupgcm_ctx *ctx, size_t bytes) {
     if (ctx->ws_bytes >= bytes) return NUPGCM_OK;
     if (ctx->d_ws) {
@@ -1454,7 +1533,7 @@ static ResidentLayout plan_resident(const nupgcm_csr *A, bool gmres, int memory)
     const char *env = getenv("NUPGCM_RESIDENT");
     if (env && atoi(env) == 0) return none;
     if (!A->d_loc || A->res_max_nnz == 0) return none;
-    const int static_smem = gmres ? 6144 : 2048;          // the kernels' static shared memory
+    const int static_smem = gmres ? 8192 : 4096;          // the kernels' static shared memory
     const int limit = 227 * 1024 - static_smem;
     const char *envv = getenv("NUPGCM_VEC_SMEM");
     const int n_vec = (envv && atoi(envv) == 0) ? 1 << 20 : (gmres ? memory + 1 : 5);
@@ -1470,7 +1549,7 @@ static ResidentLayout plan_streaming(const nupgcm_csr *A, bool gmres, int memory
     const char *env = getenv("NUPGCM_STREAM_TMA");
     if (env && atoi(env) == 0) return L;
     if (!A->d_chunk_ptr) return L;
-    const int static_smem = gmres ? 6144 : 2048;
+    const int static_smem = gmres ? 8192 : 4096;
     const int limit = 227 * 1024 - static_smem;
     int off = 0;
     L.st_vals = off; off += kStreamStages * kStreamChunk * 8;
@@ -1565,6 +1644,9 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
     args.rank = comm ? comm->rank : 0;
     args.nranks = nranks;
     args.xgen_base = comm ? comm->xgen : 0;
+    args.xmode = 1;
+    if (const char *ex = getenv("NUPGCM_XMODE")) args.xmode = atoi(ex) != 0;
+    if (const char *ex = getenv("NUPGCM_XFENCE")) args.xfence = atoi(ex) != 0;
     for (int p = 0; p < nranks && comm; ++p) {
         args.arena[p] = comm->peer[p];
         args.push_lo[p] = A->push_lo[p];
@@ -1741,6 +1823,62 @@ extern "C" int32_t nupgcm_diag_pingpong(nupgcm_ctx *ctx, int32_t peer, int32_t v
     NUPGCM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->h_scalars[7] != 0.0) return nupgcm_fail(ctx, NUPGCM_ERR_CUDA, "%s", "ping-pong timed out");
     *us_round_trip = (float)(ctx->h_scalars[0] * 1e-3 / reps);
+    return NUPGCM_OK;
+}
+
+// Ping-pong between two RANKS through one word of each other's arena: the one-way latency of a
+// flag that crosses NVLink (variant 0: relaxed.sys, 1: release.sys / acquire.sys, 2: fence.sys +
+// relaxed).  Collective over the two ranks involved; the others return immediately.
+__global__ void k_diag_xping(unsigned long long *mine, unsigned long long *theirs, int initiator, int variant,
+                             unsigned long long seq0, int reps, double *out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const unsigned long long t_start = global_timer_ns();
+    bool ok = true;
+    for (int i = 1; i <= reps && ok; ++i) {
+        const unsigned long long tag = seq0 + (unsigned long long)i;
+        for (int phase = 0; phase < 2; ++phase) {
+            if ((phase == 0) == (initiator != 0)) {
+                if (variant == 2) __threadfence_system();
+                if (variant == 1) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(tag) : "memory");
+                else asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(tag) : "memory");
+            } else {
+                unsigned long long v, spins = 0;
+                for (;;) {
+                    if (variant == 1) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+                    else asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+                    if (v >= tag) break;
+                    if ((++spins & 1023ULL) == 0 && global_timer_ns() - t_start > kWaitTimeoutNs) { ok = false; break; }
+                }
+                if (!ok) break;
+            }
+        }
+    }
+    out[0] = (double)(global_timer_ns() - t_start);
+    out[7] = ok ? 0.0 : 1.0;
+}
+
+extern "C" int32_t nupgcm_diag_xping(nupgcm_comm *comm, int32_t rank_a, int32_t rank_b, int32_t variant,
+                                     int32_t reps, float *us_one_way) {
+    NUPGCM_REQUIRE(nullptr, comm, "comm is NULL");
+    nupgcm_ctx *ctx = comm->ctx;
+    NUPGCM_REQUIRE(ctx, comm->connected && rank_a != rank_b && rank_a >= 0 && rank_b >= 0 &&
+                            rank_a < comm->nranks && rank_b < comm->nranks && reps > 0 && us_one_way,
+                   "diag_xping: bad argument");
+    const unsigned long long seq0 = comm->ping_seq;
+    comm->ping_seq += (unsigned long long)reps;
+    *us_one_way = 0.f;
+    if (comm->rank != rank_a && comm->rank != rank_b) return NUPGCM_OK;
+    const int other = comm->rank == rank_a ? rank_b : rank_a;
+    unsigned long long *mine = reinterpret_cast<unsigned long long *>(comm->arena + 64);
+    unsigned long long *theirs = reinterpret_cast<unsigned long long *>(comm->peer[other] + 64);
+    NUPGCM_CUDA(ctx, cudaSetDevice(ctx->device));
+    k_diag_xping<<<1, 32, 0, ctx->stream>>>(mine, theirs, comm->rank == rank_a, variant, seq0, reps, ctx->d_scalars);
+    ctx->launches++;
+    NUPGCM_CUDA(ctx, cudaGetLastError());
+    NUPGCM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NUPGCM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_scalars[7] != 0.0) return nupgcm_fail(ctx, NUPGCM_ERR_CUDA, "%s", "cross-rank ping-pong timed out");
+    *us_one_way = (float)(ctx->h_scalars[0] * 1e-3 / reps / 2.0);
     return NUPGCM_OK;
 }
 
