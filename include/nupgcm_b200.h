@@ -220,6 +220,11 @@ int32_t nupgcm_diag_pingpong(nupgcm_ctx *ctx, int32_t peer, int32_t variant, int
 int32_t nupgcm_diag_xping(nupgcm_comm *comm, int32_t rank_a, int32_t rank_b, int32_t variant,
                           int32_t reps, float *us_one_way);
 
+/* diagnostics: average latency (µs) of the sharded solvers' reduction of `count` values
+ * (publish != 0: the variant that also publishes pushed rows).  Collective over all ranks. */
+int32_t nupgcm_diag_xreduce(nupgcm_comm *comm, int32_t count, int32_t publish, int32_t reps,
+                            float *us_per_reduction);
+
 /* ---- per-step element right-hand side (replaces the CPU Gridap assemble_vector of
  *      src/model.jl:269-275 and the broadcast of :278) -----------------------------------
  * P2 tetrahedra (n_loc = 10) or P2 triangles (n_loc = 6).

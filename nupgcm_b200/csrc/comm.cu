@@ -21,7 +21,8 @@ extern "C" int32_t nupgcm_comm_create(nupgcm_ctx *ctx, int32_t rank, int32_t nra
     c->nranks = nranks;
     c->max_n = max_n;
     c->xgen = 1;
-    c->arena_bytes = kArenaVecOffset + 3 * (size_t)((max_n + 15) & ~(int64_t)15) * sizeof(double);
+    c->n_pad = (max_n + 15) & ~(int64_t)15;
+    c->arena_bytes = kArenaVecOffset + 3 * (size_t)c->n_pad * (sizeof(double) + 16);   // plain + flagged forms
     NUPGCM_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaError_t e = cudaMalloc(&c->arena, c->arena_bytes);
     if (e != cudaSuccess) {

@@ -40,8 +40,12 @@ struct nupgcm_ctx {
 // between processes, plain pointers inside one process):
 //   [0, 128)                    abort word (sticky: a rank whose watchdog fired raises it everywhere)
 //   [kArenaXrOffset, +24 KB)    inter-rank reduction slots  LLSlot[2 banks][kPartialSlots][kXRep][kMaxRanks]
-//   [kArenaVecOffset, ...)      exchange vectors, 3 x max_n doubles: the rows of the multiplied
-//                               vector / iterate that the rank's SpMV gathers (own rows + halo)
+//   [kArenaVecOffset, ...)      exchange vectors, 3 x n_pad doubles: the rows of the multiplied
+//                               vector / iterate that the rank's SpMV gathers (own rows + halo),
+//                               followed by 3 x n_pad flagged 16-byte words: the "mailbox" form of
+//                               the same vectors, into which peers push halo rows (value + tag in
+//                               one word, so no fence is needed; the reader unpacks them into the
+//                               plain vectors before its SpMV)
 static const int kMaxRanks = NUPGCM_MAX_RANKS;
 static const int kXRep = 4;                  // replicas of the all-reader inter-rank slots
 static const size_t kArenaXrOffset = 128, kArenaVecOffset = 32768;
@@ -49,7 +53,7 @@ static const size_t kArenaXrOffset = 128, kArenaVecOffset = 32768;
 struct nupgcm_comm {
     nupgcm_ctx *ctx;
     int rank, nranks;
-    int64_t max_n;
+    int64_t max_n, n_pad;
     char *arena;                   // this rank's arena
     size_t arena_bytes;
     char *peer[kMaxRanks];         // every rank's arena as mapped here (peer[rank] == arena)
@@ -111,6 +115,9 @@ struct nupgcm_csr {
     nupgcm_comm *comm;
     int prepared_ranks;
     int push_lo[kMaxRanks], push_hi[kMaxRanks];
+    int32_t *d_halo_ptr;           // [grid+1] per CTA of this rank: its columns owned by other ranks
+    int32_t *d_halo_idx;
+    int64_t halo_total;            // distinct halo columns of the whole rank
 };
 
 int32_t nupgcm_csr_prepare(nupgcm_csr *A, int grid);

@@ -335,6 +335,36 @@ int32_t nupgcm_csr_prepare(nupgcm_csr *A, int grid_per_rank) {
         for (int p = 0; p < nranks; ++p)
             if (p != me) halo_range(h_rowptr.data(), A->h_pcol, part, grid_per_rank, p, me, A->push_lo[p], A->push_hi[p]);
     }
+    // per CTA of this rank: the columns of its rows that other ranks own (unpacked from the
+    // flagged halo words before each SpMV)
+    cudaFree(A->d_halo_ptr); A->d_halo_ptr = nullptr;
+    cudaFree(A->d_halo_idx); A->d_halo_idx = nullptr;
+    A->halo_total = 0;
+    if (nranks > 1) {
+        const int me = A->comm->rank;
+        const int32_t my0 = part[(size_t)me * grid_per_rank], my1 = part[(size_t)(me + 1) * grid_per_rank];
+        std::vector<int32_t> hptr(grid_per_rank + 1, 0), hidx, tmp, all;
+        for (int b = 0; b < grid_per_rank; ++b) {
+            const int lgb = me * grid_per_rank + b;
+            tmp.clear();
+            for (int32_t k = h_rowptr[part[lgb]]; k < h_rowptr[part[lgb + 1]]; ++k) {
+                const int32_t c = A->h_pcol[k];
+                if (c < my0 || c >= my1) tmp.push_back(c);
+            }
+            std::sort(tmp.begin(), tmp.end());
+            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+            hidx.insert(hidx.end(), tmp.begin(), tmp.end());
+            all.insert(all.end(), tmp.begin(), tmp.end());
+            hptr[b + 1] = (int32_t)hidx.size();
+        }
+        std::sort(all.begin(), all.end());
+        A->halo_total = (int64_t)(std::unique(all.begin(), all.end()) - all.begin());
+        NUPGCM_CUDA(ctx, cudaMalloc(&A->d_halo_ptr, hptr.size() * sizeof(int32_t)));
+        NUPGCM_CUDA(ctx, cudaMemcpy(A->d_halo_ptr, hptr.data(), hptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        NUPGCM_CUDA(ctx, cudaMalloc(&A->d_halo_idx, (hidx.size() + 1) * sizeof(int32_t)));
+        if (!hidx.empty())
+            NUPGCM_CUDA(ctx, cudaMemcpy(A->d_halo_idx, hidx.data(), hidx.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
     A->prepared_grid = grid;
     A->prepared_ranks = nranks;
     NUPGCM_CUDA(ctx, cudaDeviceSynchronize());   // set-up copies ran on the default stream
@@ -539,6 +569,8 @@ extern "C" int32_t nupgcm_csr_destroy(nupgcm_csr *A) {
     cudaFree(A->d_pvals);
     cudaFree(A->d_chunk_ptr);
     cudaFree(A->d_chunk_rowend);
+    cudaFree(A->d_halo_ptr);
+    cudaFree(A->d_halo_idx);
     free(A->h_rowptr);
     free(A->h_col);
     free(A->h_prow);

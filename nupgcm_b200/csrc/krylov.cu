@@ -76,6 +76,9 @@ struct KrylovArgs {
     unsigned xgen_base;      // sequence number of the communicator's inter-rank reductions so far
     char *arena[kMaxRanks];  // exchange arenas of all ranks as mapped here (common.cuh: nupgcm_comm)
     int push_lo[kMaxRanks], push_hi[kMaxRanks];   // rows of this rank that peer p's SpMV gathers
+    const int32_t *halo_ptr;     // [grid+1] per CTA: columns of its rows owned by other ranks
+    const int32_t *halo_idx;
+    long long ll_off;            // byte offset of the flagged form of the exchange vectors in an arena
 };
 
 // Watchdog of every cross-CTA wait: a CTA that waits longer than this raises the abort word and
@@ -444,13 +447,24 @@ struct GridReduce {
     unsigned long long *trace;
     unsigned gen;
     bool dead;
-    bool mr;                         // sharded solve: rows were also stored into peer GPUs' memory
-    __device__ __forceinline__ void init(CommMailbox *m, unsigned long long *tr = nullptr, bool multi_rank = false) {
+    bool remote;                     // sharded solve: this CTA also stores rows into peer GPUs' memory
+    __device__ __forceinline__ void init(CommMailbox *m, unsigned long long *tr = nullptr, bool pushes_remote = false) {
         mb = m;
         trace = tr;
         gen = 0;
         dead = false;
-        mr = multi_rank;
+        remote = pushes_remote;
+    }
+    // Rows stored over NVLink must be performed at the peers before the flag chain of a publishing
+    // reduction starts.  One cumulative system fence per CTA, by thread 0 after a CTA barrier (the
+    // NCCL "barrier, one thread fences, then the flag" pattern): a fence in each of the 352 main
+    // threads of each CTA was measured at 8.7 us per reduction, this form at ~1.6 us and only in
+    // CTAs that actually push.
+    __device__ __forceinline__ void fence_remote() {
+        if (remote) {
+            main_sync();
+            if (threadIdx.x == 0) __threadfence_system();
+        }
     }
     __device__ __forceinline__ bool aborted() const { return dead; }
     __device__ __forceinline__ void round_trip() {
@@ -468,8 +482,7 @@ struct GridReduce {
     // kMainWarps warp partials.
     template <bool PUBLISH>
     __device__ __forceinline__ double sum_threads(double v) {
-        // remote (NVLink) row stores of this thread must be performed before the flag chain starts
-        if (PUBLISH && mr) __threadfence_system();
+        if (PUBLISH) fence_remote();
         v = warp_sum(v);
         if ((threadIdx.x & 31) == 0) mb->wpart[threadIdx.x >> 5] = v;
         if (threadIdx.x == 0) { mb->count = 1; mb->from_warps = 1; mb->publish = PUBLISH ? 1 : 0; }
@@ -484,7 +497,7 @@ struct GridReduce {
     }
     // Grid barrier that publishes this CTA's global-memory rows.
     __device__ __forceinline__ void barrier() {
-        if (mr) __threadfence_system();
+        fence_remote();
         if (threadIdx.x == 0) { mb->count = 0; mb->from_warps = 0; mb->in[0] = 0.0; mb->publish = 1; }
         round_trip();
     }
@@ -896,9 +909,13 @@ template <>
 struct HaloPush<true> {
     const int *range;       // shared: [2*j], [2*j+1] row range of active peer j (intersected with the CTA's rows)
     char *const *dest;      // shared: arena of active peer j
-    const char *local;
+    char *local;
     char *const *all;       // arenas of all ranks
-    int np, rank, nranks, row_bias;
+    const double *vec0;     // first exchange vector in the local arena
+    const int32_t *hlist;   // columns of this CTA's rows owned by other ranks
+    long long ll_off;
+    int np, nh, rank, nranks;
+    unsigned tag;           // sequence number of the publishing reduction that follows the stores
     // `sh_range` (2*kMaxRanks ints) and `sh_dest` (kMaxRanks pointers) are shared-memory scratch;
     // call from all threads, followed by a CTA barrier before the first put().
     __device__ __forceinline__ void init(const KrylovArgs &a, int r0, int r1, int *sh_range, char **sh_dest) {
@@ -918,21 +935,65 @@ struct HaloPush<true> {
         all = a.arena;
         rank = a.rank;
         nranks = a.nranks;
+        vec0 = reinterpret_cast<const double *>(local + kArenaVecOffset);
+        ll_off = a.ll_off;
+        hlist = a.halo_idx + a.halo_ptr[blockIdx.x];
+        nh = a.halo_ptr[blockIdx.x + 1] - a.halo_ptr[blockIdx.x];
+        tag = 0;
     }
-    // p_local = address of the row's entry in the LOCAL arena; row = p_local's row index is
-    // recovered from the vector base by the caller: pass the row explicitly.
+    // Row `row` of the exchange vector whose local entry is p_local: value + tag as ONE flagged
+    // 16-byte word into the mailbox form of that vector in every peer that gathers the row.  No
+    // fence: the reader accepts the word only when both halves carry the tag.
     __device__ __forceinline__ void put_row(const double *p_local, int row, double v) const {
+        const size_t idx = (size_t)(p_local - vec0);
         for (int j = 0; j < np; ++j)
             if (row >= range[2 * j] && row < range[2 * j + 1])
-                *reinterpret_cast<double *>(dest[j] + (reinterpret_cast<const char *>(p_local) - local)) = v;
+                ll_store<false, true>(reinterpret_cast<LLSlot *>(dest[j] + ll_off) + idx, v, tag);
     }
-    // store to every peer (the all-gather that ends a solve)
+    // plain store to every peer (the all-gather that ends a solve; followed by a system fence)
     __device__ __forceinline__ void put_all(const double *p_local, double v) const {
         for (int p = 0; p < nranks; ++p)
             if (p != rank)
                 *reinterpret_cast<double *>(all[p] + (reinterpret_cast<const char *>(p_local) - local)) = v;
     }
+    // Before an SpMV that gathers `xin` (an exchange vector of the local arena): take this CTA's halo
+    // entries out of the mailbox form (waiting for the tag of the last publishing reduction) and
+    // store them into the plain vector, where the SpMV engines read them like any other entry.
+    // Several CTAs may unpack the same column: they store the same value.
+    __device__ __forceinline__ bool unpack(const double *xin, unsigned want, unsigned long long *abort_word) const {
+        bool bad = false;
+        if (nh > 0) {
+            const LLSlot *box = reinterpret_cast<const LLSlot *>(local + ll_off) + (size_t)(xin - vec0);
+            double *dst = const_cast<double *>(xin);
+            for (int i = threadIdx.x; i < nh; i += kMainThreads) {
+                const int c = hlist[i];
+                dst[c] = wait_flagged<false, true>(box + c, want, abort_word, bad);
+            }
+        }
+        return bad;
+    }
 };
+template <bool MR>
+__device__ __forceinline__ bool pushes_remote(const HaloPush<MR> &hp) {
+    (void)hp;              // halo rows travel as flagged words; only the closing all-gather fences
+    return false;
+}
+// Arm the pushes that follow with the tag of the NEXT reduction (the one that publishes them), and
+// the SpMV-side counterpart: unpack the halo of `xin`, published by the LAST reduction.
+template <bool MR>
+__device__ __forceinline__ void halo_arm(HaloPush<MR> &hp, const KrylovArgs &a, unsigned gen) {
+    if constexpr (MR) hp.tag = a.xgen_base + gen + 1u;
+}
+template <bool MR>
+__device__ __forceinline__ void halo_unpack(const HaloPush<MR> &hp, const KrylovArgs &a, unsigned gen, CommMailbox *mb,
+                                            const double *xin) {
+    if constexpr (MR) {
+        if (hp.nh > 0) {
+            if (hp.unpack(xin, a.xgen_base + gen, reinterpret_cast<unsigned long long *>(a.arena[a.rank]))) mb->dead = 1;
+            main_sync();
+        }
+    }
+}
 template <bool MR>
 __device__ __forceinline__ void halo_put(const HaloPush<MR> &hp, const double *p_local, int row, double v) {
     if constexpr (MR) hp.put_row(p_local, row, v);
@@ -959,7 +1020,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg(const __grid_constant__ Kryl
         return;
     }
     GridReduce gr;
-    gr.init(&mailbox, a.trace, MR);
+    gr.init(&mailbox, a.trace, pushes_remote(hp));
     const int n = a.n;
     // CTA-local vectors: r, Ap, local copy of p, the iterate, the Jacobi diagonal
     VecSlices loc(a, dyn_smem, a.work + n, r0);       // global fallback: work[n .. 6n)
@@ -974,6 +1035,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg(const __grid_constant__ Kryl
 
     // vectors cross the ABI in caller order; internally rows follow the reordered matrix
     double *xi = MR ? xbase + n : a.work + 6 * (size_t)n;   // Δx in internal order, gathered by all CTAs
+    halo_arm(hp, a, gr.gen);
     for (int row = r0 + tid; row < r1; row += nthr) {
         const int src = a.perm[row];
         const double x0 = a.x[src];                    // Δx, the warm start
@@ -985,6 +1047,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg(const __grid_constant__ Kryl
     gr.barrier();
     // r = b − A Δx ; z = M r ; p = z ; γ = r·z          (own rows; z is never stored)
     double part = 0.0;
+    halo_unpack(hp, a, gr.gen, &mailbox, xi);
+    halo_arm(hp, a, gr.gen);
     eng.run(xi, [&](int row, double ax) {
         const double rv = a.b[a.perm[row]] - ax;
         const double zv = dl[row] * rv;
@@ -1012,6 +1076,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg(const __grid_constant__ Kryl
     while (!(solved || tired || zero_curv || gr.aborted())) {
         // Ap = A p ; pAp = p·Ap
         part = 0.0;
+        halo_unpack(hp, a, gr.gen, &mailbox, pg);
         eng.run(pg, [&](int row, double ap) {
             Ap[row] = ap;
             part = fma(pl[row], ap, part);
@@ -1040,6 +1105,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg(const __grid_constant__ Kryl
             pnorm2 = gamma_next + beta * beta * pnorm2;
             gamma = gamma_next;
             // p = z + β p   (own rows), then publish p for the next SpMV gather
+            halo_arm(hp, a, gr.gen);
             for (int row = r0 + tid; row < r1; row += nthr) {
                 const double pv = fma(beta, pl[row], dl[row] * r[row]);
                 pl[row] = pv;
@@ -1059,6 +1125,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg(const __grid_constant__ Kryl
             xi[row] = xv;
             hp.put_all(xi + row, xv);
         }
+        gr.remote = true;
         gr.barrier();
         for (int row = blockIdx.x * nthr + tid; row < n; row += gridDim.x * nthr) a.x[a.perm[row]] = ld_cg(xi + row);
         gr.barrier();      // no rank leaves (and lets the next solve reuse the arena) before all have read it
@@ -1173,7 +1240,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
         return;
     }
     GridReduce gr;
-    gr.init(&mailbox, a.trace, MR);
+    gr.init(&mailbox, a.trace, pushes_remote(hp));
     double *sm_in = mailbox.in, *sm_out = mailbox.out;
     const int n = a.n;
     const int mem = a.mem;
@@ -1186,6 +1253,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
     const int tid = threadIdx.x, nthr = kMainThreads;
     const int lane = tid & 31, wid = tid >> 5, nwarps = kMainWarps;
     // vectors cross the ABI in caller order; internally rows follow the reordered matrix
+    halo_arm(hp, a, gr.gen);
     for (int row = r0 + tid; row < r1; row += nthr) {
         const double xv = a.x[a.perm[row]];
         x[row] = xv;
@@ -1204,6 +1272,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
         double part = 0.0;
         double *q0 = qbuf;
         double *v0 = V.at(0);
+        halo_unpack(hp, a, gr.gen, &mailbox, x);
+        halo_arm(hp, a, gr.gen);
         eng.run(x, [&](int row, double ax) {
             const double v = precond(a, row, a.b[a.perm[row]] - ax);
             q0[row] = v;
@@ -1236,6 +1306,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
             double part = 0.0;
             double *q0 = qbuf + (size_t)cur * n;
             double *v0 = V.at(0);
+            halo_unpack(hp, a, gr.gen, &mailbox, x);
+            halo_arm(hp, a, gr.gen);
             eng.run(x, [&](int row, double ax) {
                 const double v = precond(a, row, a.b[a.perm[row]] - ax);
                 q0[row] = v;
@@ -1264,6 +1336,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
             const double *src = qbuf + (size_t)cur * n;
             double *dst = qbuf + (size_t)(cur ^ 1) * n;
             pc.mark(3);
+            halo_unpack(hp, a, gr.gen, &mailbox, src);
             eng.run(src, [&](int row, double av) { q[row] = precond(a, row, av * inv_h); });
             main_sync();
             pc.mark(0);
@@ -1287,6 +1360,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
                 }
                 const double *vp = V.at(k - 1);
                 double part = 0.0;
+                halo_arm(hp, a, gr.gen);
                 for (int row = r0 + tid; row < r1; row += nthr) {
                     const double qv = fma(-hprev, vp[row], q[row]);
                     q[row] = qv;
@@ -1326,6 +1400,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
                     pc.mark(2);
                     // q −= Σ h_i v_i  (own rows)
                     double part = 0.0;
+                    halo_arm(hp, a, gr.gen);
                     for (int row = r0 + tid; row < r1; row += nthr) {
                         double qv = q[row];
                         for (int i = 0; i < k; ++i) qv = fma(-sm_out[i], V.at(i)[row], qv);
@@ -1395,6 +1470,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
         }
         main_sync();
         if (s_flags[1] != 0.0) inconsistent = true;
+        halo_arm(hp, a, gr.gen);
         for (int row = r0 + tid; row < r1; row += nthr) {
             double xr = 0.0;
             for (int i = 0; i < k; ++i) xr = fma(sy[i], V.at(i)[row], xr);
@@ -1414,6 +1490,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
     if constexpr (MR) {
         // all-gather of the solution (see k_cg)
         for (int row = r0 + tid; row < r1; row += nthr) hp.put_all(x + row, x[row]);
+        gr.remote = true;
         gr.barrier();
         for (int row = blockIdx.x * nthr + tid; row < n; row += gridDim.x * nthr) a.x[a.perm[row]] = ld_cg(x + row);
         gr.barrier();
@@ -1647,6 +1724,9 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
     args.xmode = 1;
     if (const char *ex = getenv("NUPGCM_XMODE")) args.xmode = atoi(ex) != 0;
     if (const char *ex = getenv("NUPGCM_XFENCE")) args.xfence = atoi(ex) != 0;
+    args.halo_ptr = A->d_halo_ptr;
+    args.halo_idx = A->d_halo_idx;
+    args.ll_off = comm ? (long long)(kArenaVecOffset + 3 * (size_t)comm->n_pad * sizeof(double)) : 0;
     for (int p = 0; p < nranks && comm; ++p) {
         args.arena[p] = comm->peer[p];
         args.push_lo[p] = A->push_lo[p];
@@ -1879,6 +1959,80 @@ extern "C" int32_t nupgcm_diag_xping(nupgcm_comm *comm, int32_t rank_a, int32_t 
     NUPGCM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->h_scalars[7] != 0.0) return nupgcm_fail(ctx, NUPGCM_ERR_CUDA, "%s", "cross-rank ping-pong timed out");
     *us_one_way = (float)(ctx->h_scalars[0] * 1e-3 / reps / 2.0);
+    return NUPGCM_OK;
+}
+
+// Latency of the sharded solvers' reduction: `count` values per reduction (1: sum_threads, >1: sumN),
+// publish = 1 adds the system fence + release/acquire chain.  Collective over all ranks.
+__global__ void __launch_bounds__(kThreads, 1) k_diag_xreduce(const __grid_constant__ KrylovArgs a, int count, int publish,
+                                                               int reps, double *out) {
+    __shared__ CommMailbox mailbox;
+    if (threadIdx.x == 0) mailbox.dead = 0;
+    __syncthreads();
+    if (threadIdx.x >= kMainThreads) {
+        comm_warp_loop<true>(&mailbox, a, a.poll_depth);
+        return;
+    }
+    GridReduce gr;
+    gr.init(&mailbox, nullptr, publish == 1 || (publish == 2 && (blockIdx.x % 8) == 0));   // 1: every CTA pushes, 2: one in eight
+    double v = 1.0 + blockIdx.x, acc = 0.0;
+    const unsigned long long t0 = global_timer_ns();
+    for (int i = 0; i < reps && !gr.aborted(); ++i) {
+        double s;
+        if (count == 1) {
+            const double mine = threadIdx.x == 0 ? v : 0.0;
+            s = publish ? gr.sum_threads<true>(mine) : gr.sum_threads<false>(mine);
+        } else {
+            if (threadIdx.x < count) mailbox.in[threadIdx.x] = v + threadIdx.x;
+            main_sync();
+            gr.sumN(count);
+            s = mailbox.out[count - 1];
+            main_sync();
+        }
+        acc += s;
+        v = s * 1e-9 + blockIdx.x;
+    }
+    const unsigned long long t1 = global_timer_ns();
+    if (blockIdx.x == 0 && threadIdx.x == 0) { out[0] = acc; out[1] = (double)(t1 - t0); out[7] = gr.aborted() ? 1.0 : 0.0; out[13] = (double)gr.gen; }
+    gr.finish();
+}
+
+extern "C" int32_t nupgcm_diag_xreduce(nupgcm_comm *comm, int32_t count, int32_t publish, int32_t reps,
+                                       float *us_per_reduction) {
+    NUPGCM_REQUIRE(nullptr, comm, "comm is NULL");
+    nupgcm_ctx *ctx = comm->ctx;
+    NUPGCM_REQUIRE(ctx, comm->connected && !comm->broken && comm->nranks > 1, "diag_xreduce: needs a connected multi-rank communicator");
+    NUPGCM_REQUIRE(ctx, count >= 1 && count <= kMaxMemory && reps > 0 && us_per_reduction, "diag_xreduce: bad argument");
+    const int grid = ctx->coop_grid;
+    NUPGCM_CUDA(ctx, cudaSetDevice(ctx->device));
+    NUPGCM_CUDA(ctx, cudaMemsetAsync(ctx->d_barrier, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    NUPGCM_CUDA(ctx, cudaMemsetAsync(ctx->d_partials, 0, reduce_scratch_bytes(ctx->coop_grid), ctx->stream));
+    KrylovArgs args;
+    memset(&args, 0, sizeof(args));
+    args.barrier = ctx->d_barrier;
+    args.partials = ctx->d_partials;
+    args.poll_depth = poll_config(grid);
+    args.rank = comm->rank;
+    args.nranks = comm->nranks;
+    args.xgen_base = comm->xgen;
+    args.xmode = 1;
+    if (const char *ex = getenv("NUPGCM_XMODE")) args.xmode = atoi(ex) != 0;
+    if (const char *ex = getenv("NUPGCM_XFENCE")) args.xfence = atoi(ex) != 0;
+    for (int p = 0; p < comm->nranks; ++p) args.arena[p] = comm->peer[p];
+    double *out = ctx->d_scalars;
+    int c = count, pb = publish, r = reps;
+    void *params[] = {&args, &c, &pb, &r, &out};
+    NUPGCM_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_diag_xreduce, dim3(grid), dim3(kThreads), params, 0, ctx->stream));
+    ctx->launches++;
+    NUPGCM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 14 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    cudaError_t es = cudaStreamSynchronize(ctx->stream);
+    if (es != cudaSuccess) { comm->broken = 1; NUPGCM_CUDA(ctx, es); }
+    if (ctx->h_scalars[7] != 0.0) {
+        comm->broken = 1;
+        return nupgcm_fail(ctx, NUPGCM_ERR_CUDA, "%s", "diag kernel aborted: cross-rank wait watchdog expired");
+    }
+    comm->xgen += (unsigned)ctx->h_scalars[13];
+    *us_per_reduction = (float)(ctx->h_scalars[1] * 1e-3 / reps);
     return NUPGCM_OK;
 }
 

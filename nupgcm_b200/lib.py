@@ -84,6 +84,7 @@ SIGNATURES = {
     "nupgcm_diag_reduce_latency": [_P, c_int32, c_int32, c_int32, c_int32, POINTER(c_float)],
     "nupgcm_diag_pingpong": [_P, c_int32, c_int32, c_int32, POINTER(c_float)],
     "nupgcm_diag_xping": [_P, c_int32, c_int32, c_int32, c_int32, POINTER(c_float)],
+    "nupgcm_diag_xreduce": [_P, c_int32, c_int32, c_int32, POINTER(c_float)],
     "nupgcm_mesh_create": [_P, c_int64, c_int32, _i32p, _i32p, _dp, _dp, c_int32, _dp, _dp, c_int64,
                            _dp, c_int64, c_int64, _dp, c_int64, POINTER(_P)],
     "nupgcm_mesh_destroy": [_P],
@@ -225,6 +226,11 @@ class Comm:
     def xping(self, rank_a=0, rank_b=1, variant=0, reps=2000) -> float:
         us = c_float()
         _check(self.lib.nupgcm_diag_xping(self.h, rank_a, rank_b, variant, reps, byref(us)), self.ctx.h)
+        return us.value
+
+    def xreduce(self, count=1, publish=False, reps=2000) -> float:
+        us = c_float()
+        _check(self.lib.nupgcm_diag_xreduce(self.h, count, int(publish), reps, byref(us)), self.ctx.h)
         return us.value
 
     def ipc_handle(self) -> bytes:

@@ -31,6 +31,13 @@ def main():
             us = comm.xping(0, b, variant, 5000)
             if rank == 0:
                 print(f"flag over NVLink rank0<->rank{b} {name:20s}: {us:6.2f} us one way", flush=True)
+    for xmode in ("1", "0"):
+        os.environ["NUPGCM_XMODE"] = xmode
+        for count, publish in ((1, 0), (1, 1), (1, 2), (10, 0), (20, 0)):
+            dist.barrier()
+            us = comm.xreduce(count, publish, 3000)
+            if rank == 0:
+                print(f"xmode={xmode} reduction of {count:2d} value(s), publish={int(publish)}: {us:6.2f} us ({world} ranks)", flush=True)
     y = ops["B"] @ ops["b_init"] + ops["b0"]
     dA = ctx.csr(A, drop_zeros=True).shard(comm)
     dy = ctx.vector(y)
