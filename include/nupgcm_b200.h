@@ -247,6 +247,15 @@ int32_t nupgcm_mesh_destroy(nupgcm_mesh *m);
 int32_t nupgcm_rhs_adv(nupgcm_mesh *m, int32_t scheme, double dt, double N2, const nupgcm_vec *b,
                        const nupgcm_vec *b_prev, const nupgcm_vec *u, const nupgcm_vec *u_prev,
                        nupgcm_vec *out);
+/* Adaptive timestep, update_Δt! of src/timesteppers.jl:108-119 (production runs use
+ * BDF1(adaptive=true), scratch/run.jl:163):
+ *   *dt_out = cfl_factor * min over cells of h_cells[c] / max(max_q |u(x_q)|, u_min)
+ * with the quadrature points of the mesh handle and h_cells = compute_h_cells (longest edge per
+ * cell, src/meshes.jl:127-134) set once with nupgcm_mesh_set_cell_sizes.  u: vector whose first nu
+ * entries are the velocity in solver order. */
+int32_t nupgcm_mesh_set_cell_sizes(nupgcm_mesh *m, const double *h_cells, int64_t n_cells);
+int32_t nupgcm_cfl_dt(nupgcm_mesh *m, const nupgcm_vec *u, double cfl_factor, double u_min,
+                      double *dt_out);
 /* out = rhs_adv + theta*rhs_diff + dt*rhs_flux − (rhs_m + theta*(rhs_h + rhs_v))  (src/model.jl:278) */
 int32_t nupgcm_rhs_combine(nupgcm_vec *out, const nupgcm_vec *rhs_adv, double theta, double dt,
                            const nupgcm_vec *rhs_diff, const nupgcm_vec *rhs_flux,

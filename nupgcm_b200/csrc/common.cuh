@@ -139,6 +139,8 @@ struct nupgcm_mesh {
     double *d_phi;                 // [nq][n_loc] basis values
     double *d_dphi;                // [nq][n_loc][n_vert] barycentric derivatives
     double *d_w;                   // [nq]
+    double *d_hcells;              // [n_cells] longest edge per cell (adaptive Δt)
+    unsigned long long *d_minbits; // scratch of the CFL minimum
 };
 
 static const int kStreamChunk = 4096;  // matrix entries per TMA pipeline stage of the streaming SpMV

@@ -111,6 +111,64 @@ k_elem(const int32_t *__restrict__ cell_b, const int32_t *__restrict__ cell_u,
     for (int i = 0; i < NLOC; ++i) elem[i * n_cells + c] = out[i];
 }
 
+// Adaptive timestep (reference src/timesteppers.jl:108-119): Δt = c · min_K h_K / max(|u|_{L∞(K)}, u_min),
+// |u|_{L∞(K)} being the largest Euclidean speed over the cell's quadrature points.  One thread per
+// cell; block minimum by shuffles, then atomicMin on the bit pattern (positive doubles order like
+// unsigned integers; min is exact, so the result does not depend on the order).
+template <int NV>
+__global__ void __launch_bounds__(128)
+k_cfl(const int32_t *__restrict__ cell_u, const double *__restrict__ bary, int nq, int64_t n_cells,
+      const double *__restrict__ u, const double *__restrict__ udir, int64_t nu,
+      const double *__restrict__ h_cells, double u_min, unsigned long long *__restrict__ min_bits) {
+    constexpr int NLOC = P2<NV>::NLOC;
+    constexpr int NE = P2<NV>::NE;
+    extern __shared__ double s_q[];               // bary[nq][NV]
+    __shared__ double s_min[4];
+    for (int i = threadIdx.x; i < nq * NV; i += blockDim.x) s_q[i] = bary[i];
+    __syncthreads();
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    double ratio = 1.7976931348623157e308;
+    if (c < n_cells) {
+        double us[NLOC][3];
+#pragma unroll
+        for (int i = 0; i < NLOC; ++i)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const int32_t iu = cell_u[(i * 3 + d) * n_cells + c];
+                us[i][d] = iu < nu ? u[iu] : udir[iu - nu];
+            }
+        double smax = 0.0;
+        for (int q = 0; q < nq; ++q) {
+            double lam[NV], uq[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int k = 0; k < NV; ++k) lam[k] = s_q[q * NV + k];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const double ph = lam[i] * (2.0 * lam[i] - 1.0);
+#pragma unroll
+                for (int d = 0; d < 3; ++d) uq[d] = fma(ph, us[i][d], uq[d]);
+            }
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                const double ph = 4.0 * lam[c_edge_a[e]] * lam[c_edge_b[e]];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) uq[d] = fma(ph, us[NV + e][d], uq[d]);
+            }
+            smax = fmax(smax, sqrt(uq[0] * uq[0] + uq[1] * uq[1] + uq[2] * uq[2]));
+        }
+        ratio = h_cells[c] / fmax(smax, u_min);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ratio = fmin(ratio, __shfl_xor_sync(0xffffffffu, ratio, o));
+    if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = ratio;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m = s_min[0];
+        for (int wv = 1; wv < (int)(blockDim.x >> 5); ++wv) m = fmin(m, s_min[wv]);
+        atomicMin(min_bits, (unsigned long long)__double_as_longlong(m));
+    }
+}
+
 __global__ void k_gather_elem(const int32_t *__restrict__ gptr, const int32_t *__restrict__ gidx,
                               const double *__restrict__ elem, double *__restrict__ out, int64_t nb) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nb;
@@ -224,6 +282,8 @@ extern "C" int32_t nupgcm_mesh_destroy(nupgcm_mesh *m) {
     cudaFree(m->d_phi);
     cudaFree(m->d_w);
     cudaFree(m->d_elem);
+    cudaFree(m->d_hcells);
+    cudaFree(m->d_minbits);
     free(m);
     return NUPGCM_OK;
 }
@@ -252,6 +312,47 @@ extern "C" int32_t nupgcm_rhs_adv(nupgcm_mesh *m, int32_t scheme, double dt, dou
         NUPGCM_CUDA(ctx, cudaGetLastError());
     }
     ctx->launches += 2;
+    return NUPGCM_OK;
+}
+
+extern "C" int32_t nupgcm_mesh_set_cell_sizes(nupgcm_mesh *m, const double *h_cells, int64_t n_cells) {
+    NUPGCM_REQUIRE(nullptr, m, "mesh is NULL");
+    nupgcm_ctx *ctx = m->ctx;
+    NUPGCM_REQUIRE(ctx, h_cells && n_cells == m->n_cells, "mesh_set_cell_sizes: NULL sizes or cell count mismatch");
+    for (int64_t c = 0; c < n_cells; ++c)
+        if (!(h_cells[c] > 0.0)) return nupgcm_fail(ctx, NUPGCM_ERR_INVALID, "invalid argument: %s", "mesh_set_cell_sizes: sizes must be positive");
+    NUPGCM_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!m->d_hcells) NUPGCM_CUDA(ctx, cudaMalloc(&m->d_hcells, (size_t)n_cells * sizeof(double)));
+    if (!m->d_minbits) NUPGCM_CUDA(ctx, cudaMalloc(&m->d_minbits, sizeof(unsigned long long)));
+    NUPGCM_CUDA(ctx, cudaMemcpyAsync(m->d_hcells, h_cells, (size_t)n_cells * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    NUPGCM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NUPGCM_OK;
+}
+
+extern "C" int32_t nupgcm_cfl_dt(nupgcm_mesh *m, const nupgcm_vec *u, double cfl_factor, double u_min,
+                                 double *dt_out) {
+    NUPGCM_REQUIRE(nullptr, m && u && dt_out, "cfl_dt: NULL argument");
+    nupgcm_ctx *ctx = m->ctx;
+    NUPGCM_REQUIRE(ctx, m->d_hcells, "cfl_dt: call nupgcm_mesh_set_cell_sizes first");
+    NUPGCM_REQUIRE(ctx, u->n >= m->nu, "cfl_dt: velocity vector shorter than nu");
+    NUPGCM_REQUIRE(ctx, cfl_factor > 0.0 && u_min > 0.0, "cfl_dt: cfl_factor and u_min must be positive");
+    const unsigned long long inf_bits = 0x7fefffffffffffffULL;     // largest finite double
+    NUPGCM_CUDA(ctx, cudaMemcpyAsync(m->d_minbits, &inf_bits, sizeof(inf_bits), cudaMemcpyHostToDevice, ctx->stream));
+    const int block = 128;
+    const int grid = (int)((m->n_cells + block - 1) / block);
+    const size_t smem = (size_t)m->nq * m->n_vert * sizeof(double);
+    if (m->n_vert == 4)
+        k_cfl<4><<<grid, block, smem, ctx->stream>>>(m->d_cell_u, m->d_phi, m->nq, m->n_cells, u->d, m->d_udir, m->nu, m->d_hcells, u_min, m->d_minbits);
+    else
+        k_cfl<3><<<grid, block, smem, ctx->stream>>>(m->d_cell_u, m->d_phi, m->nq, m->n_cells, u->d, m->d_udir, m->nu, m->d_hcells, u_min, m->d_minbits);
+    ctx->launches++;
+    NUPGCM_CUDA(ctx, cudaGetLastError());
+    unsigned long long bits = 0;
+    NUPGCM_CUDA(ctx, cudaMemcpyAsync(&bits, m->d_minbits, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
+    NUPGCM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double r;
+    memcpy(&r, &bits, sizeof(r));
+    *dt_out = cfl_factor * r;
     return NUPGCM_OK;
 }
 

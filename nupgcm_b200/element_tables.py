@@ -9,6 +9,7 @@ from __future__ import annotations
 import numpy as np
 
 from .dofs import FEData
+from .meshes import compute_h_cells
 
 
 def _extended_index(owner_dofs, inv_perm, nfree):
@@ -37,4 +38,5 @@ def element_tables(fe_data: FEData) -> dict:
         "nb": Bs.nfree, "nu": U.nfree,
         "b_dirichlet": Bs.dirichlet_values.copy(), "u_dirichlet": U.dirichlet_values.copy(),
         "rule": integ.rule,
+        "h_cells": compute_h_cells(fe_data.mesh),           # for update_Δt! (timesteppers.jl:108-119)
     }

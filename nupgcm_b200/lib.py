@@ -88,6 +88,8 @@ SIGNATURES = {
     "nupgcm_mesh_create": [_P, c_int64, c_int32, _i32p, _i32p, _dp, _dp, c_int32, _dp, _dp, c_int64,
                            _dp, c_int64, c_int64, _dp, c_int64, POINTER(_P)],
     "nupgcm_mesh_destroy": [_P],
+    "nupgcm_mesh_set_cell_sizes": [_P, _dp, c_int64],
+    "nupgcm_cfl_dt": [_P, _P, c_double, c_double, _dp],
     "nupgcm_rhs_adv": [_P, c_int32, c_double, c_double, _P, _P, _P, _P, _P],
     "nupgcm_rhs_combine": [_P, _P, c_double, c_double, _P, _P, _P, _P, _P],
 }
@@ -490,6 +492,8 @@ class ElementMesh:
             _ptr(vol), w.size, _ptr(bary), _ptr(w), int(tables["nb"]), _ptr(bd), bd.size,
             int(tables["nu"]), _ptr(ud), ud.size, byref(h)), ctx.h)
         self.h = h
+        if "h_cells" in tables:
+            self.set_cell_sizes(tables["h_cells"])
 
     def __del__(self):
         try:
@@ -497,6 +501,16 @@ class ElementMesh:
                 self.lib.nupgcm_mesh_destroy(self.h)
         except Exception:
             pass
+
+    def set_cell_sizes(self, h_cells):
+        h = _f64(h_cells)
+        _check(self.lib.nupgcm_mesh_set_cell_sizes(self.h, _ptr(h), h.size), self.ctx.h)
+        return self
+
+    def cfl_dt(self, u: Vector, cfl_factor=0.8, u_min=0.01) -> float:
+        out = c_double()
+        _check(self.lib.nupgcm_cfl_dt(self.h, u.h, float(cfl_factor), float(u_min), byref(out)), self.ctx.h)
+        return out.value
 
     def rhs_adv(self, scheme, dt, N2, b, b_prev, u, u_prev, out):
         _check(self.lib.nupgcm_rhs_adv(self.h, int(scheme), float(dt), float(N2), b.h, b_prev.h,

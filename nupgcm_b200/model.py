@@ -106,6 +106,10 @@ def evolve_(model: Model, u_prev: lib.Vector, b_prev: lib.Vector):
     ts = model.timestepper
     solver = ev.solver
     θ = evolution_parameter(model.params, ts)                      # model.jl:227
+    if ts.adaptive:
+        # A = M + θ(Kₕ+Kᵥ), P = 1/diag(A) with this step's Δt (model.jl:251-261): two kernels on the
+        # device-resident operands instead of a host sparse add + CSC->CSR + upload
+        collect_evolution_LHS_(ev, model.params, model.forcings, ts)
     model.mesh.rhs_adv(ts.scheme, ts.Δt, model.params.N2, model.xb, b_prev,
                        model.inversion.solver.x, u_prev, model._rhs_adv)   # model.jl:269-275
     lib.rhs_combine(solver.y, model._rhs_adv, θ, ts.Δt, ev.rhs_diff, ev.rhs_flux, ev.rhs_m,
@@ -130,7 +134,7 @@ def run_(model: Model, n_info=10, n_save=float("inf"), n_steps=None, sync_state=
     i = getattr(model, "_step_index", 1)
     done = 0
     while ts.t < ts.t_stop and (n_steps is None or done < n_steps):
-        update_Δt_(ts)                                              # model.jl:131
+        update_Δt_(ts, model.mesh, xu)                              # model.jl:131
         if i == 2 and isinstance(ts, BDF2):
             collect_evolution_LHS_(model.evolution, model.params, model.forcings, ts)  # :134-137
         if sync_state and host_state is not None:

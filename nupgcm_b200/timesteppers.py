@@ -1,6 +1,6 @@
 """Timesteppers.  Mirrors reference ``src/timesteppers.jl:7-29`` (BDF1), ``:36-63`` (BDF2),
-``:80-83`` (``update_t!``).  ``update_Δt!`` (adaptive CFL, ``:108-119``) is a "next" row of the
-scope table: ``adaptive=True`` is rejected for now."""
+``:80-83`` (``update_t!``) and ``:108-122`` (``update_Δt!``: CFL-adaptive Δt for BDF1, evaluated
+on the device by ``nupgcm_cfl_dt``; a no-op for BDF2)."""
 from __future__ import annotations
 
 
@@ -20,9 +20,8 @@ class BDF1(AbstractTimestepper):
 
     def __init__(self, *, t_start, t_stop, Δt, t=None, adaptive=False, CFL_factor=0.8):
         super().__init__(t_start, t_stop, Δt, t)
-        if adaptive:
-            raise NotImplementedError("adaptive Δt is not on the B200 path yet (SURVEY.md §8 f-1)")
-        self.CFL_factor = CFL_factor
+        self.adaptive = bool(adaptive)
+        self.CFL_factor = float(CFL_factor)
 
 
 class BDF2(AbstractTimestepper):
@@ -38,8 +37,12 @@ def update_t_(ts: AbstractTimestepper):
     return ts
 
 
-def update_Δt_(ts, *args, **kw):
-    """``update_Δt!`` — a no-op for fixed-Δt steppers (timesteppers.jl:120-122)."""
+def update_Δt_(ts, mesh=None, u=None, u_min=0.01):
+    """``update_Δt!`` (timesteppers.jl:108-122): Δt = CFL_factor · min_K h_K / max(|u|_{L∞(K)}, u_min)
+    for an adaptive BDF1 — one kernel over the cells of ``mesh`` (a ``lib.ElementMesh``) and the
+    device velocity ``u`` — and a no-op otherwise."""
+    if getattr(ts, "adaptive", False):
+        ts.Δt = mesh.cfl_dt(u, ts.CFL_factor, u_min)
     return ts
 
 

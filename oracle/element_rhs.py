@@ -66,6 +66,17 @@ def rhs_adv(tables, scheme, dt, N2, b, b_prev, u, u_prev):
     return out[:tables["nb"]]
 
 
+def cfl_dt(tables, u, cfl_factor=0.8, u_min=0.01):
+    """``update_Δt!`` of reference ``src/timesteppers.jl:108-119``: c · min_K h_K / max(|u|_{L∞(K)},
+    u_min) with |u|_{L∞(K)} the largest Euclidean speed over the cell's quadrature points and
+    h_K = ``tables["h_cells"]`` (``compute_h_cells``, src/meshes.jl:127-134)."""
+    phi, _ = _p2(tables["bary"])
+    ux = np.concatenate([u, tables["u_dirichlet"]])
+    uq = np.einsum("qi,cid->cqd", phi, ux[tables["cell_u"]])
+    speed = np.sqrt((uq ** 2).sum(axis=2)).max(axis=1)
+    return cfl_factor * float(np.min(tables["h_cells"] / np.maximum(speed, u_min)))
+
+
 def rhs_combine(rhs_adv_v, θ, dt, rhs_diff, rhs_flux, rhs_m, rhs_h, rhs_v):
     """``y = rhs_adv + θ rhs_diff + Δt rhs_flux − (rhsₘ + θ (rhsₕ + rhsᵥ))`` (model.jl:278)."""
     return rhs_adv_v + θ * rhs_diff + dt * rhs_flux - (rhs_m + θ * (rhs_h + rhs_v))

@@ -27,17 +27,21 @@ import numpy as np
 import scipy.sparse.linalg as spla
 
 from . import krylov
-from .element_rhs import rhs_adv, rhs_combine
+from .element_rhs import cfl_dt, rhs_adv, rhs_combine
 
 
 class CpuModel:
     def __init__(self, ops: dict, params: dict, scheme: int, dt: float, t_start: float,
                  t_stop: float, solver: str = "direct", atol=1e-6, rtol=1e-6, memory=20,
-                 orth="mgs"):
+                 orth="mgs", adaptive=False, cfl_factor=0.8):
         self.ops = ops
         self.α, self.ε, self.μϱ, self.N2 = (params[k] for k in ("α", "ε", "μϱ", "N2"))
         self.scheme, self.dt, self.t, self.t_stop = scheme, dt, t_start, t_stop
         self.solver = solver
+        # BDF1(adaptive=true): Δt from the CFL condition every step (timesteppers.jl:108-119) and the
+        # LHS re-formed (and, on the reference's CPU path, re-factorised) every step (model.jl:251-261)
+        self.adaptive, self.cfl_factor = adaptive, cfl_factor
+        self.dts = []
         self.kw = dict(atol=atol, rtol=rtol)
         self.memory, self.orth = memory, orth
         self.xu = np.zeros(ops["A"].shape[0])        # [u; p] in solver order
@@ -78,6 +82,8 @@ class CpuModel:
         o = self.ops
         nu = o["nu"]
         θ = self.theta(self.scheme)
+        if self.adaptive:
+            self._lhs(self.scheme)
         adv = rhs_adv(o["tables"], self.scheme, self.dt, self.N2, self.xb, b_prev,
                       self.xu[:nu], u_prev[:nu])
         y = rhs_combine(adv, θ, self.dt, o["rhs_diff"], o["rhs_flux"], o["rhs_m"], o["rhs_h"],
@@ -93,6 +99,9 @@ class CpuModel:
         u_prev, b_prev = self.xu.copy(), self.xb.copy()
         done = 0
         while self.t < self.t_stop and (n_steps is None or done < n_steps):
+            if self.adaptive:
+                self.dt = cfl_dt(self.ops["tables"], self.xu[:self.ops["nu"]], self.cfl_factor)
+                self.dts.append(self.dt)
             if self.i == 2 and self.scheme == 2:
                 self._lhs(2)
             u_curr, b_curr = self.xu.copy(), self.xb.copy()
@@ -118,6 +127,7 @@ def cpu_model_for(workload, ops=None, **kw):
     ops = host_operands(workload) if ops is None else ops
     p = workload.params
     tk = workload.timestepper_kwargs
-    m = CpuModel(ops, {"α": p.α, "ε": p.ε, "μϱ": p.μϱ, "N2": p.N2}, 2, tk["Δt"], tk["t_start"],
+    scheme = kw.pop("scheme", 2)
+    m = CpuModel(ops, {"α": p.α, "ε": p.ε, "μϱ": p.μϱ, "N2": p.N2}, scheme, tk["Δt"], tk["t_start"],
                  tk["t_stop"], **kw)
     return m
