@@ -63,6 +63,16 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(kernel="k_gmres"):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/ncu_traffic_r01.json, written from tools/profile_round.sh output); None if absent."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+    try:
+        return float(json.load(open(p))[kernel]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def spmv_bytes(n, nnz):
     return 12.0 * nnz + 20.0 * n                           # SURVEY.md §8(d)
 
@@ -339,7 +349,10 @@ def main():
     roofline = {"bound": "hbm", "kernel": "k_gmres (persistent GMRES(20), one launch per invert!"
                                           + (f", sharded over {world} GPUs)" if world > 1 else ")"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": measured_traffic() if world == 1 else None, "peak_source": peak_src,
+                "traffic_note": "DRAM read+write bytes of one k_gmres launch (ncu --set full, "
+                                "profiles/ncu_gmres_r01.txt): the matrix is read from HBM once per solve and "
+                                "then served from shared memory, so traffic << algorithmic bytes",
                 "algorithmic_bytes_per_launch": g_bytes, "ms_per_launch": float(g_ms.mean()),
                 "nnz_counted": nnz, "share_of_step": float(g_ms.sum() / total_ms)}
 
