@@ -256,6 +256,14 @@ int32_t nupgcm_rhs_adv(nupgcm_mesh *m, int32_t scheme, double dt, double N2, con
 int32_t nupgcm_mesh_set_cell_sizes(nupgcm_mesh *m, const double *h_cells, int64_t n_cells);
 int32_t nupgcm_cfl_dt(nupgcm_mesh *m, const nupgcm_vec *u, double cfl_factor, double u_min,
                       double *dt_out);
+/* Convection parameterisation (src/model.jl:229-246, src/inputs.jl:87-91): per-step rebuild of
+ *   Kv = ∫ κᵥ ∂z b ∂z d,  rhs_v = ∫ κᵥ ∂z b_diri ∂z d,  rhs_diff = ∫ −N² κᵥ ∂z d
+ * with κᵥ(x_q) = kv_q[c*nq+q] + kappa_c (1 + tanh(−alpha (N2 + ∂z b)(x_q) / N2min)) / 2, replacing
+ * the CPU build_Kᵥ / build_rhs_diff + permutation + upload.  `pattern` / `Kv`: nb x nb matrices in
+ * solver order created with drop_zeros = 0 from the evolution pattern (M, Kh, Kv share it). */
+int32_t nupgcm_mesh_enable_kv_rebuild(nupgcm_mesh *m, const nupgcm_csr *pattern, const double *kv_q);
+int32_t nupgcm_rebuild_kv(nupgcm_mesh *m, double alpha, double N2, double kappa_c, double N2min,
+                          const nupgcm_vec *b, nupgcm_csr *Kv, nupgcm_vec *rhs_v, nupgcm_vec *rhs_diff);
 /* out = rhs_adv + theta*rhs_diff + dt*rhs_flux − (rhs_m + theta*(rhs_h + rhs_v))  (src/model.jl:278) */
 int32_t nupgcm_rhs_combine(nupgcm_vec *out, const nupgcm_vec *rhs_adv, double theta, double dt,
                            const nupgcm_vec *rhs_diff, const nupgcm_vec *rhs_flux,

@@ -141,6 +141,11 @@ struct nupgcm_mesh {
     double *d_w;                   // [nq]
     double *d_hcells;              // [n_cells] longest edge per cell (adaptive Δt)
     unsigned long long *d_minbits; // scratch of the CFL minimum
+    // Kᵥ rebuild (convection parameterisation): per stored matrix entry, its element-matrix slots
+    int32_t *d_kptr, *d_kidx;
+    double *d_kvq;                 // [n_cells][nq] base κᵥ at the quadrature points
+    double *d_emat, *d_evec;       // [n_loc*n_loc][n_cells], 2 x [n_loc][n_cells]
+    int64_t kv_nnz;
 };
 
 static const int kStreamChunk = 4096;  // matrix entries per TMA pipeline stage of the streaming SpMV

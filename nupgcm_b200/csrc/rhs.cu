@@ -9,6 +9,7 @@
 //      cell's DOF indices, Dirichlet values living behind the free ones);
 //   2. k_gather: one thread per free buoyancy DOF sums its elemental slots in a FIXED order
 //      (sorted by cell id at set-up), so the result is independent of scheduling and GPU count.
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -169,6 +170,88 @@ k_cfl(const int32_t *__restrict__ cell_u, const double *__restrict__ bary, int n
     }
 }
 
+// Convection parameterisation (reference src/model.jl:229-246, src/inputs.jl:87-91): every step
+//   κᵥ(x_q) = κᵥ⁰(x_q) + κᶜ (1 + tanh(−α(N² + ∂z b)(x_q) / N²min)) / 2
+// and Kᵥ = ∫ κᵥ ∂z b ∂z d, rhsᵥ = ∫ κᵥ ∂z b_diri ∂z d, rhs_diff = ∫ −N² κᵥ ∂z d are re-assembled
+// (src/evolution.jl:243-246,256-260,269-278).  The reference does this on the CPU with Gridap and
+// uploads the results; here one thread per cell writes the cell's 10x10 element matrix and two
+// element vectors to [slot][cell] arrays, and gather kernels add each matrix entry's / DOF's
+// slots in a fixed order (sorted by cell): no atomics, bitwise reproducible.
+template <int NV>
+__global__ void __launch_bounds__(128)
+k_kv_elem(const int32_t *__restrict__ cell_b, const double *__restrict__ grad, const double *__restrict__ vol,
+          const double *__restrict__ bary, const double *__restrict__ w, int nq, int64_t n_cells,
+          const double *__restrict__ b, const double *__restrict__ bdir, int64_t nb,
+          const double *__restrict__ kv_q, double alpha, double N2, double kappa_c, double N2min,
+          double *__restrict__ emat, double *__restrict__ evec_v, double *__restrict__ evec_d) {
+    constexpr int NLOC = P2<NV>::NLOC;
+    constexpr int MAXQ = 16;
+    extern __shared__ double s_q[];               // bary[nq][NV], w[nq]
+    for (int i = threadIdx.x; i < nq * NV; i += blockDim.x) s_q[i] = bary[i];
+    for (int i = threadIdx.x; i < nq; i += blockDim.x) s_q[nq * NV + i] = w[i];
+    __syncthreads();
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    double bv[NLOC], bd[NLOC], gz[NV];
+#pragma unroll
+    for (int i = 0; i < NLOC; ++i) {
+        const int32_t ib = cell_b[i * n_cells + c];
+        bv[i] = ib < nb ? b[ib] : bdir[ib - nb];
+        bd[i] = ib < nb ? 0.0 : bdir[ib - nb];        // b_diri: Dirichlet values, zero elsewhere
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) gz[k] = grad[(k * 3 + 2) * n_cells + c];
+    const double vc = vol[c];
+    // ∂z φ_i at quadrature point q
+    auto dz = [&](int q, int i) -> double {
+        const double *lam = s_q + q * NV;
+        if (i < NV) return (4.0 * lam[i] - 1.0) * gz[i];
+        const int ia = c_edge_a[i - NV], ib = c_edge_b[i - NV];
+        return 4.0 * fma(lam[ia], gz[ib], lam[ib] * gz[ia]);
+    };
+    double kq[MAXQ], dbd[MAXQ];                       // w_q |K| κᵥ(x_q) and ∂z b_diri(x_q)
+    for (int q = 0; q < nq; ++q) {
+        double dzb = 0.0, dzd = 0.0;
+#pragma unroll
+        for (int i = 0; i < NLOC; ++i) {
+            const double d = dz(q, i);
+            dzb = fma(bv[i], d, dzb);
+            dzd = fma(bd[i], d, dzd);
+        }
+        const double abz = alpha * (N2 + dzb);
+        const double kap = kv_q[c * (int64_t)nq + q] + kappa_c * (1.0 + tanh(-abz / N2min)) * 0.5;
+        kq[q] = s_q[nq * NV + q] * vc * kap;
+        dbd[q] = dzd;
+    }
+    for (int i = 0; i < NLOC; ++i) {
+        double row[NLOC], rv = 0.0, rd = 0.0;
+#pragma unroll
+        for (int j = 0; j < NLOC; ++j) row[j] = 0.0;
+        for (int q = 0; q < nq; ++q) {
+            const double di = kq[q] * dz(q, i);
+            rv = fma(di, dbd[q], rv);
+            rd = fma(di, -N2, rd);
+#pragma unroll
+            for (int j = 0; j < NLOC; ++j) row[j] = fma(di, dz(q, j), row[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < NLOC; ++j) emat[(size_t)(i * NLOC + j) * n_cells + c] = row[j];
+        evec_v[(size_t)i * n_cells + c] = rv;
+        evec_d[(size_t)i * n_cells + c] = rd;
+    }
+}
+
+// one thread per stored matrix entry: add its element-matrix slots in the fixed (cell) order
+__global__ void k_gather_mat(const int32_t *__restrict__ kptr, const int32_t *__restrict__ kidx,
+                             const double *__restrict__ emat, double *__restrict__ vals, int64_t nnz) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nnz;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int32_t k = kptr[e]; k < kptr[e + 1]; ++k) acc += emat[kidx[k]];
+        vals[e] = acc;
+    }
+}
+
 __global__ void k_gather_elem(const int32_t *__restrict__ gptr, const int32_t *__restrict__ gidx,
                               const double *__restrict__ elem, double *__restrict__ out, int64_t nb) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nb;
@@ -284,6 +367,11 @@ extern "C" int32_t nupgcm_mesh_destroy(nupgcm_mesh *m) {
     cudaFree(m->d_elem);
     cudaFree(m->d_hcells);
     cudaFree(m->d_minbits);
+    cudaFree(m->d_kptr);
+    cudaFree(m->d_kidx);
+    cudaFree(m->d_kvq);
+    cudaFree(m->d_emat);
+    cudaFree(m->d_evec);
     free(m);
     return NUPGCM_OK;
 }
@@ -353,6 +441,90 @@ extern "C" int32_t nupgcm_cfl_dt(nupgcm_mesh *m, const nupgcm_vec *u, double cfl
     double r;
     memcpy(&r, &bits, sizeof(r));
     *dt_out = cfl_factor * r;
+    return NUPGCM_OK;
+}
+
+extern "C" int32_t nupgcm_mesh_enable_kv_rebuild(nupgcm_mesh *m, const nupgcm_csr *pattern, const double *kv_q) {
+    NUPGCM_REQUIRE(nullptr, m && pattern, "mesh_enable_kv_rebuild: NULL argument");
+    nupgcm_ctx *ctx = m->ctx;
+    NUPGCM_REQUIRE(ctx, kv_q, "mesh_enable_kv_rebuild: NULL kv_q");
+    NUPGCM_REQUIRE(ctx, !pattern->dropped && pattern->n_rows == m->nb && pattern->n_cols == m->nb,
+                   "mesh_enable_kv_rebuild: pattern must be the nb x nb evolution pattern created with drop_zeros=0");
+    NUPGCM_REQUIRE(ctx, m->nq <= 16, "mesh_enable_kv_rebuild: at most 16 quadrature points");
+    const int64_t nc = m->n_cells, nnz = pattern->nnz;
+    const int nl = m->n_loc;
+    NUPGCM_REQUIRE(ctx, (int64_t)nl * nl * nc < INT32_MAX, "mesh_enable_kv_rebuild: mesh too large for int32 slots");
+    // host copy of the transposed cell_b table
+    std::vector<int32_t> tb((size_t)nc * nl);
+    NUPGCM_CUDA(ctx, cudaSetDevice(ctx->device));
+    NUPGCM_CUDA(ctx, cudaMemcpy(tb.data(), m->d_cell_b, tb.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    const int32_t *rp = pattern->h_rowptr, *col = pattern->h_col;
+    std::vector<int32_t> kptr(nnz + 1, 0), pos((size_t)nc * nl * nl, -1);
+    for (int64_t c = 0; c < nc; ++c)
+        for (int i = 0; i < nl; ++i) {
+            const int32_t r = tb[(size_t)i * nc + c];
+            if (r >= m->nb) continue;
+            for (int j = 0; j < nl; ++j) {
+                const int32_t cc = tb[(size_t)j * nc + c];
+                if (cc >= m->nb) continue;
+                const int32_t *lo = std::lower_bound(col + rp[r], col + rp[r + 1], cc);
+                if (lo == col + rp[r + 1] || *lo != cc)
+                    return nupgcm_fail(ctx, NUPGCM_ERR_INVALID, "invalid argument: %s",
+                                       "mesh_enable_kv_rebuild: a cell couples two DOFs that the pattern does not store");
+                const int32_t e = (int32_t)(lo - col);
+                pos[((size_t)c * nl + i) * nl + j] = e;
+                kptr[e + 1]++;
+            }
+        }
+    for (int64_t e = 0; e < nnz; ++e) kptr[e + 1] += kptr[e];
+    std::vector<int32_t> kidx(kptr[nnz]), fill(kptr.begin(), kptr.end() - 1);
+    for (int64_t c = 0; c < nc; ++c)               // cells in order -> each entry's slots sorted by cell
+        for (int i = 0; i < nl; ++i)
+            for (int j = 0; j < nl; ++j) {
+                const int32_t e = pos[((size_t)c * nl + i) * nl + j];
+                if (e >= 0) kidx[fill[e]++] = (int32_t)((int64_t)(i * nl + j) * nc + c);
+            }
+    cudaFree(m->d_kptr); cudaFree(m->d_kidx); cudaFree(m->d_kvq); cudaFree(m->d_emat); cudaFree(m->d_evec);
+    m->d_kptr = m->d_kidx = nullptr; m->d_kvq = m->d_emat = m->d_evec = nullptr;
+    NUPGCM_CUDA(ctx, upload(&m->d_kptr, kptr));
+    NUPGCM_CUDA(ctx, upload(&m->d_kidx, kidx));
+    NUPGCM_CUDA(ctx, upload(&m->d_kvq, std::vector<double>(kv_q, kv_q + (size_t)nc * m->nq)));
+    NUPGCM_CUDA(ctx, cudaMalloc(&m->d_emat, (size_t)nc * nl * nl * sizeof(double)));
+    NUPGCM_CUDA(ctx, cudaMalloc(&m->d_evec, 2 * (size_t)nc * nl * sizeof(double)));
+    m->kv_nnz = nnz;
+    NUPGCM_CUDA(ctx, cudaDeviceSynchronize());
+    return NUPGCM_OK;
+}
+
+extern "C" int32_t nupgcm_rebuild_kv(nupgcm_mesh *m, double alpha, double N2, double kappa_c, double N2min,
+                                     const nupgcm_vec *b, nupgcm_csr *Kv, nupgcm_vec *rhs_v, nupgcm_vec *rhs_diff) {
+    NUPGCM_REQUIRE(nullptr, m && b && Kv && rhs_v && rhs_diff, "rebuild_kv: NULL argument");
+    nupgcm_ctx *ctx = m->ctx;
+    NUPGCM_REQUIRE(ctx, m->d_kptr, "rebuild_kv: call nupgcm_mesh_enable_kv_rebuild first");
+    NUPGCM_REQUIRE(ctx, !Kv->dropped && Kv->nnz == m->kv_nnz && Kv->n_rows == m->nb, "rebuild_kv: Kv does not have the bound pattern");
+    NUPGCM_REQUIRE(ctx, b->n == m->nb && rhs_v->n == m->nb && rhs_diff->n == m->nb, "rebuild_kv: vector length mismatch");
+    NUPGCM_REQUIRE(ctx, N2min != 0.0, "rebuild_kv: N2min must be non-zero");
+    const int block = 128;
+    const int grid = (int)((m->n_cells + block - 1) / block);
+    const size_t smem = (size_t)m->nq * (m->n_vert + 1) * sizeof(double);
+    double *ev = m->d_evec, *ed = m->d_evec + (size_t)m->n_cells * m->n_loc;
+    if (m->n_vert == 4)
+        k_kv_elem<4><<<grid, block, smem, ctx->stream>>>(m->d_cell_b, m->d_grad, m->d_vol, m->d_phi, m->d_w, m->nq, m->n_cells, b->d, m->d_bdir, m->nb, m->d_kvq, alpha, N2, kappa_c, N2min, m->d_emat, ev, ed);
+    else
+        k_kv_elem<3><<<grid, block, smem, ctx->stream>>>(m->d_cell_b, m->d_grad, m->d_vol, m->d_phi, m->d_w, m->nq, m->n_cells, b->d, m->d_bdir, m->nb, m->d_kvq, alpha, N2, kappa_c, N2min, m->d_emat, ev, ed);
+    NUPGCM_CUDA(ctx, cudaGetLastError());
+    int g = (int)std::min<int64_t>((m->kv_nnz + 255) / 256, (int64_t)ctx->sm_count * 8);
+    if (g < 1) g = 1;
+    k_gather_mat<<<g, 256, 0, ctx->stream>>>(m->d_kptr, m->d_kidx, m->d_emat, Kv->d_vals, m->kv_nnz);
+    NUPGCM_CUDA(ctx, cudaGetLastError());
+    Kv->vals_version++;
+    if (m->nb > 0) {
+        int g2 = (int)std::min<int64_t>((m->nb + 255) / 256, (int64_t)ctx->sm_count * 8);
+        k_gather_elem<<<g2, 256, 0, ctx->stream>>>(m->d_gptr, m->d_gidx, ev, rhs_v->d, m->nb);
+        k_gather_elem<<<g2, 256, 0, ctx->stream>>>(m->d_gptr, m->d_gidx, ed, rhs_diff->d, m->nb);
+        NUPGCM_CUDA(ctx, cudaGetLastError());
+    }
+    ctx->launches += 4;
     return NUPGCM_OK;
 }
 

@@ -90,6 +90,8 @@ SIGNATURES = {
     "nupgcm_mesh_destroy": [_P],
     "nupgcm_mesh_set_cell_sizes": [_P, _dp, c_int64],
     "nupgcm_cfl_dt": [_P, _P, c_double, c_double, _dp],
+    "nupgcm_mesh_enable_kv_rebuild": [_P, _P, _dp],
+    "nupgcm_rebuild_kv": [_P, c_double, c_double, c_double, c_double, _P, _P, _P, _P],
     "nupgcm_rhs_adv": [_P, c_int32, c_double, c_double, _P, _P, _P, _P, _P],
     "nupgcm_rhs_combine": [_P, _P, c_double, c_double, _P, _P, _P, _P, _P],
 }
@@ -511,6 +513,15 @@ class ElementMesh:
         out = c_double()
         _check(self.lib.nupgcm_cfl_dt(self.h, u.h, float(cfl_factor), float(u_min), byref(out)), self.ctx.h)
         return out.value
+
+    def enable_kv_rebuild(self, pattern: "CsrMatrix", kv_q):
+        kv = _f64(kv_q)
+        _check(self.lib.nupgcm_mesh_enable_kv_rebuild(self.h, pattern.h, _ptr(kv)), self.ctx.h)
+        return self
+
+    def rebuild_kv(self, alpha, N2, kappa_c, N2min, b: Vector, Kv: "CsrMatrix", rhs_v: Vector, rhs_diff: Vector):
+        _check(self.lib.nupgcm_rebuild_kv(self.h, float(alpha), float(N2), float(kappa_c), float(N2min),
+                                          b.h, Kv.h, rhs_v.h, rhs_diff.h), self.ctx.h)
 
     def rhs_adv(self, scheme, dt, N2, b, b_prev, u, u_prev, out):
         _check(self.lib.nupgcm_rhs_adv(self.h, int(scheme), float(dt), float(N2), b.h, b_prev.h,

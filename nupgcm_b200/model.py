@@ -74,6 +74,10 @@ class Model:
         if evolution is not None:
             self.mesh = lib.ElementMesh(ctx, tables if tables is not None else element_tables(fe_data))
             self._rhs_adv = ctx.vector(nb)
+            if forcings.conv_param.is_on:
+                # base κᵥ at the quadrature points of every cell; the device adds the convective part
+                kv_q = fe_data.mesh.dΩ.coefficient(forcings.κᵥ, slice(None))
+                self.mesh.enable_kv_rebuild(evolution.Kv, kv_q)
             self._b_prev, self._b_curr = ctx.vector(nb), ctx.vector(nb)
             self._u_prev, self._u_curr = ctx.vector(N), ctx.vector(N)
 
@@ -106,9 +110,14 @@ def evolve_(model: Model, u_prev: lib.Vector, b_prev: lib.Vector):
     ts = model.timestepper
     solver = ev.solver
     θ = evolution_parameter(model.params, ts)                      # model.jl:227
-    if ts.adaptive:
-        # A = M + θ(Kₕ+Kᵥ), P = 1/diag(A) with this step's Δt (model.jl:251-261): two kernels on the
-        # device-resident operands instead of a host sparse add + CSC->CSR + upload
+    conv = model.forcings.conv_param
+    if conv.is_on:
+        # κᵥ(α ∂z b_total) -> Kᵥ, rhsᵥ, rhs_diff re-assembled on the device (model.jl:229-246)
+        model.mesh.rebuild_kv(model.params.α, model.params.N2, conv.κᶜ, conv.N2min, model.xb,
+                              ev.Kv, ev.rhs_v, ev.rhs_diff)
+    if conv.is_on or ts.adaptive:
+        # A = M + θ(Kₕ+Kᵥ), P = 1/diag(A) with this step's Δt / Kᵥ (model.jl:251-261): two kernels on
+        # the device-resident operands instead of a host sparse add + CSC->CSR + upload
         collect_evolution_LHS_(ev, model.params, model.forcings, ts)
     model.mesh.rhs_adv(ts.scheme, ts.Δt, model.params.N2, model.xb, b_prev,
                        model.inversion.solver.x, u_prev, model._rhs_adv)   # model.jl:269-275

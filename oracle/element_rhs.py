@@ -77,6 +77,45 @@ def cfl_dt(tables, u, cfl_factor=0.8, u_min=0.01):
     return cfl_factor * float(np.min(tables["h_cells"] / np.maximum(speed, u_min)))
 
 
+def kv_rebuild(tables, kv_q, α, N2, κc, N2min, b, pattern):
+    """Convection parameterisation, reference ``src/model.jl:229-246``: κᵥ(x_q) = κᵥ⁰(x_q) +
+    κᶜ(1 + tanh(−α(N² + ∂z b)/N²min))/2 (``src/inputs.jl:87-91``), then ``build_Kᵥ``
+    (``src/evolution.jl:243-246``: Kᵥ = ∫κᵥ ∂z b ∂z d and the Dirichlet lift rhsᵥ = a(b_diri, d),
+    ``:256-260``) and ``build_rhs_diff`` (``:269-278``: ∫ −N² κᵥ ∂z d), all in solver order.
+
+    ``pattern``: SciPy CSR with the evolution sparsity pattern (values ignored).  Returns
+    ``(Kv_csr, rhs_v, rhs_diff)``."""
+    import scipy.sparse as sp
+    cb = tables["cell_b"]
+    nb = tables["nb"]
+    _, dphi = _p2(tables["bary"])
+    gz = tables["grad"][:, :, 2]                                          # (nc, d+1)
+    dz = np.einsum("qik,ck->cqi", dphi, gz)                               # ∂z φ_i at q
+    bx = np.concatenate([b, tables["b_dirichlet"]])
+    bdx = np.concatenate([np.zeros(nb), tables["b_dirichlet"]])
+    dzb = np.einsum("cqi,ci->cq", dz, bx[cb])
+    dzd = np.einsum("cqi,ci->cq", dz, bdx[cb])
+    kap = kv_q + κc * (1.0 + np.tanh(-(α * (N2 + dzb)) / N2min)) / 2.0
+    wq = tables["w"][None, :] * tables["vol"][:, None] * kap
+    ke = np.einsum("cq,cqi,cqj->cij", wq, dz, dz)
+    fv = np.einsum("cq,cq,cqi->ci", wq, dzd, dz)
+    fd = np.einsum("cq,cqi->ci", wq, dz) * (-N2)
+    nloc = cb.shape[1]
+    rows = np.repeat(cb, nloc, axis=1).ravel()
+    cols = np.tile(cb, (1, nloc)).ravel()
+    keep = (rows < nb) & (cols < nb)
+    K = sp.coo_matrix((ke.ravel()[keep], (rows[keep], cols[keep])), shape=(nb, nb)).tocsr()
+    # same stored pattern as the other evolution matrices
+    P = sp.csr_matrix((np.zeros(pattern.nnz), pattern.indices, pattern.indptr), shape=pattern.shape)
+    K = (K + P).tocsr()
+    K.sort_indices()
+    rv = np.zeros(nb + tables["b_dirichlet"].size)
+    rd = np.zeros_like(rv)
+    np.add.at(rv, cb.ravel(), fv.ravel())
+    np.add.at(rd, cb.ravel(), fd.ravel())
+    return K, rv[:nb], rd[:nb]
+
+
 def rhs_combine(rhs_adv_v, θ, dt, rhs_diff, rhs_flux, rhs_m, rhs_h, rhs_v):
     """``y = rhs_adv + θ rhs_diff + Δt rhs_flux − (rhsₘ + θ (rhsₕ + rhsᵥ))`` (model.jl:278)."""
     return rhs_adv_v + θ * rhs_diff + dt * rhs_flux - (rhs_m + θ * (rhs_h + rhs_v))

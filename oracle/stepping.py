@@ -27,13 +27,13 @@ import numpy as np
 import scipy.sparse.linalg as spla
 
 from . import krylov
-from .element_rhs import cfl_dt, rhs_adv, rhs_combine
+from .element_rhs import cfl_dt, kv_rebuild, rhs_adv, rhs_combine
 
 
 class CpuModel:
     def __init__(self, ops: dict, params: dict, scheme: int, dt: float, t_start: float,
                  t_stop: float, solver: str = "direct", atol=1e-6, rtol=1e-6, memory=20,
-                 orth="mgs", adaptive=False, cfl_factor=0.8):
+                 orth="mgs", adaptive=False, cfl_factor=0.8, conv=None, kv_q=None):
         self.ops = ops
         self.α, self.ε, self.μϱ, self.N2 = (params[k] for k in ("α", "ε", "μϱ", "N2"))
         self.scheme, self.dt, self.t, self.t_stop = scheme, dt, t_start, t_stop
@@ -42,6 +42,11 @@ class CpuModel:
         # LHS re-formed (and, on the reference's CPU path, re-factorised) every step (model.jl:251-261)
         self.adaptive, self.cfl_factor = adaptive, cfl_factor
         self.dts = []
+        # ConvectionParameterization(κᶜ, N²min): Kᵥ, rhsᵥ, rhs_diff rebuilt from b every step
+        # (model.jl:229-246); `kv_q` = base κᵥ at the quadrature points
+        self.conv, self.kv_q = conv, kv_q
+        if conv is not None:
+            self.ops = dict(ops)
         self.kw = dict(atol=atol, rtol=rtol)
         self.memory, self.orth = memory, orth
         self.xu = np.zeros(ops["A"].shape[0])        # [u; p] in solver order
@@ -82,8 +87,11 @@ class CpuModel:
         o = self.ops
         nu = o["nu"]
         θ = self.theta(self.scheme)
-        if self.adaptive:
-            self._lhs(self.scheme)
+        if self.conv is not None:
+            o["Kv"], o["rhs_v"], o["rhs_diff"] = kv_rebuild(o["tables"], self.kv_q, self.α, self.N2,
+                                                             self.conv[0], self.conv[1], self.xb, o["M"])
+        if self.adaptive or self.conv is not None:
+            self._lhs(self.scheme)      # θ of the current timestepper, also on a BDF2 run's first step (model.jl:227,251-255)
         adv = rhs_adv(o["tables"], self.scheme, self.dt, self.N2, self.xb, b_prev,
                       self.xu[:nu], u_prev[:nu])
         y = rhs_combine(adv, θ, self.dt, o["rhs_diff"], o["rhs_flux"], o["rhs_m"], o["rhs_h"],
