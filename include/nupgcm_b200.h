@@ -264,6 +264,15 @@ int32_t nupgcm_cfl_dt(nupgcm_mesh *m, const nupgcm_vec *u, double cfl_factor, do
 int32_t nupgcm_mesh_enable_kv_rebuild(nupgcm_mesh *m, const nupgcm_csr *pattern, const double *kv_q);
 int32_t nupgcm_rebuild_kv(nupgcm_mesh *m, double alpha, double N2, double kappa_c, double N2min,
                           const nupgcm_vec *b, nupgcm_csr *Kv, nupgcm_vec *rhs_v, nupgcm_vec *rhs_diff);
+/* Eddy parameterisation (src/model.jl:160-170, src/inputs.jl:130-137): rebuild of the inversion
+ * matrix with ν(x_q) = LogSumExp_smoothing(nu_min, f_q² / sqrt(N2min² + (alpha (N2 + ∂z b))²)):
+ *   A.vals = A0_vals + assembled ∫ 2 a2e2 ν σ(u)⊙σ(v)            (src/inversion.jl:172-182)
+ * A: N x N inversion matrix in solver order, created with drop_zeros = 0; A0_vals: its
+ * frictionless part (pressure gradient, divergence, Coriolis) on the same pattern; f_q[c*nq+q]. */
+int32_t nupgcm_mesh_enable_nu_rebuild(nupgcm_mesh *m, const nupgcm_csr *A, const double *A0_vals,
+                                      const double *f_q);
+int32_t nupgcm_rebuild_A_friction(nupgcm_mesh *m, double a2e2, double alpha, double N2, double N2min,
+                                  double smoothing, double nu_min, const nupgcm_vec *b, nupgcm_csr *A);
 /* out = rhs_adv + theta*rhs_diff + dt*rhs_flux − (rhs_m + theta*(rhs_h + rhs_v))  (src/model.jl:278) */
 int32_t nupgcm_rhs_combine(nupgcm_vec *out, const nupgcm_vec *rhs_adv, double theta, double dt,
                            const nupgcm_vec *rhs_diff, const nupgcm_vec *rhs_flux,

@@ -10,7 +10,8 @@ from .architectures import (CPU, GPU, architecture, on_architecture, print_memor
                             vector_type)
 from .dofs import DoFHandler, FEData
 from .evolution import EvolutionToolkit, collect_evolution_LHS_
-from .inputs import Forcings, Parameters, SurfaceDirichletBC, SurfaceFluxBC
+from .inputs import (ConvectionParameterization, EddyParameterization, Forcings, Parameters,
+                     SurfaceDirichletBC, SurfaceFluxBC)
 from .inversion import InversionToolkit
 from .iterative_solvers import IterativeSolverToolkit, iterative_solve_
 from .meshes import Mesh
@@ -21,6 +22,7 @@ from .timesteppers import BDF1, BDF2, evolution_parameter, update_t_
 __all__ = [
     "CPU", "GPU", "architecture", "on_architecture", "print_memory_status", "vector_type",
     "DoFHandler", "FEData", "EvolutionToolkit", "collect_evolution_LHS_", "Forcings",
+    "ConvectionParameterization", "EddyParameterization",
     "Parameters", "SurfaceDirichletBC", "SurfaceFluxBC", "InversionToolkit",
     "IterativeSolverToolkit", "iterative_solve_", "Mesh", "Model", "State", "evolve_",
     "invert_", "run_", "set_b_", "sync_flow_", "Spaces", "BDF1", "BDF2",

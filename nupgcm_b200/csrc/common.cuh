@@ -146,6 +146,12 @@ struct nupgcm_mesh {
     double *d_kvq;                 // [n_cells][nq] base κᵥ at the quadrature points
     double *d_emat, *d_evec;       // [n_loc*n_loc][n_cells], 2 x [n_loc][n_cells]
     int64_t kv_nnz;
+    // friction-block rebuild (eddy parameterisation)
+    int32_t *d_nptr, *d_nidx;
+    double *d_fq;                  // [n_cells][nq] Coriolis parameter of the parameterisation
+    double *d_nmat;                // [(n_loc*3)^2][n_cells] element blocks
+    double *d_A0;                  // [nnz] frictionless part of the inversion matrix
+    int64_t nu_nnz;
 };
 
 static const int kStreamChunk = 4096;  // matrix entries per TMA pipeline stage of the streaming SpMV

@@ -241,6 +241,105 @@ k_kv_elem(const int32_t *__restrict__ cell_b, const double *__restrict__ grad, c
     }
 }
 
+// Eddy parameterisation (reference src/model.jl:160-170, src/inputs.jl:130-137): every 10 steps
+//   ν(x_q) = LogSumExp_s(ν_min, f² / sqrt(N²min² + (α(N² + ∂z b))²))
+// and the friction block of the inversion matrix, ∫ 2α²ε² ν σ(u)⊙σ(v) (src/inversion.jl:172-182), is
+// re-assembled; the reference rebuilds the whole matrix on the CPU with Gridap, permutes and uploads
+// it.  Here the constant part (pressure gradient, divergence, Coriolis) stays on the device and one
+// thread per cell writes the 3x3 blocks of the cell's 10x10 (6x6) node pairs:
+//   block(i,j)[a][b] = α²ε² Σ_q w_q |K| ν_q (δ_ab ∇φ_i·∇φ_j + ∂_a φ_j ∂_b φ_i).
+template <int NV>
+__global__ void __launch_bounds__(64)
+k_nu_elem(const int32_t *__restrict__ cell_b, const double *__restrict__ grad, const double *__restrict__ vol,
+          const double *__restrict__ bary, const double *__restrict__ w, int nq, int64_t n_cells,
+          const double *__restrict__ b, const double *__restrict__ bdir, int64_t nb,
+          const double *__restrict__ f_q, double a2e2, double alpha, double N2, double N2min, double smoothing,
+          double nu_min, double *__restrict__ emat) {
+    constexpr int NLOC = P2<NV>::NLOC;
+    constexpr int MAXQ = 16;
+    extern __shared__ double s_q[];               // bary[nq][NV], w[nq]
+    for (int i = threadIdx.x; i < nq * NV; i += blockDim.x) s_q[i] = bary[i];
+    for (int i = threadIdx.x; i < nq; i += blockDim.x) s_q[nq * NV + i] = w[i];
+    __syncthreads();
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    double gl[NV][3];
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) gl[k][d] = grad[(k * 3 + d) * n_cells + c];
+    auto gphi = [&](int q, int i, double g[3]) {
+        const double *lam = s_q + q * NV;
+        if (i < NV) {
+            const double t = 4.0 * lam[i] - 1.0;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) g[d] = t * gl[i][d];
+        } else {
+            const int ia = c_edge_a[i - NV], ib = c_edge_b[i - NV];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) g[d] = 4.0 * fma(lam[ia], gl[ib][d], lam[ib] * gl[ia][d]);
+        }
+    };
+    double cq[MAXQ];                                  // α²ε² w_q |K| ν(x_q)
+    {
+        double bv[NLOC];
+#pragma unroll
+        for (int i = 0; i < NLOC; ++i) {
+            const int32_t ib = cell_b[i * n_cells + c];
+            bv[i] = ib < nb ? b[ib] : bdir[ib - nb];
+        }
+        const double vc = vol[c];
+        for (int q = 0; q < nq; ++q) {
+            double dzb = 0.0;
+#pragma unroll
+            for (int i = 0; i < NLOC; ++i) {
+                double g[3];
+                gphi(q, i, g);
+                dzb = fma(bv[i], g[2], dzb);
+            }
+            const double abz = alpha * (N2 + dzb);
+            const double f = f_q[c * (int64_t)nq + q];
+            const double nu_e = f * (f / sqrt(N2min * N2min + abz * abz));
+            // LogSumExp, written so that the larger exponent is factored out (no overflow)
+            const double hi = fmax(nu_min, nu_e), lo = fmin(nu_min, nu_e);
+            const double nu = hi + log1p(exp(smoothing * (lo - hi))) / smoothing;
+            cq[q] = a2e2 * s_q[nq * NV + q] * vc * nu;
+        }
+    }
+    for (int i = 0; i < NLOC; ++i)
+        for (int j = 0; j < NLOC; ++j) {
+            double S = 0.0, T[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+            for (int q = 0; q < nq; ++q) {
+                double gi[3], gj[3];
+                gphi(q, i, gi);
+                gphi(q, j, gj);
+                const double cw = cq[q];
+                S = fma(cw, gi[0] * gj[0] + gi[1] * gj[1] + gi[2] * gj[2], S);
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int bb = 0; bb < 3; ++bb) T[a][bb] = fma(cw * gj[a], gi[bb], T[a][bb]);
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int bb = 0; bb < 3; ++bb)
+                    emat[(size_t)(((i * NLOC + j) * 3 + a) * 3 + bb) * n_cells + c] = T[a][bb] + (a == bb ? S : 0.0);
+        }
+}
+
+// A.vals[e] = A0[e] + (sum of the entry's friction slots, fixed order)
+__global__ void k_gather_mat_add(const int32_t *__restrict__ kptr, const int32_t *__restrict__ kidx,
+                                 const double *__restrict__ emat, const double *__restrict__ base,
+                                 double *__restrict__ vals, int64_t nnz) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nnz;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int32_t k = kptr[e]; k < kptr[e + 1]; ++k) acc += emat[kidx[k]];
+        vals[e] = base[e] + acc;
+    }
+}
+
 // one thread per stored matrix entry: add its element-matrix slots in the fixed (cell) order
 __global__ void k_gather_mat(const int32_t *__restrict__ kptr, const int32_t *__restrict__ kidx,
                              const double *__restrict__ emat, double *__restrict__ vals, int64_t nnz) {
@@ -372,6 +471,11 @@ extern "C" int32_t nupgcm_mesh_destroy(nupgcm_mesh *m) {
     cudaFree(m->d_kvq);
     cudaFree(m->d_emat);
     cudaFree(m->d_evec);
+    cudaFree(m->d_nptr);
+    cudaFree(m->d_nidx);
+    cudaFree(m->d_fq);
+    cudaFree(m->d_nmat);
+    cudaFree(m->d_A0);
     free(m);
     return NUPGCM_OK;
 }
@@ -525,6 +629,87 @@ extern "C" int32_t nupgcm_rebuild_kv(nupgcm_mesh *m, double alpha, double N2, do
         NUPGCM_CUDA(ctx, cudaGetLastError());
     }
     ctx->launches += 4;
+    return NUPGCM_OK;
+}
+
+extern "C" int32_t nupgcm_mesh_enable_nu_rebuild(nupgcm_mesh *m, const nupgcm_csr *A, const double *A0_vals,
+                                                const double *f_q) {
+    NUPGCM_REQUIRE(nullptr, m && A, "mesh_enable_nu_rebuild: NULL argument");
+    nupgcm_ctx *ctx = m->ctx;
+    NUPGCM_REQUIRE(ctx, A0_vals && f_q, "mesh_enable_nu_rebuild: NULL A0_vals or f_q");
+    NUPGCM_REQUIRE(ctx, !A->dropped && A->n_rows == A->n_cols && A->n_rows >= m->nu,
+                   "mesh_enable_nu_rebuild: A must be the square inversion matrix created with drop_zeros=0");
+    NUPGCM_REQUIRE(ctx, m->nq <= 16, "mesh_enable_nu_rebuild: at most 16 quadrature points");
+    const int64_t nc = m->n_cells, nnz = A->nnz;
+    const int nl = m->n_loc, nd = nl * 3;
+    NUPGCM_REQUIRE(ctx, (int64_t)nd * nd * nc < INT32_MAX, "mesh_enable_nu_rebuild: mesh too large for int32 slots");
+    std::vector<int32_t> tu((size_t)nc * nd);
+    NUPGCM_CUDA(ctx, cudaSetDevice(ctx->device));
+    NUPGCM_CUDA(ctx, cudaMemcpy(tu.data(), m->d_cell_u, tu.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    const int32_t *rp = A->h_rowptr, *col = A->h_col;
+    std::vector<int32_t> kptr(nnz + 1, 0);
+    std::vector<int32_t> pos((size_t)nc * nd * nd, -1);
+    // local velocity DOF (i, a) of cell c is tu[(i*3 + a)*nc + c]; free ones (< nu) are rows/columns of A
+    for (int64_t c = 0; c < nc; ++c)
+        for (int ia = 0; ia < nd; ++ia) {
+            const int32_t r = tu[(size_t)ia * nc + c];
+            if (r >= m->nu) continue;
+            for (int jb = 0; jb < nd; ++jb) {
+                const int32_t cc = tu[(size_t)jb * nc + c];
+                if (cc >= m->nu) continue;
+                const int32_t *lo = std::lower_bound(col + rp[r], col + rp[r + 1], cc);
+                if (lo == col + rp[r + 1] || *lo != cc)
+                    return nupgcm_fail(ctx, NUPGCM_ERR_INVALID, "invalid argument: %s",
+                                       "mesh_enable_nu_rebuild: a cell couples two velocity DOFs that A does not store");
+                const int32_t e = (int32_t)(lo - col);
+                pos[((size_t)c * nd + ia) * nd + jb] = e;
+                kptr[e + 1]++;
+            }
+        }
+    for (int64_t e = 0; e < nnz; ++e) kptr[e + 1] += kptr[e];
+    std::vector<int32_t> kidx(kptr[nnz]), fill(kptr.begin(), kptr.end() - 1);
+    for (int64_t c = 0; c < nc; ++c)
+        for (int ia = 0; ia < nd; ++ia)
+            for (int jb = 0; jb < nd; ++jb) {
+                const int32_t e = pos[((size_t)c * nd + ia) * nd + jb];
+                if (e < 0) continue;
+                const int i = ia / 3, a = ia % 3, j = jb / 3, b = jb % 3;
+                kidx[fill[e]++] = (int32_t)((int64_t)(((i * nl + j) * 3 + a) * 3 + b) * nc + c);
+            }
+    cudaFree(m->d_nptr); cudaFree(m->d_nidx); cudaFree(m->d_fq); cudaFree(m->d_nmat); cudaFree(m->d_A0);
+    m->d_nptr = m->d_nidx = nullptr; m->d_fq = m->d_nmat = m->d_A0 = nullptr;
+    NUPGCM_CUDA(ctx, upload(&m->d_nptr, kptr));
+    NUPGCM_CUDA(ctx, upload(&m->d_nidx, kidx));
+    NUPGCM_CUDA(ctx, upload(&m->d_fq, std::vector<double>(f_q, f_q + (size_t)nc * m->nq)));
+    NUPGCM_CUDA(ctx, upload(&m->d_A0, std::vector<double>(A0_vals, A0_vals + nnz)));
+    NUPGCM_CUDA(ctx, cudaMalloc(&m->d_nmat, (size_t)nc * nd * nd * sizeof(double)));
+    m->nu_nnz = nnz;
+    NUPGCM_CUDA(ctx, cudaDeviceSynchronize());
+    return NUPGCM_OK;
+}
+
+extern "C" int32_t nupgcm_rebuild_A_friction(nupgcm_mesh *m, double a2e2, double alpha, double N2, double N2min,
+                                             double smoothing, double nu_min, const nupgcm_vec *b, nupgcm_csr *A) {
+    NUPGCM_REQUIRE(nullptr, m && b && A, "rebuild_A_friction: NULL argument");
+    nupgcm_ctx *ctx = m->ctx;
+    NUPGCM_REQUIRE(ctx, m->d_nptr, "rebuild_A_friction: call nupgcm_mesh_enable_nu_rebuild first");
+    NUPGCM_REQUIRE(ctx, !A->dropped && A->nnz == m->nu_nnz, "rebuild_A_friction: A does not have the bound pattern");
+    NUPGCM_REQUIRE(ctx, b->n == m->nb, "rebuild_A_friction: buoyancy length mismatch");
+    NUPGCM_REQUIRE(ctx, smoothing > 0.0, "rebuild_A_friction: smoothing must be positive");
+    const int block = 64;
+    const int grid = (int)((m->n_cells + block - 1) / block);
+    const size_t smem = (size_t)m->nq * (m->n_vert + 1) * sizeof(double);
+    if (m->n_vert == 4)
+        k_nu_elem<4><<<grid, block, smem, ctx->stream>>>(m->d_cell_b, m->d_grad, m->d_vol, m->d_phi, m->d_w, m->nq, m->n_cells, b->d, m->d_bdir, m->nb, m->d_fq, a2e2, alpha, N2, N2min, smoothing, nu_min, m->d_nmat);
+    else
+        k_nu_elem<3><<<grid, block, smem, ctx->stream>>>(m->d_cell_b, m->d_grad, m->d_vol, m->d_phi, m->d_w, m->nq, m->n_cells, b->d, m->d_bdir, m->nb, m->d_fq, a2e2, alpha, N2, N2min, smoothing, nu_min, m->d_nmat);
+    NUPGCM_CUDA(ctx, cudaGetLastError());
+    int g = (int)std::min<int64_t>((m->nu_nnz + 255) / 256, (int64_t)ctx->sm_count * 8);
+    if (g < 1) g = 1;
+    k_gather_mat_add<<<g, 256, 0, ctx->stream>>>(m->d_nptr, m->d_nidx, m->d_nmat, m->d_A0, A->d_vals, m->nu_nnz);
+    NUPGCM_CUDA(ctx, cudaGetLastError());
+    A->vals_version++;
+    ctx->launches += 2;
     return NUPGCM_OK;
 }
 

@@ -3,9 +3,9 @@
 Mirrors reference ``src/inputs.jl:3-15`` (Parameters), ``:33-59`` (surface BCs) and ``:141-189``
 (Forcings).  Functions of space take an ``(n, 3)`` array of points and return ``(n,)`` values
 (the vectorised form of the reference's ``x -> ...`` closures); plain numbers are accepted too.
-``ConvectionParameterization`` (``inputs.jl:62-91``) is on the device path (per-step Kᵥ rebuild,
-``nupgcm_rebuild_kv``); the eddy parameterisation (``inputs.jl:95-137``, friction block of the
-inversion matrix every 10 steps) is the remaining half of SURVEY.md §8 f-2 and is rejected loudly.
+``ConvectionParameterization`` (``inputs.jl:62-91``; per-step Kᵥ rebuild, ``nupgcm_rebuild_kv``)
+and ``EddyParameterization`` (``inputs.jl:95-137``; friction block of the inversion matrix every
+10 steps, ``nupgcm_rebuild_A_friction``) are both evaluated on the device.
 """
 from __future__ import annotations
 
@@ -59,6 +59,22 @@ def κᵥ_convection(conv_param: ConvectionParameterization, κᵥ, αbz):
 
 
 @dataclass
+class EddyParameterization:
+    """``EddyParameterization(; f, N²min)`` (inputs.jl:95-137): ν = f²/(α ∂z b_total), smoothly
+    limited to ν_min ≤ ν ≤ f²/N²min."""
+    f: Coef
+    N2min: float
+    is_on: bool = True
+
+
+def ν_eddy(eddy_param: EddyParameterization, f, αbz, smoothing=10, ν_min=1):
+    """inputs.jl:130-137 on arrays of quadrature-point values (``f`` evaluated there too)."""
+    import numpy as np
+    ν = f * (f / np.sqrt(eddy_param.N2min ** 2 + αbz * αbz))
+    return np.logaddexp(smoothing * ν_min, smoothing * ν) / smoothing
+
+
+@dataclass
 class Forcings:
     ν: Coef
     κₕ: Coef
@@ -70,7 +86,4 @@ class Forcings:
     eddy_param: Any = field(default_factory=_Off)
 
     def __post_init__(self):
-        if self.eddy_param.is_on:
-            raise NotImplementedError(
-                "the eddy parameterisation (ν rebuild of the inversion matrix) is not on the B200 "
-                "hot path yet (SURVEY.md §8 f-2)")
+        pass

@@ -92,6 +92,8 @@ SIGNATURES = {
     "nupgcm_cfl_dt": [_P, _P, c_double, c_double, _dp],
     "nupgcm_mesh_enable_kv_rebuild": [_P, _P, _dp],
     "nupgcm_rebuild_kv": [_P, c_double, c_double, c_double, c_double, _P, _P, _P, _P],
+    "nupgcm_mesh_enable_nu_rebuild": [_P, _P, _dp, _dp],
+    "nupgcm_rebuild_A_friction": [_P, c_double, c_double, c_double, c_double, c_double, c_double, _P, _P],
     "nupgcm_rhs_adv": [_P, c_int32, c_double, c_double, _P, _P, _P, _P, _P],
     "nupgcm_rhs_combine": [_P, _P, c_double, c_double, _P, _P, _P, _P, _P],
 }
@@ -522,6 +524,15 @@ class ElementMesh:
     def rebuild_kv(self, alpha, N2, kappa_c, N2min, b: Vector, Kv: "CsrMatrix", rhs_v: Vector, rhs_diff: Vector):
         _check(self.lib.nupgcm_rebuild_kv(self.h, float(alpha), float(N2), float(kappa_c), float(N2min),
                                           b.h, Kv.h, rhs_v.h, rhs_diff.h), self.ctx.h)
+
+    def enable_nu_rebuild(self, A: "CsrMatrix", A0_vals, f_q):
+        a0, fq = _f64(A0_vals), _f64(f_q)
+        _check(self.lib.nupgcm_mesh_enable_nu_rebuild(self.h, A.h, _ptr(a0), _ptr(fq)), self.ctx.h)
+        return self
+
+    def rebuild_A_friction(self, a2e2, alpha, N2, N2min, smoothing, nu_min, b: Vector, A: "CsrMatrix"):
+        _check(self.lib.nupgcm_rebuild_A_friction(self.h, float(a2e2), float(alpha), float(N2), float(N2min),
+                                                  float(smoothing), float(nu_min), b.h, A.h), self.ctx.h)
 
     def rhs_adv(self, scheme, dt, N2, b, b_prev, u, u_prev, out):
         _check(self.lib.nupgcm_rhs_adv(self.h, int(scheme), float(dt), float(N2), b.h, b_prev.h,

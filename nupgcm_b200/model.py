@@ -78,6 +78,19 @@ class Model:
                 # base κᵥ at the quadrature points of every cell; the device adds the convective part
                 kv_q = fe_data.mesh.dΩ.coefficient(forcings.κᵥ, slice(None))
                 self.mesh.enable_kv_rebuild(evolution.Kv, kv_q)
+            if forcings.eddy_param.is_on:
+                # the frictionless part of the inversion matrix stays on the device; the friction
+                # block is re-assembled from ν(∂z b) every 10 steps (model.jl:160-170)
+                from ._forms import build_A_inversion
+                info = inversion.solver.A.info()
+                if info["nnz_stored"] != info["nnz_given"]:
+                    raise ValueError("the eddy parameterisation changes the value pattern of the "
+                                     "inversion matrix: build InversionToolkit(..., drop_zeros=False)")
+                p = fe_data.dofs.p_inversion
+                A0 = build_A_inversion(fe_data, params, 0.0)[p][:, p].tocsr()
+                A0.sort_indices()
+                f_q = fe_data.mesh.dΩ.coefficient(forcings.eddy_param.f, slice(None))
+                self.mesh.enable_nu_rebuild(inversion.solver.A, A0.data, f_q)
             self._b_prev, self._b_curr = ctx.vector(nb), ctx.vector(nb)
             self._u_prev, self._u_curr = ctx.vector(N), ctx.vector(N)
 
@@ -128,7 +141,7 @@ def evolve_(model: Model, u_prev: lib.Vector, b_prev: lib.Vector):
 
 
 def run_(model: Model, n_info=10, n_save=float("inf"), n_steps=None, sync_state=False,
-         host_state=None, log=None):
+         host_state=None, log=None, advection=True):
     """``run!`` (model.jl:90-211).  ``n_steps`` bounds the number of steps taken by this call
     (the reference loops until ``t >= t_stop``).  With ``sync_state`` the state is copied to the
     host (Gridap order) and back every step, reproducing the reference's PCIe pattern."""
@@ -161,6 +174,11 @@ def run_(model: Model, n_info=10, n_save=float("inf"), n_steps=None, sync_state=
             raise RuntimeError("Blow-up detected, stopping simulation")
         model._u_prev, model._u_curr = model._u_curr, model._u_prev  # model.jl:156-157
         model._b_prev, model._b_curr = model._b_curr, model._b_prev
+        eddy = model.forcings.eddy_param
+        if eddy.is_on and advection and i % 10 == 0:                # model.jl:160-170
+            p = model.params
+            model.mesh.rebuild_A_friction(p.α ** 2 * p.ε ** 2, p.α, p.N2, eddy.N2min, 10.0, 1.0, xb,
+                                          model.inversion.solver.A)
         if sync_state and host_state is not None:
             x = xu.download()[dofs.inv_p_inversion]
             host_state["u"], host_state["p"] = x[:nu], x[nu:]

@@ -116,6 +116,32 @@ def kv_rebuild(tables, kv_q, α, N2, κc, N2min, b, pattern):
     return K, rv[:nb], rd[:nb]
 
 
+def nu_friction(tables, f_q, a2e2, α, N2, N2min, b, N, smoothing=10.0, ν_min=1.0):
+    """Eddy parameterisation, reference ``src/model.jl:160-170``: ν(x_q) = ν_eddy(α(N² + ∂z b))
+    (``src/inputs.jl:130-137``: f²/sqrt(N²min² + (α∂z b)²), LogSumExp-limited below by ν_min) and the
+    friction block ∫ 2α²ε² ν σ(u)⊙σ(v) (``src/inversion.jl:172-182``) as an N x N CSR in solver
+    order (rows/columns beyond the velocity DOFs are empty)."""
+    import scipy.sparse as sp
+    cb, cu = tables["cell_b"], tables["cell_u"]
+    nb, nu = tables["nb"], tables["nu"]
+    _, dphi = _p2(tables["bary"])
+    g = np.einsum("qik,ckd->cqid", dphi, tables["grad"])                  # ∇φ_i at q
+    bx = np.concatenate([b, tables["b_dirichlet"]])
+    dzb = np.einsum("cqi,ci->cq", g[:, :, :, 2], bx[cb])
+    αbz = α * (N2 + dzb)
+    ν = f_q * (f_q / np.sqrt(N2min ** 2 + αbz * αbz))
+    ν = np.logaddexp(smoothing * ν_min, smoothing * ν) / smoothing
+    wq = a2e2 * tables["w"][None, :] * tables["vol"][:, None] * ν
+    S = np.einsum("cq,cqid,cqjd->cij", wq, g, g)
+    T = np.einsum("cq,cqja,cqib->ciajb", wq, g, g)                        # ∂_a φ_j ∂_b φ_i
+    nloc = cb.shape[1]
+    blk = T + np.einsum("cij,ab->ciajb", S, np.eye(3))
+    rows = np.broadcast_to(cu[:, :, :, None, None], blk.shape).ravel()
+    cols = np.broadcast_to(cu[:, None, None, :, :], blk.shape).ravel()
+    keep = (rows < nu) & (cols < nu)
+    return sp.coo_matrix((blk.ravel()[keep], (rows[keep], cols[keep])), shape=(N, N)).tocsr()
+
+
 def rhs_combine(rhs_adv_v, θ, dt, rhs_diff, rhs_flux, rhs_m, rhs_h, rhs_v):
     """``y = rhs_adv + θ rhs_diff + Δt rhs_flux − (rhsₘ + θ (rhsₕ + rhsᵥ))`` (model.jl:278)."""
     return rhs_adv_v + θ * rhs_diff + dt * rhs_flux - (rhs_m + θ * (rhs_h + rhs_v))

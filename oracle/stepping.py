@@ -27,13 +27,14 @@ import numpy as np
 import scipy.sparse.linalg as spla
 
 from . import krylov
-from .element_rhs import cfl_dt, kv_rebuild, rhs_adv, rhs_combine
+from .element_rhs import cfl_dt, kv_rebuild, nu_friction, rhs_adv, rhs_combine
 
 
 class CpuModel:
     def __init__(self, ops: dict, params: dict, scheme: int, dt: float, t_start: float,
                  t_stop: float, solver: str = "direct", atol=1e-6, rtol=1e-6, memory=20,
-                 orth="mgs", adaptive=False, cfl_factor=0.8, conv=None, kv_q=None):
+                 orth="mgs", adaptive=False, cfl_factor=0.8, conv=None, kv_q=None, eddy=None,
+                 f_q=None, A0=None):
         self.ops = ops
         self.α, self.ε, self.μϱ, self.N2 = (params[k] for k in ("α", "ε", "μϱ", "N2"))
         self.scheme, self.dt, self.t, self.t_stop = scheme, dt, t_start, t_stop
@@ -45,7 +46,10 @@ class CpuModel:
         # ConvectionParameterization(κᶜ, N²min): Kᵥ, rhsᵥ, rhs_diff rebuilt from b every step
         # (model.jl:229-246); `kv_q` = base κᵥ at the quadrature points
         self.conv, self.kv_q = conv, kv_q
-        if conv is not None:
+        # EddyParameterization(f, N²min): eddy = N²min, f_q = f at the quadrature points, A0 = the
+        # frictionless part of the inversion matrix; A rebuilt every 10 steps (model.jl:160-170)
+        self.eddy, self.f_q, self.A0 = eddy, f_q, A0
+        if conv is not None or eddy is not None:
             self.ops = dict(ops)
         self.kw = dict(atol=atol, rtol=rtol)
         self.memory, self.orth = memory, orth
@@ -122,6 +126,11 @@ class CpuModel:
             if max(u_max, b_max) > 1e3 or np.isnan(u_max) or np.isnan(b_max):
                 raise RuntimeError("Blow-up detected, stopping simulation")
             u_prev, b_prev = u_curr, b_curr
+            if self.eddy is not None and self.i % 10 == 0:
+                o = self.ops
+                o["A"] = (self.A0 + nu_friction(o["tables"], self.f_q, self.α ** 2 * self.ε ** 2, self.α,
+                                                self.N2, self.eddy, self.xb, self.A0.shape[0])).tocsr()
+                self._lu_A = None
             self.log.append({"i": self.i, "cg_iters": cg_it, "gmres_iters": gm_it,
                              "seconds": time.perf_counter() - t0})
             self.i += 1
