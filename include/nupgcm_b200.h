@@ -271,7 +271,7 @@ int32_t nupgcm_rebuild_kv(nupgcm_mesh *m, double alpha, double N2, double kappa_
  * frictionless part (pressure gradient, divergence, Coriolis) on the same pattern; f_q[c*nq+q]. */
 int32_t nupgcm_mesh_enable_nu_rebuild(nupgcm_mesh *m, const nupgcm_csr *A, const double *A0_vals,
                                       const double *f_q);
-int32_t nupgcm_rebuild_A_friction(nupgcm_mesh *m, double a2e2, double alpha, double N2, double N2min,
+int32_t nupgcm_rebuild_friction(nupgcm_mesh *m, double a2e2, double alpha, double N2, double N2min,
                                   double smoothing, double nu_min, const nupgcm_vec *b, nupgcm_csr *A);
 /* out = rhs_adv + theta*rhs_diff + dt*rhs_flux − (rhs_m + theta*(rhs_h + rhs_v))  (src/model.jl:278) */
 int32_t nupgcm_rhs_combine(nupgcm_vec *out, const nupgcm_vec *rhs_adv, double theta, double dt,

@@ -13,6 +13,7 @@ from .evolution import EvolutionToolkit, collect_evolution_LHS_
 from .inputs import (ConvectionParameterization, EddyParameterization, Forcings, Parameters,
                      SurfaceDirichletBC, SurfaceFluxBC)
 from .inversion import InversionToolkit
+from .io import save_state, set_state_from_file_
 from .iterative_solvers import IterativeSolverToolkit, iterative_solve_
 from .meshes import Mesh
 from .model import Model, State, evolve_, invert_, run_, set_b_, sync_flow_
@@ -26,5 +27,5 @@ __all__ = [
     "Parameters", "SurfaceDirichletBC", "SurfaceFluxBC", "InversionToolkit",
     "IterativeSolverToolkit", "iterative_solve_", "Mesh", "Model", "State", "evolve_",
     "invert_", "run_", "set_b_", "sync_flow_", "Spaces", "BDF1", "BDF2",
-    "evolution_parameter", "update_t_",
+    "evolution_parameter", "update_t_", "save_state", "set_state_from_file_",
 ]

@@ -688,14 +688,14 @@ extern "C" int32_t nupgcm_mesh_enable_nu_rebuild(nupgcm_mesh *m, const nupgcm_cs
     return NUPGCM_OK;
 }
 
-extern "C" int32_t nupgcm_rebuild_A_friction(nupgcm_mesh *m, double a2e2, double alpha, double N2, double N2min,
+extern "C" int32_t nupgcm_rebuild_friction(nupgcm_mesh *m, double a2e2, double alpha, double N2, double N2min,
                                              double smoothing, double nu_min, const nupgcm_vec *b, nupgcm_csr *A) {
-    NUPGCM_REQUIRE(nullptr, m && b && A, "rebuild_A_friction: NULL argument");
+    NUPGCM_REQUIRE(nullptr, m && b && A, "rebuild_friction: NULL argument");
     nupgcm_ctx *ctx = m->ctx;
-    NUPGCM_REQUIRE(ctx, m->d_nptr, "rebuild_A_friction: call nupgcm_mesh_enable_nu_rebuild first");
-    NUPGCM_REQUIRE(ctx, !A->dropped && A->nnz == m->nu_nnz, "rebuild_A_friction: A does not have the bound pattern");
-    NUPGCM_REQUIRE(ctx, b->n == m->nb, "rebuild_A_friction: buoyancy length mismatch");
-    NUPGCM_REQUIRE(ctx, smoothing > 0.0, "rebuild_A_friction: smoothing must be positive");
+    NUPGCM_REQUIRE(ctx, m->d_nptr, "rebuild_friction: call nupgcm_mesh_enable_nu_rebuild first");
+    NUPGCM_REQUIRE(ctx, !A->dropped && A->nnz == m->nu_nnz, "rebuild_friction: A does not have the bound pattern");
+    NUPGCM_REQUIRE(ctx, b->n == m->nb, "rebuild_friction: buoyancy length mismatch");
+    NUPGCM_REQUIRE(ctx, smoothing > 0.0, "rebuild_friction: smoothing must be positive");
     const int block = 64;
     const int grid = (int)((m->n_cells + block - 1) / block);
     const size_t smem = (size_t)m->nq * (m->n_vert + 1) * sizeof(double);

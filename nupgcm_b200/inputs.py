@@ -5,7 +5,7 @@ Mirrors reference ``src/inputs.jl:3-15`` (Parameters), ``:33-59`` (surface BCs) 
 (the vectorised form of the reference's ``x -> ...`` closures); plain numbers are accepted too.
 ``ConvectionParameterization`` (``inputs.jl:62-91``; per-step Kᵥ rebuild, ``nupgcm_rebuild_kv``)
 and ``EddyParameterization`` (``inputs.jl:95-137``; friction block of the inversion matrix every
-10 steps, ``nupgcm_rebuild_A_friction``) are both evaluated on the device.
+10 steps, ``nupgcm_rebuild_friction``) are both evaluated on the device.
 """
 from __future__ import annotations
 

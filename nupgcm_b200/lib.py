@@ -93,7 +93,7 @@ SIGNATURES = {
     "nupgcm_mesh_enable_kv_rebuild": [_P, _P, _dp],
     "nupgcm_rebuild_kv": [_P, c_double, c_double, c_double, c_double, _P, _P, _P, _P],
     "nupgcm_mesh_enable_nu_rebuild": [_P, _P, _dp, _dp],
-    "nupgcm_rebuild_A_friction": [_P, c_double, c_double, c_double, c_double, c_double, c_double, _P, _P],
+    "nupgcm_rebuild_friction": [_P, c_double, c_double, c_double, c_double, c_double, c_double, _P, _P],
     "nupgcm_rhs_adv": [_P, c_int32, c_double, c_double, _P, _P, _P, _P, _P],
     "nupgcm_rhs_combine": [_P, _P, c_double, c_double, _P, _P, _P, _P, _P],
 }
@@ -530,8 +530,8 @@ class ElementMesh:
         _check(self.lib.nupgcm_mesh_enable_nu_rebuild(self.h, A.h, _ptr(a0), _ptr(fq)), self.ctx.h)
         return self
 
-    def rebuild_A_friction(self, a2e2, alpha, N2, N2min, smoothing, nu_min, b: Vector, A: "CsrMatrix"):
-        _check(self.lib.nupgcm_rebuild_A_friction(self.h, float(a2e2), float(alpha), float(N2), float(N2min),
+    def rebuild_friction(self, a2e2, alpha, N2, N2min, smoothing, nu_min, b: Vector, A: "CsrMatrix"):
+        _check(self.lib.nupgcm_rebuild_friction(self.h, float(a2e2), float(alpha), float(N2), float(N2min),
                                                   float(smoothing), float(nu_min), b.h, A.h), self.ctx.h)
 
     def rhs_adv(self, scheme, dt, N2, b, b_prev, u, u_prev, out):

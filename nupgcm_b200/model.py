@@ -177,7 +177,7 @@ def run_(model: Model, n_info=10, n_save=float("inf"), n_steps=None, sync_state=
         eddy = model.forcings.eddy_param
         if eddy.is_on and advection and i % 10 == 0:                # model.jl:160-170
             p = model.params
-            model.mesh.rebuild_A_friction(p.α ** 2 * p.ε ** 2, p.α, p.N2, eddy.N2min, 10.0, 1.0, xb,
+            model.mesh.rebuild_friction(p.α ** 2 * p.ε ** 2, p.α, p.N2, eddy.N2min, 10.0, 1.0, xb,
                                           model.inversion.solver.A)
         if sync_state and host_state is not None:
             x = xu.download()[dofs.inv_p_inversion]

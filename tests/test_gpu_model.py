@@ -194,7 +194,7 @@ def test_convection_steps_match_oracle():
 
 @pytest.mark.parametrize("kw", [{"dim": 2}, {}])
 def test_friction_rebuild_matches_oracle(ctx, kw):
-    """nupgcm_rebuild_A_friction (eddy parameterisation, model.jl:160-170) against the NumPy
+    """nupgcm_rebuild_friction (eddy parameterisation, model.jl:160-170) against the NumPy
     restatement, probed through SpMV; bitwise reproducible."""
     from nupgcm_b200 import lib
     from nupgcm_b200._forms import build_A_inversion
@@ -214,7 +214,7 @@ def test_friction_rebuild_matches_oracle(ctx, kw):
     x = rng.uniform(-1, 1, A0.shape[0])
     ys = []
     for _ in range(2):
-        mesh.rebuild_A_friction(a2e2, α, N2, 0.3, 10.0, 1.0, ctx.vector(b), dA)
+        mesh.rebuild_friction(a2e2, α, N2, 0.3, 10.0, 1.0, ctx.vector(b), dA)
         y = ctx.vector(A0.shape[0])
         dA.spmv(ctx.vector(x), y)
         ys.append(y.download())
