@@ -235,9 +235,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--h", type=float, default=0.08)
-    ap.add_argument("--orth", default="cgs2", choices=["mgs", "cgs2"],
-                    help="Arnoldi orthogonalisation: cgs2 (3 grid reductions per iteration, default) or "
-                         "mgs (Krylov.jl order, k+1 reductions)")
+    ap.add_argument("--orth", default="cgs2f", choices=["mgs", "cgs2", "cgs2f"],
+                    help="Arnoldi orthogonalisation: cgs2f (CGS2 with 2 grid reductions per iteration, "
+                         "default), cgs2 (3 reductions) or mgs (Krylov.jl order, k+1 reductions)")
     ap.add_argument("--keep-zeros", action="store_true", help="store Gridap's explicit zeros too")
     ap.add_argument("--cpu-sample-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -271,7 +271,7 @@ def main():
     else:
         arch = npg.GPU(local)
     ctx = arch.ctx
-    orth = lib.ORTH_MGS if args.orth == "mgs" else lib.ORTH_CGS2
+    orth = {"mgs": lib.ORTH_MGS, "cgs2": lib.ORTH_CGS2, "cgs2f": lib.ORTH_CGS2_FUSED}[args.orth]
 
     def make_model():
         inv = npg.InversionToolkit(arch, ops["A"], ops["pscale"], ops["B"], ops["b0"], orth=orth,

@@ -198,6 +198,8 @@ int32_t nupgcm_cg_solve(const nupgcm_csr *A, const nupgcm_vec *dinv, double psca
 /* orthogonalisation variants of the Arnoldi step */
 #define NUPGCM_ORTH_MGS 0  /* modified Gram-Schmidt, what Krylov.jl does: parity default */
 #define NUPGCM_ORTH_CGS2 1 /* classical Gram-Schmidt twice: 3 grid reductions per iteration */
+#define NUPGCM_ORTH_CGS2_FUSED 2 /* CGS2 with 2 reductions: norm by Pythagoras from the second pass,
+                                    next SpMV on the exchanged q1 corrected with the Arnoldi relation */
 
 /* restarted GMRES(memory), left preconditioned (GmresWorkspace, src/inversion.jl:74-94) */
 int32_t nupgcm_gmres_solve(const nupgcm_csr *A, const nupgcm_vec *dinv, double pscale,

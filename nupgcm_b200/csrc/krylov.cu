@@ -292,7 +292,7 @@ __device__ __forceinline__ bool comm_sum1(CommMailbox *mb, const KrylovArgs &a, 
 // measured at 6-12 us; this form issues (grid + copies) x count.
 // MR: the reducer CTA of value j exchanges its rank's total with the reducer CTAs of value j on the
 // other ranks (one remote store per peer), adds the nranks totals in rank order and broadcasts.
-template <bool MR>
+template <bool MR, bool PUBLISH>
 __device__ __forceinline__ bool comm_sumN(CommMailbox *mb, const KrylovArgs &a, LLSlot *bank_base, unsigned long long *abort_word,
                                           unsigned long long *trow, bool tr, unsigned gen, int grid, int gpad,
                                           int count) {
@@ -300,13 +300,19 @@ __device__ __forceinline__ bool comm_sumN(CommMailbox *mb, const KrylovArgs &a, 
     const int bid = blockIdx.x;
     LLSlot *vals = bank_base + (size_t)kMaxReplicas * gpad;                 // [kPartialSlots][gpad]
     LLSlot *res = vals + (size_t)kPartialSlots * gpad;                      // [kBcastCopies][kBcastStride]
-    if (ct < count) ll_store<false>(vals + (size_t)ct * gpad + bid, mb->in[ct], gen);
+    // PUBLISH: value 0 carries the publication (release by its store, acquire by its reducer, release by
+    // the reducer's result, acquire by every CTA's wait for result 0); the other values stay relaxed.
+    if (ct < count) {
+        if (PUBLISH && ct == 0) ll_store<true>(vals + bid, mb->in[0], gen);
+        else ll_store<false>(vals + (size_t)ct * gpad + bid, mb->in[ct], gen);
+    }
     if (tr) trow[2 * (size_t)grid] = global_timer_ns();
     bool bad = false;
     if (bid < count) {                                                      // reducer of value `bid`
         const int c = cw * 32 + lane;
         double v = 0.0;
-        if (c < grid) v = wait_flagged<false>(vals + (size_t)bid * gpad + c, gen, abort_word, bad);
+        if (c < grid) v = (PUBLISH && bid == 0) ? wait_flagged<true>(vals + c, gen, abort_word, bad)
+                                                : wait_flagged<false>(vals + (size_t)bid * gpad + c, gen, abort_word, bad);
         v = warp_sum(v);
         if (lane == 0) mb->part[0][cw] = v;
         named_sync(NUPGCM_BAR_COMM, kCommThreads);
@@ -322,17 +328,20 @@ __device__ __forceinline__ bool comm_sumN(CommMailbox *mb, const KrylovArgs &a, 
                 double total = 0.0;
                 for (int r = 0; r < a.nranks; ++r)
                     total += wait_flagged<false, true>(xr_slot(a.arena[a.rank], xbank, bid, 0, r), xgen, abort_word, bad);
-                ll_store<false>(res + (size_t)ct * kBcastStride + bid, total, gen);
+                if (PUBLISH && bid == 0) ll_store<true>(res + (size_t)ct * kBcastStride, total, gen);
+                else ll_store<false>(res + (size_t)ct * kBcastStride + bid, total, gen);
             }
         } else if (ct < kBcastCopies) {
             double total = 0.0;
             for (int g = 0; g < npw; ++g) total += mb->part[0][g];
-            ll_store<false>(res + (size_t)ct * kBcastStride + bid, total, gen);
+            if (PUBLISH && bid == 0) ll_store<true>(res + (size_t)ct * kBcastStride, total, gen);
+                else ll_store<false>(res + (size_t)ct * kBcastStride + bid, total, gen);
         }
     }
     if (tr) trow[3 * (size_t)grid] = global_timer_ns();
     if (ct < count)
-        mb->out[ct] = wait_flagged<false>(res + (size_t)(bid % kBcastCopies) * kBcastStride + ct, gen, abort_word, bad);
+        mb->out[ct] = (PUBLISH && ct == 0) ? wait_flagged<true>(res + (size_t)(bid % kBcastCopies) * kBcastStride, gen, abort_word, bad)
+                                           : wait_flagged<false>(res + (size_t)(bid % kBcastCopies) * kBcastStride + ct, gen, abort_word, bad);
     if (bad) mb->dead = 1;
     if (tr) trow[4 * (size_t)grid] = global_timer_ns();
     return bad;
@@ -361,13 +370,16 @@ __device__ __forceinline__ bool comm_mr(CommMailbox *mb, const KrylovArgs &a, LL
             if (lane == 0) ll_store<PUBLISH>(vals + bid, val, gen);
         }
     } else if (ct < count) {
-        ll_store<PUBLISH>(vals + (size_t)ct * gpad + bid, mb->in[ct], gen);
+        // value 0 carries the publication of this CTA's rows, the other values stay relaxed
+        if (PUBLISH && ct == 0) ll_store<true>(vals + bid, mb->in[0], gen);
+        else ll_store<false>(vals + (size_t)ct * gpad + bid, mb->in[ct], gen);
     }
     bool bad = false;
     if (bid < count) {                                                      // reducer of value `bid` on this rank
         const int c = cw * 32 + lane;
         double v = 0.0;
-        if (c < grid) v = wait_flagged<PUBLISH>(vals + (size_t)bid * gpad + c, gen, abort_word, bad);
+        if (c < grid) v = (PUBLISH && bid == 0) ? wait_flagged<true>(vals + c, gen, abort_word, bad)
+                                                : wait_flagged<false>(vals + (size_t)bid * gpad + c, gen, abort_word, bad);
         v = warp_sum(v);
         if (lane == 0) mb->part[0][cw] = v;
         named_sync(NUPGCM_BAR_COMM, kCommThreads);
@@ -381,15 +393,17 @@ __device__ __forceinline__ bool comm_mr(CommMailbox *mb, const KrylovArgs &a, LL
             // enough (the NCCL pattern: writers fence, then the flag).  xfence = 1 uses formal
             // release.sys / acquire.sys instead, at +1.6 us per hop (tools/xrank_latency.py).
             LLSlot *dst = xr_slot(a.arena[ct % P], xbank, bid, ct / P, a.rank);
-            if (PUBLISH && a.xfence) ll_store<true, true>(dst, total, xgen);
+            if (PUBLISH && bid == 0 && a.xfence) ll_store<true, true>(dst, total, xgen);
+            else if (PUBLISH && bid == 0 && ct % P == a.rank) ll_store<true, false>(dst, total, xgen);   // rows of this rank's own CTAs
             else ll_store<false, true>(dst, total, xgen);
         }
     }
     if (ct < count * P) {
         const int j = ct / P, r = ct % P;
         const LLSlot *src = xr_slot(a.arena[a.rank], xbank, j, bid % kXRep, r);
-        mb->xpart[j][r] = (PUBLISH && a.xfence) ? wait_flagged<true, true>(src, xgen, abort_word, bad)
-                                                : wait_flagged<false, true>(src, xgen, abort_word, bad);
+        if (PUBLISH && j == 0 && a.xfence) mb->xpart[j][r] = wait_flagged<true, true>(src, xgen, abort_word, bad);
+        else if (PUBLISH && j == 0 && r == a.rank) mb->xpart[j][r] = wait_flagged<true, false>(src, xgen, abort_word, bad);
+        else mb->xpart[j][r] = wait_flagged<false, true>(src, xgen, abort_word, bad);
     }
     if (bad) mb->dead = 1;
     named_sync(NUPGCM_BAR_COMM, kCommThreads);
@@ -427,7 +441,8 @@ __device__ __forceinline__ void comm_warp_loop(CommMailbox *mb, const KrylovArgs
                 const int cnt = count > 0 ? count : 1;           // a bare barrier sums one zero
                 bad = mb->publish ? comm_mr<true>(mb, a, bank_base, abort_word, gen, grid, gpad, cnt)
                                   : comm_mr<false>(mb, a, bank_base, abort_word, gen, grid, gpad, cnt);
-            } else if (count > 1) bad = comm_sumN<MR>(mb, a, bank_base, abort_word, trow, tr, gen, grid, gpad, count);
+            } else if (count > 1) bad = mb->publish ? comm_sumN<MR, true>(mb, a, bank_base, abort_word, trow, tr, gen, grid, gpad, count)
+                                                    : comm_sumN<MR, false>(mb, a, bank_base, abort_word, trow, tr, gen, grid, gpad, count);
             else if (mb->publish) bad = comm_sum1<true, MR>(mb, a, bank_base, abort_word, trow, tr, gen, grid, gpad, nrep);
             else bad = comm_sum1<false, MR>(mb, a, bank_base, abort_word, trow, tr, gen, grid, gpad, nrep);
             dead = __any_sync(0xffffffffu, bad) || mb->dead != 0;
@@ -491,8 +506,9 @@ struct GridReduce {
     }
     // Sum of `count` values per CTA that main threads put into mb->in[0..count) beforehand
     // (followed by main_sync()).  Results in mb->out[0..count).
-    __device__ __forceinline__ void sumN(int count) {
-        if (threadIdx.x == 0) { mb->count = count; mb->from_warps = 0; mb->publish = 0; }
+    __device__ __forceinline__ void sumN(int count, bool publish = false) {
+        if (publish) fence_remote();
+        if (threadIdx.x == 0) { mb->count = count; mb->from_warps = 0; mb->publish = publish ? 1 : 0; }
         round_trip();
     }
     // Grid barrier that publishes this CTA's global-memory rows.
@@ -1225,6 +1241,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
     __shared__ double sR[kMaxMemory * (kMaxMemory + 1) / 2];
     __shared__ double s_flags[4];      // rnorm, inconsistent, -, Hbis
     __shared__ double s_seg[32];
+    // fused CGS2: unrotated Hessenberg columns (packed: column j holds rows 0..j+1 at j(j+3)/2),
+    // the second-pass coefficients h₂, the correction H̄ h₂ / H and per-warp partial norms
+    __shared__ double sHbar[kMaxMemory * (kMaxMemory + 3) / 2], s_h2[kMaxMemory], s_corr[kMaxMemory + 1], s_wsum[kMainWarps];
     __shared__ int s_prange[2 * kMaxRanks];
     __shared__ char *s_pdest[kMaxRanks];
 
@@ -1329,6 +1348,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
         int k = 0;          // inner_iter
         int nr = 0;
         bool inner_tired = false;
+        bool have_corr = false;     // fused CGS2: the exchanged vector is q₁, corrected after the SpMV
         while (!(solved || inner_tired || breakdown || gr.aborted())) {
             k++;
             // ---- q = M A v_k on own rows (raw v_k gathered from qbuf[cur], scaled by inv_h)
@@ -1371,6 +1391,96 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
                 pc.mark(1);
                 hsq = gr.sum_threads<true>(part);     // publishes dst for the next gather
                 pc.mark(2);
+            } else if (a.orth == NUPGCM_ORTH_CGS2_FUSED) {
+                // CGS2 with two grid reductions per iteration instead of three:
+                //   1. h₁ = Vᵀq ;            q₁ = q − V h₁ — q₁ is what the other CTAs will gather
+                //   2. [h₂ = Vᵀq₁, ‖q₁‖²] in ONE reduction that also publishes q₁;
+                //      ‖q₂‖² = ‖q₁‖² − ‖h₂‖² (Pythagoras; h₂ = O(ε)‖q₁‖), q₂ = q₁ − V h₂ locally.
+                // The next SpMV runs on the published q₁ instead of q₂ = q₁ − V h₂.  By the Arnoldi relation
+                // (Â V_k = V_{k+1} H̄_k) that adds V_{k+1} c, c = H̄_k h₂ / H, to the operator's output: a
+                // vector INSIDE the span the next projection removes.  So q₁ of the next iteration is
+                // unchanged and only its coefficients need the correction h = Vᵀq̂ − c (VᵀV = I up to
+                // O(ε), c = O(ε): the neglected term is O(ε²)).  Equal to CGS2 in exact arithmetic.
+                const int nseg = nwarps / k > 0 ? nwarps / k : 1;
+                const int rows = r1 - r0;
+                const int seglen = (rows + nseg - 1) / nseg;
+                auto project = [&]() {                         // s_seg <- per-segment partial dots
+                    for (int u = wid; u < k * nseg; u += nwarps) {
+                        const int i = u % k, sg = u / k;
+                        const double *vi = V.at(i);
+                        const int lo = r0 + sg * seglen, hi = min(r1, lo + seglen);
+                        double part = 0.0;
+                        for (int row = lo + lane; row < hi; row += 32) part = fma(vi[row], q[row], part);
+                        part = warp_sum(part);
+                        if (lane == 0) s_seg[u] = part;
+                    }
+                };
+                main_sync();
+                project();
+                main_sync();
+                if (tid < k) {
+                    double t = 0.0;
+                    for (int sg = 0; sg < nseg; ++sg) t += s_seg[sg * k + tid];
+                    sm_in[tid] = t;
+                }
+                main_sync();
+                pc.mark(1);
+                gr.sumN(k);
+                pc.mark(2);
+                double part = 0.0;
+                halo_arm(hp, a, gr.gen);
+                for (int row = r0 + tid; row < r1; row += nthr) {
+                    double qv = q[row];
+                    for (int i = 0; i < k; ++i) qv = fma(-sm_out[i], V.at(i)[row], qv);
+                    q[row] = qv;
+                    dst[row] = qv;
+                    halo_put(hp, dst + row, row, qv);
+                    part = fma(qv, qv, part);
+                }
+                if (tid < k) sR[nr + tid] = have_corr ? sm_out[tid] - s_corr[tid] : sm_out[tid];
+                part = warp_sum(part);
+                if (lane == 0) s_wsum[wid] = part;
+                main_sync();
+                project();
+                main_sync();
+                if (tid < k) {
+                    double t = 0.0;
+                    for (int sg = 0; sg < nseg; ++sg) t += s_seg[sg * k + tid];
+                    sm_in[tid] = t;
+                } else if (tid == k) {
+                    double t = 0.0;
+                    for (int wv = 0; wv < nwarps; ++wv) t += s_wsum[wv];
+                    sm_in[k] = t;
+                }
+                main_sync();
+                pc.mark(1);
+                gr.sumN(k + 1, true);                          // also publishes dst (= q₁)
+                pc.mark(2);
+                double h2sq = 0.0;
+                for (int i = 0; i < k; ++i) h2sq = fma(sm_out[i], sm_out[i], h2sq);
+                hsq = fmax(sm_out[k] - h2sq, 0.0);
+                for (int row = r0 + tid; row < r1; row += nthr) {
+                    double qv = q[row];
+                    for (int i = 0; i < k; ++i) qv = fma(-sm_out[i], V.at(i)[row], qv);
+                    q[row] = qv;
+                }
+                const int hc = (k - 1) * (k + 2) / 2;          // packed offset of H̄ column k-1
+                if (tid < k) {
+                    const double h = sR[nr + tid] + sm_out[tid];
+                    sR[nr + tid] = h;
+                    s_h2[tid] = sm_out[tid];
+                    sHbar[hc + tid] = h;
+                } else if (tid == k) {
+                    sHbar[hc + k] = sqrt(hsq);
+                }
+                main_sync();
+                if (tid <= k) {
+                    const double Hb = sqrt(hsq);
+                    double c = 0.0;
+                    for (int j = tid > 0 ? tid - 1 : 0; j < k; ++j) c = fma(sHbar[j * (j + 3) / 2 + tid], s_h2[j], c);
+                    s_corr[tid] = Hb > 0.0 ? c / Hb : 0.0;
+                }
+                have_corr = true;
             } else {
                 // CGS2: all k projections at once, twice; warp w handles basis vector w % k on
                 // row segment w / k.
@@ -1610,7 +1720,7 @@ static ResidentLayout plan_resident(const nupgcm_csr *A, bool gmres, int memory)
     const char *env = getenv("NUPGCM_RESIDENT");
     if (env && atoi(env) == 0) return none;
     if (!A->d_loc || A->res_max_nnz == 0) return none;
-    const int static_smem = gmres ? 8192 : 4096;          // the kernels' static shared memory
+    const int static_smem = gmres ? 8704 : 4096;          // the kernels' static shared memory
     const int limit = 227 * 1024 - static_smem;
     const char *envv = getenv("NUPGCM_VEC_SMEM");
     const int n_vec = (envv && atoi(envv) == 0) ? 1 << 20 : (gmres ? memory + 1 : 5);
@@ -1626,7 +1736,7 @@ static ResidentLayout plan_streaming(const nupgcm_csr *A, bool gmres, int memory
     const char *env = getenv("NUPGCM_STREAM_TMA");
     if (env && atoi(env) == 0) return L;
     if (!A->d_chunk_ptr) return L;
-    const int static_smem = gmres ? 8192 : 4096;
+    const int static_smem = gmres ? 8704 : 4096;
     const int limit = 227 * 1024 - static_smem;
     int off = 0;
     L.st_vals = off; off += kStreamStages * kStreamChunk * 8;
@@ -1667,7 +1777,7 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
     NUPGCM_REQUIRE(ctx, grid <= 32 * kPollWarps, "solve: grid larger than the reduction supports");
     if (gmres) {
         NUPGCM_REQUIRE(ctx, memory >= 1 && memory <= kMaxMemory, "gmres: memory must be in 1..20");
-        NUPGCM_REQUIRE(ctx, orth == NUPGCM_ORTH_MGS || orth == NUPGCM_ORTH_CGS2, "gmres: unknown orth");
+        NUPGCM_REQUIRE(ctx, orth == NUPGCM_ORTH_MGS || orth == NUPGCM_ORTH_CGS2 || orth == NUPGCM_ORTH_CGS2_FUSED, "gmres: unknown orth");
     }
     NUPGCM_REQUIRE(ctx, hist_cap >= 0 && (hist_cap == 0 || resid_hist), "solve: hist_cap without buffer");
     const int64_t n = A->n_rows;
@@ -1682,8 +1792,8 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
         NUPGCM_REQUIRE(ctx, !comm->broken, "solve: communicator is unusable after an aborted sharded solve");
         NUPGCM_REQUIRE(ctx, n <= comm->max_n, "solve: system larger than the communicator's max_n");
     }
-    if (gmres && orth == NUPGCM_ORTH_CGS2)
-        NUPGCM_REQUIRE(ctx, grid >= memory, "gmres: CGS2 needs at least `memory` CTAs (one reducer per projection)");
+    if (gmres && orth != NUPGCM_ORTH_MGS)
+        NUPGCM_REQUIRE(ctx, grid >= memory + 1, "gmres: CGS2 needs at least `memory` CTAs (one reducer per projection)");
     NUPGCM_CUDA(ctx, cudaSetDevice(ctx->device));
     int32_t rcp = nupgcm_csr_prepare(const_cast<nupgcm_csr *>(A), grid);
     if (rcp) return rcp;

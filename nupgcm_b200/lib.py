@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnupgcm_b200.so")
 
-ORTH_MGS, ORTH_CGS2 = 0, 1
+ORTH_MGS, ORTH_CGS2, ORTH_CGS2_FUSED = 0, 1, 2
 
 
 class NupgcmError(RuntimeError):

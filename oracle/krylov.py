@@ -121,7 +121,12 @@ def gmres(A, b, x0=None, M=None, atol=np.sqrt(EPS), rtol=np.sqrt(EPS), itmax=0, 
 
     ``orth``: ``"mgs"`` is what Krylov.jl does (sequential dot/axpy pairs); ``"cgs2"`` (classical
     Gram-Schmidt applied twice) is provided to measure how far a batched-reduction variant moves
-    the iteration count.
+    the iteration count; ``"cgs2f"`` is CGS2 with two instead of three global synchronisations
+    per iteration (what ``NUPGCM_ORTH_CGS2_FUSED`` runs on the device): the norm of the new vector
+    comes from the second projection by Pythagoras, ‖q₂‖² = ‖q₁‖² − ‖h₂‖², and the next operator
+    application is done on q₁ (the vector that was exchanged); by the Arnoldi relation that adds
+    V_{k+1}(H̄_k h₂)/H — a vector inside the span the next projection removes — so only the next
+    Hessenberg column needs the correction.  Identical to CGS2 in exact arithmetic.
     """
     if not restart:
         raise NotImplementedError("the reference always passes restart=true (inversion.jl:76)")
@@ -172,11 +177,28 @@ def gmres(A, b, x0=None, M=None, atol=np.sqrt(EPS), rtol=np.sqrt(EPS), itmax=0, 
         npass += 1
         k = 0                          # inner_iter
         inner_tired = False
+        raw, inv_h, corr = r0, 1.0 / β, None          # cgs2f: exchanged vector, its scale, H̄ h₂
+        Hbar = np.zeros((mem + 1, mem))
         while not (solved or inner_tired or breakdown):
             k += 1
-            w = A @ V[k - 1]
-            q = _apply(M, w)
-            if orth == "mgs":
+            if orth == "cgs2f":
+                q = _apply(M, (A @ raw) * inv_h)       # = Â v_k + V_k c,  c = H̄ h₂ / H (Arnoldi relation)
+            else:
+                w = A @ V[k - 1]
+                q = _apply(M, w)
+            if orth == "cgs2f":
+                h1 = V[:k] @ q
+                q -= h1 @ V[:k]
+                raw = q.copy()                        # q₁: what the other owners gather next
+                h2 = V[:k] @ q
+                ssq = float(q @ q)
+                q -= h2 @ V[:k]
+                # V_k c lies in the span just projected out: only the coefficients need the correction
+                hk = h1 + h2 - (inv_h * corr[:k] if corr is not None else 0.0)
+                R[nr:nr + k] = hk
+                Hbar[:k, k - 1] = hk
+                hsq = ssq - float(h2 @ h2)
+            elif orth == "mgs":
                 for i in range(k):
                     h = float(V[i] @ q)
                     R[nr + i] = h
@@ -193,7 +215,11 @@ def gmres(A, b, x0=None, M=None, atol=np.sqrt(EPS), rtol=np.sqrt(EPS), itmax=0, 
                 R[nr:nr + k] = h1
             else:
                 raise ValueError(orth)
-            Hbis = float(np.linalg.norm(q))
+            Hbis = float(np.sqrt(max(hsq, 0.0))) if orth == "cgs2f" else float(np.linalg.norm(q))
+            if orth == "cgs2f":
+                Hbar[k, k - 1] = Hbis
+                corr = Hbar[:k + 1, :k] @ h2
+                inv_h = 1.0 / Hbis if Hbis > 0 else 0.0
             for i in range(k - 1):
                 tmp = c[i] * R[nr + i] + s[i] * R[nr + i + 1]
                 R[nr + i + 1] = s[i] * R[nr + i] - c[i] * R[nr + i + 1]

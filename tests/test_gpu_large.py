@@ -27,7 +27,7 @@ def rel(a, b):
     return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
 
 
-@pytest.mark.parametrize("orth", [lib.ORTH_MGS, lib.ORTH_CGS2])
+@pytest.mark.parametrize("orth", [lib.ORTH_MGS, lib.ORTH_CGS2, lib.ORTH_CGS2_FUSED])
 @pytest.mark.parametrize("tma", ["1", "0"])
 def test_streaming_gmres_matches_oracle(ctx, orth, tma):
     ops = refined_ops()
@@ -37,7 +37,7 @@ def test_streaming_gmres_matches_oracle(ctx, orth, tma):
     M = np.full(y.size, ops["pscale"])
     itmax = 45                                    # two full restart cycles and a partial one
     xo, so = krylov.gmres(A, y, x0=np.zeros(y.size), M=M, atol=0.0, rtol=1e-30, memory=20, itmax=itmax,
-                          orth="mgs" if orth == lib.ORTH_MGS else "cgs2")
+                          orth={lib.ORTH_MGS: "mgs", lib.ORTH_CGS2: "cgs2", lib.ORTH_CGS2_FUSED: "cgs2f"}[orth])
     os.environ["NUPGCM_STREAM_TMA"] = tma
     try:
         x = ctx.vector(y.size)

@@ -68,7 +68,7 @@ def test_cg_sharded_matches_single_rank(ctx, nranks):
     assert all(info[r]["row_end"] == info[r + 1]["row_begin"] for r in range(nranks - 1))
 
 
-@pytest.mark.parametrize("orth", [lib.ORTH_MGS, lib.ORTH_CGS2])
+@pytest.mark.parametrize("orth", [lib.ORTH_MGS, lib.ORTH_CGS2, lib.ORTH_CGS2_FUSED])
 @pytest.mark.parametrize("nranks", [2, 4])
 def test_gmres_sharded_short_run_parity(ctx, nranks, orth):
     """2-D inversion, fixed itmax: iteration counts and residual histories against the oracle and

@@ -82,7 +82,7 @@ def test_cg_itmax_and_zero_rhs(ctx):
     assert st.niter == 0 and st.solved
 
 
-@pytest.mark.parametrize("orth", [lib.ORTH_MGS, lib.ORTH_CGS2])
+@pytest.mark.parametrize("orth", [lib.ORTH_MGS, lib.ORTH_CGS2, lib.ORTH_CGS2_FUSED])
 def test_gmres_parity_2d(ctx, orth):
     _, ops = workload("bowl_mixing", dim=2)
     A = ops["A"]

@@ -56,6 +56,11 @@ def test_gmres_matches_direct_solve_and_variants_agree():
     assert len(st.residuals) == st.niter + 1
     x2, st2 = krylov.gmres(A, b, M=M, atol=0.0, rtol=1e-10, memory=20, orth="cgs2", itmax=200000)
     assert st2.solved and abs(st2.niter - st.niter) <= max(2, st.niter // 100)
+    # the two-reduction CGS2 (Pythagorean norm + Arnoldi-relation correction) is CGS2 up to rounding
+    x3, st3 = krylov.gmres(A, b, M=M, atol=0.0, rtol=1e-10, memory=20, orth="cgs2f", itmax=200000)
+    assert st3.solved and abs(st3.niter - st2.niter) <= max(2, st.niter // 100)
+    assert np.allclose(st3.residuals[:300], st2.residuals[:300], rtol=1e-9)
+    assert np.linalg.norm(b - A @ x3) / np.linalg.norm(b) < 2e-10
 
 
 def test_sym_givens():
