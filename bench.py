@@ -304,7 +304,7 @@ def main():
         for _ in range(args.steps):
             flush.fill(0.0)
             ctx.timer_start()
-            npg.run_(m, n_steps=1)
+            npg.run_(m, n_steps=1, resume=True)     # one 100-step-style run, timed step by step
             step_ms.append(ctx.timer_stop())
         barrier()
         t_wall = time.perf_counter() - t_wall0
@@ -320,7 +320,7 @@ def main():
     npg.run_(m2, n_steps=args.warmup, sync_state=True, host_state=host)
     barrier()
     t0 = time.perf_counter()
-    npg.run_(m2, n_steps=args.steps, sync_state=True, host_state=host)
+    npg.run_(m2, n_steps=args.steps, sync_state=True, host_state=host, resume=True)
     barrier()
     e2e_s = time.perf_counter() - t0
     state_bytes = 8 * (d.nu + d.np + d.nb)

@@ -140,19 +140,37 @@ def evolve_(model: Model, u_prev: lib.Vector, b_prev: lib.Vector):
     return model
 
 
+def _sync_buffers(model: Model) -> dict:
+    """Device index vectors and staging vectors of the host-synchronised mode (built once)."""
+    sy = getattr(model, "_sync", None)
+    if sy is None:
+        ctx, d = model.arch.ctx, model.fe_data.dofs
+        N = d.nu + d.np
+        sy = {"p_b": ctx.index(d.p_b), "inv_p_b": ctx.index(d.inv_p_b),
+              "p_inversion": ctx.index(d.p_inversion), "inv_p_inversion": ctx.index(d.inv_p_inversion),
+              "stage_b": ctx.vector(d.nb), "stage_x": ctx.vector(N), "host_x": np.empty(N)}
+        model._sync = sy
+    return sy
+
+
 def run_(model: Model, n_info=10, n_save=float("inf"), n_steps=None, sync_state=False,
-         host_state=None, log=None, advection=True):
+         host_state=None, log=None, advection=True, resume=False):
     """``run!`` (model.jl:90-211).  ``n_steps`` bounds the number of steps taken by this call
-    (the reference loops until ``t >= t_stop``).  With ``sync_state`` the state is copied to the
+    (the reference loops until ``t >= t_stop``); ``resume=True`` makes a call continue the previous
+    one (see below).  With ``sync_state`` the state is copied to the
     host (Gridap order) and back every step, reproducing the reference's PCIe pattern."""
     ts = model.timestepper
     xu = model.inversion.solver.x
     xb = model.xb
     nu = model.fe_data.dofs.nu
     dofs = model.fe_data.dofs
-    # copies of previous and current u, b (model.jl:120-123)
-    model._u_prev.copy_from(xu)
-    model._b_prev.copy_from(xb)
+    # copies of previous and current u, b (model.jl:120-123).  ``resume`` continues the run of an
+    # earlier ``run_`` call on this model instead (keeps the previous-step fields, so that stepping
+    # one step per call is the same computation as one call for all steps).
+    if not (resume and getattr(model, "_has_prev", False)):
+        model._u_prev.copy_from(xu)
+        model._b_prev.copy_from(xb)
+    model._has_prev = True
     i = getattr(model, "_step_index", 1)
     done = 0
     while ts.t < ts.t_stop and (n_steps is None or done < n_steps):
@@ -160,9 +178,15 @@ def run_(model: Model, n_info=10, n_save=float("inf"), n_steps=None, sync_state=
         if i == 2 and isinstance(ts, BDF2):
             collect_evolution_LHS_(model.evolution, model.params, model.forcings, ts)  # :134-137
         if sync_state and host_state is not None:
-            # host -> device of the state the step starts from (pinned buffers)
-            xb.upload(host_state["b"][dofs.p_b])
-            xu.upload(np.concatenate([host_state["u"], host_state["p"]])[dofs.p_inversion])
+            # host -> device of the state the step starts from: one copy per field in Gridap order,
+            # permuted to solver order by a gather kernel (x[p], model.jl:274; inversion.jl:37-39)
+            sy = _sync_buffers(model)
+            sy["stage_b"].upload(host_state["b"])
+            xb.gather_from(sy["stage_b"], sy["p_b"])
+            sy["host_x"][:nu] = host_state["u"]
+            sy["host_x"][nu:] = host_state["p"]
+            sy["stage_x"].upload(sy["host_x"])
+            xu.gather_from(sy["stage_x"], sy["p_inversion"])
         model._u_curr.copy_from(xu)                                 # model.jl:140-141
         model._b_curr.copy_from(xb)
         evolve_(model, model._u_prev, model._b_prev)                # model.jl:144
@@ -180,9 +204,14 @@ def run_(model: Model, n_info=10, n_save=float("inf"), n_steps=None, sync_state=
             model.mesh.rebuild_friction(p.α ** 2 * p.ε ** 2, p.α, p.N2, eddy.N2min, 10.0, 1.0, xb,
                                           model.inversion.solver.A)
         if sync_state and host_state is not None:
-            x = xu.download()[dofs.inv_p_inversion]
+            # device -> host in Gridap order (solver.x[inv_perm], model.jl:282,312): gather on the
+            # device, one copy per field
+            sy = _sync_buffers(model)
+            sy["stage_x"].gather_from(xu, sy["inv_p_inversion"])
+            x = sy["stage_x"].download()
             host_state["u"], host_state["p"] = x[:nu], x[nu:]
-            host_state["b"] = xb.download()[dofs.inv_p_b]
+            sy["stage_b"].gather_from(xb, sy["inv_p_b"])
+            host_state["b"] = sy["stage_b"].download()
         rec = {"i": i, "t": ts.t, "cg_iters": model.evolution.solver.stats.niter,
                "gmres_iters": model.inversion.solver.stats.niter,
                "cg_ms": model.evolution.solver.stats.timer * 1e3,

@@ -258,3 +258,21 @@ def test_eddy_steps_match_oracle():
     inv2 = npg.InversionToolkit(arch, ops["A"], ops["pscale"], ops["B"], ops["b0"])
     with pytest.raises(ValueError):
         npg.Model(arch, w.params, forcings, fe, inv2, evo, ts, tables=ops["tables"])
+
+
+def test_resume_makes_stepwise_calls_equal_one_call():
+    """run_(n_steps=1, resume=True) repeated == run_(n_steps=n): the previous-step fields of BDF2
+    survive between calls (without resume every call restarts with prev = curr, model.jl:120-123)."""
+    w, ops = workload("bowl_mixing", dim=2)
+    a = build_gpu_model(w, ops)
+    npg.run_(a, n_steps=4)
+    w2, _ = workload("bowl_mixing", dim=2)
+    b = build_gpu_model(w2, ops)
+    for _ in range(4):
+        npg.run_(b, n_steps=1, resume=True)
+    assert np.array_equal(a.xb.download(), b.xb.download())
+    assert [r["gmres_iters"] for r in a.step_log] == [r["gmres_iters"] for r in b.step_log]
+    c = build_gpu_model(workload("bowl_mixing", dim=2)[0], ops)
+    for _ in range(4):
+        npg.run_(c, n_steps=1)
+    assert not np.array_equal(a.xb.download(), c.xb.download())
