@@ -649,15 +649,24 @@ struct SpmvEngine {
         const int G = kMainThreads / T;
         if constexpr (RES) {
             main_sync();                                     // previous readers of xs are done
-            {   // stage the footprint of xin: 4 independent L2 gathers in flight per thread
+            {   // stage the footprint of xin.  The gathers are L2 round trips (~0.7 us under load) and a
+                // thread owns up to ~14 footprint entries: issue up to 16 of them before the first use
+                // so that the whole footprint costs one round trip instead of one per group of four.
                 const int nt = kMainThreads;
-                int i = threadIdx.x;
-                for (; i + 3 * nt < nfoot; i += 4 * nt) {
-                    const double x0 = ld_cg(xin + foot[i]), x1 = ld_cg(xin + foot[i + nt]);
-                    const double x2 = ld_cg(xin + foot[i + 2 * nt]), x3 = ld_cg(xin + foot[i + 3 * nt]);
-                    xs[i] = x0; xs[i + nt] = x1; xs[i + 2 * nt] = x2; xs[i + 3 * nt] = x3;
+                constexpr int U = 16;
+                for (int base = threadIdx.x; base < nfoot; base += U * nt) {
+                    double xv[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int i = base + u * nt;
+                        xv[u] = i < nfoot ? ld_cg(xin + foot[i]) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int i = base + u * nt;
+                        if (i < nfoot) xs[i] = xv[u];
+                    }
                 }
-                for (; i < nfoot; i += nt) xs[i] = ld_cg(xin + foot[i]);
             }
             main_sync();
             for (int base = r0; base < r1; base += G) {      // uniform trip count over the CTA
@@ -1315,6 +1324,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
     bool tired = iter >= itmax;
     int npass = 0;
 
+    const bool fused = a.orth == NUPGCM_ORTH_CGS2_FUSED;
+    // Givens / least-squares update of one Arnoldi column (Krylov.jl order), by ONE thread
+    auto scalar_step = [&](int k, int nr, double hsq) {
+        const double Hbis = sqrt(hsq);
+        for (int i = 0; i < k - 1; ++i) {
+            const double tmp = sc[i] * sR[nr + i] + ss[i] * sR[nr + i + 1];
+            sR[nr + i + 1] = ss[i] * sR[nr + i] - sc[i] * sR[nr + i + 1];
+            sR[nr + i] = tmp;
+        }
+        double c, s, rho;
+        sym_givens(sR[nr + k - 1], Hbis, c, s, rho);
+        sc[k - 1] = c;
+        ss[k - 1] = s;
+        sR[nr + k - 1] = rho;
+        const double zeta = s * sz[k - 1];
+        sz[k - 1] = c * sz[k - 1];
+        sz[k] = zeta;                 // only consumed if the pass continues
+        s_flags[0] = fabs(zeta);
+        s_flags[3] = Hbis;
+    };
     while (!(solved || tired || breakdown || gr.aborted())) {
         // ---- start of a pass ----
         if (tid < kMaxMemory) { sc[tid] = 0.0; ss[tid] = 0.0; }
@@ -1459,26 +1488,35 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
                 double h2sq = 0.0;
                 for (int i = 0; i < k; ++i) h2sq = fma(sm_out[i], sm_out[i], h2sq);
                 hsq = fmax(sm_out[k] - h2sq, 0.0);
-                for (int row = r0 + tid; row < r1; row += nthr) {
-                    double qv = q[row];
-                    for (int i = 0; i < k; ++i) qv = fma(-sm_out[i], V.at(i)[row], qv);
-                    q[row] = qv;
-                }
-                const int hc = (k - 1) * (k + 2) / 2;          // packed offset of H̄ column k-1
-                if (tid < k) {
-                    const double h = sR[nr + tid] + sm_out[tid];
-                    sR[nr + tid] = h;
-                    s_h2[tid] = sm_out[tid];
-                    sHbar[hc + tid] = h;
-                } else if (tid == k) {
-                    sHbar[hc + k] = sqrt(hsq);
-                }
-                main_sync();
-                if (tid <= k) {
-                    const double Hb = sqrt(hsq);
-                    double c = 0.0;
-                    for (int j = tid > 0 ? tid - 1 : 0; j < k; ++j) c = fma(sHbar[j * (j + 3) / 2 + tid], s_h2[j], c);
-                    s_corr[tid] = Hb > 0.0 ? c / Hb : 0.0;
+                const double Hb = sqrt(hsq);
+                if (wid == 0) {
+                    // warp 0: Hessenberg column, correction for the next iteration, Givens update —
+                    // while the other warps update and normalise the vector
+                    const int hc = (k - 1) * (k + 2) / 2;      // packed offset of H̄ column k-1
+                    if (lane < k) {
+                        const double h = sR[nr + lane] + sm_out[lane];
+                        sR[nr + lane] = h;
+                        s_h2[lane] = sm_out[lane];
+                        sHbar[hc + lane] = h;
+                    } else if (lane == k) {
+                        sHbar[hc + k] = Hb;
+                    }
+                    __syncwarp();
+                    if (lane <= k) {
+                        double c = 0.0;
+                        for (int j = lane > 0 ? lane - 1 : 0; j < k; ++j) c = fma(sHbar[j * (j + 3) / 2 + lane], s_h2[j], c);
+                        s_corr[lane] = Hb > 0.0 ? c / Hb : 0.0;
+                    }
+                    __syncwarp();
+                    if (lane == 0) scalar_step(k, nr, hsq);
+                } else {
+                    // q₂ = q₁ − V h₂ and v_{k+1} = q₂ / H in one sweep (H is known to every thread)
+                    const double ih = 1.0 / Hb;
+                    for (int row = r0 + tid - 32; row < r1; row += nthr - 32) {
+                        double qv = q[row];
+                        for (int i = 0; i < k; ++i) qv = fma(-sm_out[i], V.at(i)[row], qv);
+                        q[row] = qv * ih;
+                    }
                 }
                 have_corr = true;
             } else {
@@ -1525,25 +1563,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
                     }
                 }
             }
-            // ---- scalar recurrences, replicated per CTA (thread 0), Krylov.jl order
-            main_sync();
-            if (tid == 0) {
-                const double Hbis = sqrt(hsq);
-                for (int i = 0; i < k - 1; ++i) {
-                    const double tmp = sc[i] * sR[nr + i] + ss[i] * sR[nr + i + 1];
-                    sR[nr + i + 1] = ss[i] * sR[nr + i] - sc[i] * sR[nr + i + 1];
-                    sR[nr + i] = tmp;
-                }
-                double c, s, rho;
-                sym_givens(sR[nr + k - 1], Hbis, c, s, rho);
-                sc[k - 1] = c;
-                ss[k - 1] = s;
-                sR[nr + k - 1] = rho;
-                const double zeta = s * sz[k - 1];
-                sz[k - 1] = c * sz[k - 1];
-                sz[k] = zeta;                 // only consumed if the pass continues
-                s_flags[0] = fabs(zeta);
-                s_flags[3] = Hbis;
+            // ---- scalar recurrences, replicated per CTA (one thread), Krylov.jl order
+            if (!fused) {
+                main_sync();
+                if (tid == 0) scalar_step(k, nr, hsq);
             }
             main_sync();
             rnorm = s_flags[0];
@@ -1558,7 +1581,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
             if (!(solved || inner_tired || breakdown)) {
                 // v_{k+1} = q / Hbis on own rows (q already sits in V[k]); raw q was published in dst
                 inv_h = 1.0 / Hbis;
-                for (int row = r0 + tid; row < r1; row += nthr) q[row] *= inv_h;
+                if (!fused)
+                    for (int row = r0 + tid; row < r1; row += nthr) q[row] *= inv_h;
                 cur ^= 1;
             }
         }
