@@ -72,14 +72,26 @@ static int choose_tpr(double mean_row) {
 }
 
 // Row ranges of the persistent kernels: contiguous, balanced on (nnz + 4*rows).
+// Cost of a row in matrix-entry units (NUPGCM_ROW_WEIGHT overrides): besides its entries a row costs
+// the per-row part of the SpMV and, above all, its share of the Krylov vector work (~4 k smem
+// fma per iteration for k basis vectors), which does not depend on the row's length.
+static double row_weight() {
+    if (const char *e = getenv("NUPGCM_ROW_WEIGHT")) {
+        const double v = atof(e);
+        if (v >= 0.0) return v;
+    }
+    return 4.0;
+}
+
 static void build_partition(const std::vector<int32_t> &rowptr, int64_t n_rows, int parts,
                             std::vector<int32_t> &part) {
     part.assign(parts + 1, 0);
-    const double total = (double)rowptr[n_rows] + 4.0 * (double)n_rows;
+    const double w = row_weight();
+    const double total = (double)rowptr[n_rows] + w * (double)n_rows;
     int64_t r = 0;
     for (int p = 1; p < parts; ++p) {
         const double target = total * p / parts;
-        while (r < n_rows && (double)rowptr[r] + 4.0 * (double)r < target) ++r;
+        while (r < n_rows && (double)rowptr[r] + w * (double)r < target) ++r;
         part[p] = (int32_t)r;
     }
     part[parts] = (int32_t)n_rows;

@@ -65,6 +65,7 @@ struct KrylovArgs {
     int poll_depth;          // replicas of the reduction slots (GridReduce)
     int xmode;               // sharded solves: 1 = gather / multi-rank broadcast reductions, 0 = two-level
     int xfence;              // 1: release.sys / acquire.sys on the inter-rank flags of publishing reductions
+    int debug_skip;          // timing experiments only (NUPGCM_DEBUG_SKIP): 1 = no footprint staging, 2 = no row loop
     unsigned long long *trace;   // debug: arrival/completion stamps of a window of reductions
     unsigned long long *barrier;
     double *partials;        // LLSlot [2][kPartialSlots][grid]
@@ -649,6 +650,7 @@ struct SpmvEngine {
         const int G = kMainThreads / T;
         if constexpr (RES) {
             main_sync();                                     // previous readers of xs are done
+            if (!(a.debug_skip & 1))
             {   // stage the footprint of xin.  The gathers are L2 round trips (~0.7 us under load) and a
                 // thread owns up to ~14 footprint entries: issue up to 16 of them before the first use
                 // so that the whole footprint costs one round trip instead of one per group of four.
@@ -669,7 +671,7 @@ struct SpmvEngine {
                 }
             }
             main_sync();
-            for (int base = r0; base < r1; base += G) {      // uniform trip count over the CTA
+            for (int base = r0; base < r1; base += ((a.debug_skip & 2) ? (r1 - r0 + 1) * G : G)) {      // uniform trip count over the CTA
                 const int row = base + g;
                 const bool active = row < r1;
                 double acc = 0.0, acc2 = 0.0;
@@ -1328,13 +1330,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
     // Givens / least-squares update of one Arnoldi column (Krylov.jl order), by ONE thread
     auto scalar_step = [&](int k, int nr, double hsq) {
         const double Hbis = sqrt(hsq);
+        // previous rotations applied to the new column; the running entry stays in a register so that
+        // the loop-carried dependence is two arithmetic ops per rotation, not a shared-memory round trip
+        double ri = sR[nr];
         for (int i = 0; i < k - 1; ++i) {
-            const double tmp = sc[i] * sR[nr + i] + ss[i] * sR[nr + i + 1];
-            sR[nr + i + 1] = ss[i] * sR[nr + i] - sc[i] * sR[nr + i + 1];
-            sR[nr + i] = tmp;
+            const double ci = sc[i], si = ss[i], rn = sR[nr + i + 1];
+            sR[nr + i] = ci * ri + si * rn;
+            ri = si * ri - ci * rn;
         }
         double c, s, rho;
-        sym_givens(sR[nr + k - 1], Hbis, c, s, rho);
+        sym_givens(ri, Hbis, c, s, rho);
         sc[k - 1] = c;
         ss[k - 1] = s;
         sR[nr + k - 1] = rho;
@@ -1858,6 +1863,7 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
     args.xmode = 1;
     if (const char *ex = getenv("NUPGCM_XMODE")) args.xmode = atoi(ex) != 0;
     if (const char *ex = getenv("NUPGCM_XFENCE")) args.xfence = atoi(ex) != 0;
+    if (const char *ex = getenv("NUPGCM_DEBUG_SKIP")) args.debug_skip = atoi(ex);
     args.halo_ptr = A->d_halo_ptr;
     args.halo_idx = A->d_halo_idx;
     args.ll_off = comm ? (long long)(kArenaVecOffset + 3 * (size_t)comm->n_pad * sizeof(double)) : 0;
