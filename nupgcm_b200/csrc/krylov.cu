@@ -399,8 +399,9 @@ __device__ __forceinline__ bool comm_mr(CommMailbox *mb, const KrylovArgs &a, LL
             else ll_store<false, true>(dst, total, xgen);
         }
     }
-    if (ct < count * P) {
-        const int j = ct / P, r = ct % P;
+    // count * nranks words (up to 21 x 8 = 168) over the 160 comm threads
+    for (int w = ct; w < count * P; w += kCommThreads) {
+        const int j = w / P, r = w % P;
         const LLSlot *src = xr_slot(a.arena[a.rank], xbank, j, bid % kXRep, r);
         if (PUBLISH && j == 0 && a.xfence) mb->xpart[j][r] = wait_flagged<true, true>(src, xgen, abort_word, bad);
         else if (PUBLISH && j == 0 && r == a.rank) mb->xpart[j][r] = wait_flagged<true, false>(src, xgen, abort_word, bad);

@@ -62,7 +62,7 @@ def main():
         print(f"CG    n={E.shape[0]} single {s[0]} its {1e3*s[3]/s[0]:.2f} us/it | sharded x{world} {m[0]} its "
               f"{1e3*m[3]/m[0]:.2f} us/it | rel diff {rel(m[2], s[2]):.2e}", flush=True)
     # ---- GMRES (both orthogonalisations)
-    for orth, name in ((lib.ORTH_MGS, "mgs"), (lib.ORTH_CGS2, "cgs2")):
+    for orth, name in ((lib.ORTH_MGS, "mgs"), (lib.ORTH_CGS2, "cgs2"), (lib.ORTH_CGS2_FUSED, "cgs2f")):
         outs = {}
         for mode in ("single", "sharded"):
             dA = ctx.csr(A, drop_zeros=True)
