@@ -9,6 +9,11 @@ and initial buoyancy, restating
 * ``bowl_surface_flux`` — ``test/bowl_surface_flux_tests.jl:14-62``
 * ``bowl_example``      — ``examples/bowl_mixing.jl:35-52,83,159,171`` (config 2: h=0.08, μϱ=1,
   BDF2 Δt=1e-3, b(0) = 0.1 exp(−(z+H)/(0.1α)))
+* ``channel_basin_box`` — BASELINE config 4 on the declared substitute mesh (structured box of the
+  ``meshes/channel_basin_flat.jl`` extent): wind stress of ``test/bowl_wind_tests.jl:27``, surface
+  buoyancy flux of ``test/bowl_surface_flux_tests.jl:29``, and the production time stepping of
+  ``scratch/run.jl:119-121,163``: ``BDF1(adaptive=true, CFL_factor=0.8)`` with the convection and
+  eddy parameterisations switched on
 """
 from __future__ import annotations
 
@@ -22,7 +27,7 @@ from .dofs import FEData
 from .inputs import Forcings, Parameters, SurfaceDirichletBC, SurfaceFluxBC
 from .meshes import Mesh
 from .spaces import Spaces
-from .timesteppers import BDF2
+from .timesteppers import BDF1, BDF2
 
 MESH_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "meshes")
 
@@ -51,6 +56,8 @@ class Workload:
         return self._fe
 
     def timestepper(self):
+        if self.timestepper_kwargs.get("adaptive"):
+            return BDF1(**self.timestepper_kwargs)
         return BDF2(**self.timestepper_kwargs)
 
 
@@ -132,6 +139,28 @@ def bowl_example(h: float = 0.08, mesh=None, n_steps: int | None = None) -> Work
                     dict(_U_DIRI, b_diri_tags=["coastline", "surface"], b_diri_vals=[0.0, 0.0]),
                     dict(t_start=0.0, t_stop=t_stop, Δt=Δt),
                     lambda x: 0.1 * np.exp(-(x[:, 2] + H(x)) / (0.1 * α)), invert_first=True)
+
+
+def channel_basin_box(n=(6, 12, 4), α: float = 0.125) -> Workload:
+    """Config 4 substitute: flat channel-basin box x∈[0,1], y∈[−1,1], z∈[−α,0] (n cells per
+    direction), wind + surface flux forcing, adaptive BDF1, convection + eddy parameterisations."""
+    from .gridap_lite import box_mesh
+    from .inputs import ConvectionParameterization, EddyParameterization
+    ε, μϱ = np.sqrt(1e-1), 1.0
+    f = lambda x: 1.0 + 0.5 * x[:, 1]                                           # noqa: E731
+    H = lambda x: np.full(len(x), α)                                            # noqa: E731
+    params = Parameters(ε=ε, α=α, μϱ=μϱ, N2=1.0, f=f, H=H)
+    κ = lambda x: 1e-2 + np.exp(-(x[:, 2] + α) / (0.1 * α))                     # noqa: E731
+    forcings = Forcings(1, κ, κ, lambda x: -1e-1 * np.cos(np.pi * x[:, 1] / 2), 0.0,
+                        SurfaceFluxBC(lambda x: 1e-3 * np.sin(np.pi * x[:, 0])),
+                        conv_param=ConvectionParameterization(κᶜ=1.0, N2min=1e-3),
+                        eddy_param=EddyParameterization(f=f, N2min=np.sqrt(1e-3)))
+    mesh = box_mesh(*n, z=(-α, 0.0))
+    return Workload("channel_basin_box", params, forcings, mesh, dict(_U_DIRI),
+                    # CFL_factor: the reference's production value is 0.8 on its h = 1e-2 mesh; on this
+                    # coarse stand-in the u_min = 0.01 floor alone would give Δt ≈ 19 at rest, so 0.05
+                    dict(t_start=0.0, t_stop=float("inf"), Δt=1e-2, adaptive=True, CFL_factor=0.05),
+                    lambda x: 0.1 * x[:, 2] / α)
 
 
 def host_operands(w: Workload) -> dict:

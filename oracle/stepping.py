@@ -144,7 +144,21 @@ def cpu_model_for(workload, ops=None, **kw):
     ops = host_operands(workload) if ops is None else ops
     p = workload.params
     tk = workload.timestepper_kwargs
-    scheme = kw.pop("scheme", 2)
+    scheme = kw.pop("scheme", 1 if tk.get("adaptive") else 2)
+    if tk.get("adaptive"):
+        kw.setdefault("adaptive", True)
+        kw.setdefault("cfl_factor", tk.get("CFL_factor", 0.8))
+    f = workload.forcings
+    fe = workload.fe_data()
+    if f.conv_param.is_on and "conv" not in kw:
+        kw["conv"] = (f.conv_param.κᶜ, f.conv_param.N2min)
+        kw["kv_q"] = fe.mesh.dΩ.coefficient(f.κᵥ, slice(None))
+    if f.eddy_param.is_on and "eddy" not in kw:
+        from nupgcm_b200._forms import build_A_inversion      # host set-up code (operands), not the device path
+        pi = fe.dofs.p_inversion
+        kw["eddy"] = f.eddy_param.N2min
+        kw["f_q"] = fe.mesh.dΩ.coefficient(f.eddy_param.f, slice(None))
+        kw["A0"] = build_A_inversion(fe, p, 0.0)[pi][:, pi].tocsr()
     m = CpuModel(ops, {"α": p.α, "ε": p.ε, "μϱ": p.μϱ, "N2": p.N2}, scheme, tk["Δt"], tk["t_start"],
                  tk["t_stop"], **kw)
     return m

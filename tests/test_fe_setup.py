@@ -103,3 +103,31 @@ def test_msh_and_npz_meshes_agree():
     for d in range(4):
         assert np.array_equal(a.elements[d], b.elements[d])
         assert a.element_names[d] == b.element_names[d]
+
+
+def test_box_mesh_and_channel_basin_workload():
+    """BASELINE config 4 on its declared substitute mesh: geometry, boundary names, DOF counts,
+    and a 12-step oracle run of the production configuration (adaptive BDF1 + convection + eddy
+    parameterisations) — Δt adapts, the eddy viscosity rebuild after step 10 changes the flow."""
+    from nupgcm_b200 import workloads as W
+    from nupgcm_b200.gridap_lite import box_mesh
+    from oracle.stepping import cpu_model_for
+    raw = box_mesh(3, 4, 2, z=(-0.125, 0.0))
+    assert raw.nodes.shape == (4 * 5 * 3, 3) and raw.elements[3].shape == (3 * 4 * 2 * 6, 4)
+    assert len(raw.elements[2]) == 2 * 2 * (3 * 4 + 3 * 2 + 4 * 2)          # two triangles per boundary quad
+    assert sum(n == ("surface",) for n in raw.element_names[2]) == 2 * 3 * 4
+    assert len(raw.elements[1]) == 2 * (3 + 4)                                # rim of the top face
+    w = W.channel_basin_box()
+    fe = w.fe_data()
+    assert fe.mesh.dΩ.meas.sum() == pytest.approx(1.0 * 2.0 * 0.125, rel=1e-12)
+    assert set(fe.mesh.model.tag_names) == {"bottom", "coastline", "surface"}
+    d = fe.dofs
+    assert d.np == 7 * 13 * 5 - 1 and d.nb == 13 * 25 * 9                    # flux BC: every P2 node is free
+    ops = W.host_operands(w)
+    cpu = cpu_model_for(w, ops, solver="direct")
+    cpu.run(n_steps=12)
+    nu = ops["nu"]
+    assert np.isfinite(cpu.xu).all() and np.abs(cpu.xu[:nu]).max() < 1.0
+    assert cpu.dts[0] == pytest.approx(0.05 * ops["tables"]["h_cells"].min() / 0.01)   # flow at rest
+    assert cpu.dts[1] < 0.1 * cpu.dts[0]                                      # CFL takes over
+    assert cpu.dts[11] > 2.0 * cpu.dts[10]                                    # ν_eddy rebuilt after step 10

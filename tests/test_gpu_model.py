@@ -276,3 +276,32 @@ def test_resume_makes_stepwise_calls_equal_one_call():
     for _ in range(4):
         npg.run_(c, n_steps=1)
     assert not np.array_equal(a.xb.download(), c.xb.download())
+
+
+def test_channel_basin_production_configuration_matches_oracle():
+    """BASELINE config 4 (declared substitute mesh): wind + surface buoyancy flux, adaptive BDF1, the
+    convection parameterisation every step and the eddy-viscosity rebuild after step 10 — every
+    "next" row of the scope table in one run — against the oracle's direct-solve path."""
+    from nupgcm_b200 import workloads as W
+    w = W.channel_basin_box()
+    ops = W.host_operands(w)
+    n = 12
+    cpu = cpu_model_for(w, ops, solver="direct")
+    cpu.run(n_steps=n)
+    arch = npg.GPU(0)
+    fe = w.fe_data()
+    inv = npg.InversionToolkit(arch, ops["A"], ops["pscale"], ops["B"], ops["b0"], atol=0.0, rtol=1e-13,
+                               itmax=3000000, drop_zeros=False)
+    ts = w.timestepper()
+    evo = npg.EvolutionToolkit(arch, ops, w.params, w.forcings, ts, atol=0.0, rtol=1e-14)
+    gpu = npg.Model(arch, w.params, w.forcings, fe, inv, evo, ts, tables=ops["tables"])
+    gpu.xb.upload(ops["b_init"])
+    dts = []
+    for _ in range(n):
+        npg.run_(gpu, n_steps=1, resume=True)
+        dts.append(ts.Δt)
+    assert np.allclose(dts, cpu.dts, rtol=1e-8), (dts, cpu.dts)
+    d = fe.dofs
+    assert rel(gpu.xb.download(), cpu.xb) < 1e-8
+    assert rel(gpu.inversion.solver.x.download()[:d.nu], cpu.xu[:d.nu]) < 1e-8
+    assert all(r["gmres_solved"] and r["cg_solved"] for r in gpu.step_log)

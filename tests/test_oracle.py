@@ -104,3 +104,38 @@ def test_golden_states_within_reference_tolerance(name, gold):
     eu = (u - g["u"]) @ (Mu @ (u - g["u"])) / (g["u"] @ (Mu @ g["u"]))
     eb = (b - g["b"]) @ (Mb @ (b - g["b"])) / (g["b"] @ (Mb @ g["b"]))
     assert eu < 1e-3 and eb < 1e-3, (eu, eb)
+
+
+def test_oracle_cfl_and_parameterisation_rebuilds_match_host_assembly():
+    """Pins of the "next"-row restatements (oracle/element_rhs.py) against the host set-up code,
+    which is itself pinned to the reference's matrix fixture (tests/test_fe_setup.py):
+    * kv_rebuild with κᶜ = 0 reproduces Kᵥ, rhsᵥ, rhs_diff of build_Kv / build_rhs_diff;
+    * nu_friction with a prescribed ν(x) reproduces the friction block 2α²ε²ν σ(u)⊙σ(v);
+    * cfl_dt with u = 0 is CFL · min h / u_min and decreases once the flow is fast."""
+    from nupgcm_b200._forms import build_A_inversion
+    from oracle.element_rhs import cfl_dt, kv_rebuild, nu_friction
+    for name, kw in (("bowl_mixing", {"dim": 2}), ("bowl_dirichlet", {})):
+        w, ops = workload(name, **kw)
+        fe = w.fe_data()
+        t = ops["tables"]
+        kv_q = fe.mesh.dΩ.coefficient(w.forcings.κᵥ, slice(None))
+        K, rv, rd = kv_rebuild(t, kv_q, w.params.α, w.params.N2, 0.0, 1.0, ops["b_init"], ops["M"])
+        assert np.array_equal(K.indices, ops["Kv"].indices)
+        assert np.abs(K.data - ops["Kv"].data).max() <= 1e-14 * np.abs(ops["Kv"].data).max()
+        assert np.abs(rv - ops["rhs_v"]).max() <= 1e-14 * max(np.abs(ops["rhs_v"]).max(), 1.0)
+        assert np.abs(rd - ops["rhs_diff"]).max() <= 1e-14 * max(np.abs(ops["rhs_diff"]).max(), 1.0)
+        assert cfl_dt(t, np.zeros(ops["nu"]), 0.8, 0.01) == pytest.approx(0.8 * t["h_cells"].min() / 0.01)
+        fast = np.full(ops["nu"], 3.0)
+        assert cfl_dt(t, fast, 0.8, 0.01) < 0.8 * t["h_cells"].max() / 3.0
+    w, ops = workload("bowl_mixing", dim=2)
+    fe = w.fe_data()
+    p = fe.dofs.p_inversion
+    νf = lambda x: 1.0 + 0.3 * x[:, 0] + 0.5 * x[:, 2] ** 2                  # noqa: E731
+    a2e2 = w.params.α ** 2 * w.params.ε ** 2
+    ref = (build_A_inversion(fe, w.params, νf)[p][:, p] - build_A_inversion(fe, w.params, 0.0)[p][:, p]).tocsr()
+    νq = fe.mesh.dΩ.coefficient(νf, slice(None))
+    # f²/N²min = ν with b = 0, N² = 0; a very sharp LogSumExp and a far-away floor leave ν untouched
+    got = nu_friction(ops["tables"], np.sqrt(νq), a2e2, w.params.α, 0.0, 1.0, np.zeros(ops["nb"]),
+                      ref.shape[0], smoothing=200.0, ν_min=-50.0)
+    d = (got - ref).tocsr()
+    assert np.abs(d.data).max() <= 1e-14 * np.abs(ref.data).max()
