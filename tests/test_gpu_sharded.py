@@ -29,13 +29,48 @@ def _evol(ops, θ=0.05):
 
 
 def _sharded(nranks, A, solve, drop_zeros=False):
-    """Run `solve(ctx, dA)` collectively on `nranks` ranks sharing cuda:0; returns per-rank results."""
+    """Run `solve(ctx, dA)` collectively on `nranks` ranks sharing cuda:0; returns per-rank results.
+
+    The ranks share ONE device here, so a device-wide synchronisation on one rank's thread (cudaFree
+    of a temporary vector) would wait for another rank's persistent kernel, which in turn may be
+    waiting for this rank's next launch.  `solve` therefore runs under `_NoFree`: vectors created
+    inside it stay alive until every rank has finished (with one process per GPU, the production
+    set-up, a rank's cudaFree only ever waits for its own device)."""
+    import threading
     comms = local_ranks(nranks, A.shape[0])
     mats = [c.ctx.csr(A, drop_zeros=drop_zeros).shard(c) for c in comms]
-    try:
-        return run_collective([lambda c=c, m=m: solve(c.ctx, m) for c, m in zip(comms, mats)]), mats, comms
-    finally:
-        pass
+    done = threading.Barrier(nranks)
+
+    def rank_main(c, m):
+        keep = _NoFree(c.ctx)
+        try:
+            return solve(keep, m)
+        finally:
+            try:
+                done.wait(timeout=120)     # nobody frees anything before all ranks' kernels have ended
+            except threading.BrokenBarrierError:
+                pass
+            keep.release()
+
+    return run_collective([lambda c=c, m=m: rank_main(c, m) for c, m in zip(comms, mats)]), mats, comms
+
+
+class _NoFree:
+    """Context proxy whose vectors are kept alive until release()."""
+
+    def __init__(self, ctx):
+        self._ctx, self._keep = ctx, []
+
+    def vector(self, data_or_n):
+        v = self._ctx.vector(data_or_n)
+        self._keep.append(v)
+        return v
+
+    def __getattr__(self, name):
+        return getattr(self._ctx, name)
+
+    def release(self):
+        self._keep.clear()
 
 
 @pytest.mark.parametrize("nranks", [2, 4])
