@@ -281,6 +281,8 @@ def main():
         evo = npg.EvolutionToolkit(arch, ops, w.params, w.forcings, ts)
         m = npg.Model(arch, w.params, w.forcings, w.fe_data(), inv, evo, ts, tables=ops["tables"])
         m.xb.upload(ops["b_init"])
+        if dist is not None:
+            dist.barrier()                       # ranks enter the first collective solve together
         npg.invert_(m)                           # examples/bowl_mixing.jl:194
         return m
 

@@ -84,7 +84,7 @@ struct KrylovArgs {
 
 // Watchdog of every cross-CTA wait: a CTA that waits longer than this raises the abort word and
 // all CTAs leave the solve, so a lost CTA becomes a reported error instead of a hung GPU.
-static const unsigned long long kWaitTimeoutNs = 4000000000ULL;
+static const unsigned long long kWaitTimeoutNs = 10000000000ULL;   // 10 s: also covers the launch skew between ranks (processes)
 
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;

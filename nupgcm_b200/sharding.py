@@ -10,6 +10,10 @@ The reference is single-GPU; the sharded path is this package's answer to BASELI
   between the ranks);
 * ``run_collective(fns)`` — run one callable per rank concurrently (sharded solves are collective:
   every rank must be inside the same solve at the same time).
+
+A sharded solve waits at most 10 s for a peer (then every rank aborts with an error): when host-side
+set-up times differ between processes, put a ``torch.distributed.barrier()`` in front of the first
+collective solve.
 """
 from __future__ import annotations
 
