@@ -46,6 +46,7 @@ typedef struct nupgcm_index nupgcm_index;
 typedef struct nupgcm_csr nupgcm_csr;
 typedef struct nupgcm_mesh nupgcm_mesh;
 typedef struct nupgcm_comm nupgcm_comm;
+typedef struct nupgcm_blockprec nupgcm_blockprec;
 
 int32_t nupgcm_version(void);
 const char *nupgcm_last_error(const nupgcm_ctx *ctx);
@@ -206,6 +207,25 @@ int32_t nupgcm_gmres_solve(const nupgcm_csr *A, const nupgcm_vec *dinv, double p
                            const nupgcm_vec *y, nupgcm_vec *x, double atol, double rtol,
                            int64_t itmax, int32_t memory, int32_t orth, double *resid_hist,
                            int64_t hist_cap, nupgcm_solve_stats *stats);
+
+/* ---- operator preconditioners (src/preconditioners.jl) -------------------------------------
+ * BlockDiagonalPreconditioner of the inversion system [u; p] (:53-125): y[0:n1] = P⁻¹ x[0:n1],
+ * y[n1:] = T⁻¹ x[n1:], each inverse a CgPreconditioner (:5-37): CG on the block with a Jacobi
+ * preconditioner, atol = rtol = sqrt(eps), at most `itmax` iterations (0: 2n), warm-started from
+ * the block's previous answer.  The reference's GPU set-up uses ILU(0) for P (:102-107); Jacobi
+ * here (declared deviation).  The handles passed in must outlive the preconditioner. */
+int32_t nupgcm_blockprec_create(nupgcm_ctx *ctx, const nupgcm_csr *P, const nupgcm_vec *P_dinv,
+                                int64_t P_itmax, const nupgcm_csr *T, const nupgcm_vec *T_dinv,
+                                int64_t T_itmax, nupgcm_blockprec **out);
+int32_t nupgcm_blockprec_destroy(nupgcm_blockprec *M);
+int32_t nupgcm_blockprec_apply(nupgcm_blockprec *M, const nupgcm_vec *x, nupgcm_vec *y); /* mul!(y, M, x) */
+int32_t nupgcm_blockprec_info(const nupgcm_blockprec *M, int64_t *applies, int64_t *inner_iters);
+/* GMRES(memory), left-preconditioned by M, modified Gram-Schmidt: same contract as
+ * nupgcm_gmres_solve (x in/out = warm start; non-convergence is not an error) */
+int32_t nupgcm_gmres_solve_prec(const nupgcm_csr *A, nupgcm_blockprec *M, const nupgcm_vec *y,
+                                nupgcm_vec *x, double atol, double rtol, int64_t itmax,
+                                int32_t memory, double *resid_hist, int64_t hist_cap,
+                                nupgcm_solve_stats *stats);
 
 /* diagnostics: average latency (µs) of the grid-wide reduction the persistent solvers use.
  * mode 0: flagged-slot exchange only; 1: + block reduction; 2: + release/acquire fences. */

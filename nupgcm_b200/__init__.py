@@ -16,6 +16,7 @@ from .inversion import InversionToolkit
 from .io import save_state, set_state_from_file_
 from .iterative_solvers import IterativeSolverToolkit, iterative_solve_
 from .meshes import Mesh
+from .preconditioners import BlockDiagonalPreconditioner
 from .model import Model, State, evolve_, invert_, run_, set_b_, sync_flow_
 from .spaces import Spaces
 from .timesteppers import BDF1, BDF2, evolution_parameter, update_t_
@@ -23,7 +24,7 @@ from .timesteppers import BDF1, BDF2, evolution_parameter, update_t_
 __all__ = [
     "CPU", "GPU", "architecture", "on_architecture", "print_memory_status", "vector_type",
     "DoFHandler", "FEData", "EvolutionToolkit", "collect_evolution_LHS_", "Forcings",
-    "ConvectionParameterization", "EddyParameterization",
+    "ConvectionParameterization", "EddyParameterization", "BlockDiagonalPreconditioner",
     "Parameters", "SurfaceDirichletBC", "SurfaceFluxBC", "InversionToolkit",
     "IterativeSolverToolkit", "iterative_solve_", "Mesh", "Model", "State", "evolve_",
     "invert_", "run_", "set_b_", "sync_flow_", "Spaces", "BDF1", "BDF2",

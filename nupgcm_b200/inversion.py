@@ -62,8 +62,10 @@ class InversionToolkit:
         x = arch.ctx.vector(N)                                  # workspace.x .= 0 (inversion.jl:85)
         kwargs = dict(atol=atol, rtol=rtol, itmax=itmax, history=history, verbose=verbose,
                       restart=restart, memory=memory, orth=orth)
-        self.solver = IterativeSolverToolkit(A_dev, Diagonal(pscale), x, y, "gmres", kwargs,
-                                             "Inversion")
+        # P: the scalar 1/h^dim of inversion.jl:54, or an operator preconditioner
+        # (BlockDiagonalPreconditioner, the alternative of inversion.jl:60)
+        P = pscale if hasattr(pscale, "handle") else Diagonal(pscale)
+        self.solver = IterativeSolverToolkit(A_dev, P, x, y, "gmres", kwargs, "Inversion")
 
 
 def invert_(inversion: InversionToolkit, b: lib.Vector):

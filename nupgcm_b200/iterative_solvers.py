@@ -54,10 +54,15 @@ def iterative_solve_(tk: IterativeSolverToolkit) -> IterativeSolverToolkit:
     """``iterative_solve!`` (iterative_solvers.jl:31-68), GPU branch."""
     kw = tk.kwargs
     hist = int(kw.get("history_cap", 65536)) if kw.get("history", True) else 0
-    common = dict(dinv=tk.P.vec, pscale=tk.P.scalar if tk.P.scalar is not None else 1.0,
+    diag = tk.P if isinstance(tk.P, Diagonal) else Diagonal(1.0)
+    common = dict(dinv=diag.vec, pscale=diag.scalar if diag.scalar is not None else 1.0,
                   atol=kw.get("atol", 1e-6), rtol=kw.get("rtol", 1e-6), itmax=kw.get("itmax", 0),
                   history=hist)
-    if tk.method == "gmres":
+    if tk.method == "gmres" and hasattr(tk.P, "handle"):
+        # operator preconditioner (BlockDiagonalPreconditioner, inversion.jl:60)
+        st, res = lib.gmres_solve_prec(tk.A, tk.P.handle, tk.y, tk.x, atol=common["atol"], rtol=common["rtol"],
+                                       itmax=common["itmax"], memory=kw.get("memory", 20), history=hist)
+    elif tk.method == "gmres":
         if not kw.get("restart", True):
             raise NotImplementedError("restart=false GMRES is not provided")
         st, res = lib.gmres_solve(tk.A, tk.y, tk.x, memory=kw.get("memory", 20),

@@ -81,6 +81,12 @@ SIGNATURES = {
                         POINTER(SolveStats)],
     "nupgcm_gmres_solve": [_P, _P, c_double, _P, _P, c_double, c_double, c_int64, c_int32, c_int32,
                            _dp, c_int64, POINTER(SolveStats)],
+    "nupgcm_blockprec_create": [_P, _P, _P, c_int64, _P, _P, c_int64, POINTER(_P)],
+    "nupgcm_blockprec_destroy": [_P],
+    "nupgcm_blockprec_apply": [_P, _P, _P],
+    "nupgcm_blockprec_info": [_P, _ip, _ip],
+    "nupgcm_gmres_solve_prec": [_P, _P, _P, _P, c_double, c_double, c_int64, c_int32, _dp, c_int64,
+                                POINTER(SolveStats)],
     "nupgcm_diag_reduce_latency": [_P, c_int32, c_int32, c_int32, c_int32, POINTER(c_float)],
     "nupgcm_diag_pingpong": [_P, c_int32, c_int32, c_int32, POINTER(c_float)],
     "nupgcm_diag_xping": [_P, c_int32, c_int32, c_int32, c_int32, POINTER(c_float)],
@@ -474,6 +480,45 @@ def gmres_solve(A: CsrMatrix, y: Vector, x: Vector, dinv: Vector | None = None, 
                 atol=1e-6, rtol=1e-6, itmax=0, memory=20, orth=ORTH_MGS, history=0):
     return _solve(A.lib.nupgcm_gmres_solve, A, dinv, pscale, y, x, atol, rtol, itmax,
                   (int(memory), int(orth)), history)
+
+
+class BlockPrec:
+    """``BlockDiagonalPreconditioner`` of two ``CgPreconditioner`` blocks (``nupgcm_blockprec_*``)."""
+
+    def __init__(self, ctx: Context, P: CsrMatrix, P_dinv: Vector, P_itmax: int, T: CsrMatrix,
+                 T_dinv: Vector, T_itmax: int):
+        self.ctx, self.lib = ctx, ctx.lib
+        self._keep = (P, P_dinv, T, T_dinv)                 # the library borrows these handles
+        h = _P()
+        _check(self.lib.nupgcm_blockprec_create(ctx.h, P.h, P_dinv.h, int(P_itmax), T.h, T_dinv.h,
+                                                int(T_itmax), byref(h)), ctx.h)
+        self.h = h
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.lib.nupgcm_blockprec_destroy(self.h)
+        except Exception:
+            pass
+
+    def apply(self, x: Vector, y: Vector):
+        _check(self.lib.nupgcm_blockprec_apply(self.h, x.h, y.h), self.ctx.h)
+        return y
+
+    def info(self):
+        a, b = c_int64(), c_int64()
+        _check(self.lib.nupgcm_blockprec_info(self.h, byref(a), byref(b)), self.ctx.h)
+        return {"applies": a.value, "inner_iters": b.value}
+
+
+def gmres_solve_prec(A: CsrMatrix, M: BlockPrec, y: Vector, x: Vector, atol=1e-6, rtol=1e-6, itmax=0,
+                     memory=20, history=0):
+    cap = int(history) if history else 0
+    hist = np.empty(max(cap, 1))
+    st = SolveStats()
+    _check(A.lib.nupgcm_gmres_solve_prec(A.h, M.h, y.h, x.h, float(atol), float(rtol), int(itmax),
+                                         int(memory), _ptr(hist) if cap else None, cap, byref(st)), A.ctx.h)
+    return st, hist[:st.hist_len].copy()
 
 
 class ElementMesh:

@@ -36,7 +36,31 @@ class Stats:
 
 
 def _apply(M, r):
-    return r.copy() if M is None else M * r
+    if M is None:
+        return r.copy()
+    return M(r) if callable(M) else M * r
+
+
+class BlockDiagonalPreconditioner:
+    """Reference ``src/preconditioners.jl:53-125`` with ``CgPreconditioner`` blocks (``:5-37``):
+    ``y[:n1] = CG(P)⁻¹ x[:n1]``, ``y[n1:] = CG(T)⁻¹ x[n1:]``; each inner CG uses Krylov.jl's default
+    tolerances (atol = rtol = sqrt(eps)), an iteration cap and the block's previous answer as its
+    initial guess (``cgp.workspace.x``, ``:25``).  Inner preconditioners are Jacobi (the GPU set-up
+    of the reference uses ILU(0) for ``P``, ``:102-107`` — same deviation as the device code)."""
+
+    def __init__(self, P, T, P_itmax=100, T_itmax=0):
+        self.P, self.T = P.tocsr(), T.tocsr()
+        self.Pd, self.Td = 1.0 / self.P.diagonal(), 1.0 / self.T.diagonal()
+        self.n1 = self.P.shape[0]
+        self.P_itmax, self.T_itmax = P_itmax, T_itmax
+        self.xp, self.xt = np.zeros(self.n1), np.zeros(self.T.shape[0])
+        self.inner_iters = 0
+
+    def __call__(self, x):
+        self.xp, s1 = cg(self.P, x[:self.n1], x0=self.xp, M=self.Pd, itmax=self.P_itmax, history=False)
+        self.xt, s2 = cg(self.T, x[self.n1:], x0=self.xt, M=self.Td, itmax=self.T_itmax, history=False)
+        self.inner_iters += s1.niter + s2.niter
+        return np.concatenate([self.xp, self.xt])
 
 
 def cg(A, b, x0=None, M=None, atol=np.sqrt(EPS), rtol=np.sqrt(EPS), itmax=0, history=True):
