@@ -23,7 +23,14 @@
 //
 // The recurrences restate Krylov.jl 0.10 `cg!` and `gmres!`: warm start
 // (x on entry is the initial guess), preconditioned stopping measure against
-// atol + rtol*(initial measure), itmax = 2n when 0, MGS Arnoldi (optionally CGS2).
+// atol + rtol*(initial measure), itmax = 2n when 0, MGS Arnoldi — or CGS2 with three, or (fused)
+// two, grid reductions per iteration (see the orthogonalisation branches of k_gmres).
+//
+// Multi-GPU (template parameter MR): the same kernels run one rank per GPU on a row-block sharded
+// system.  Rank r's CTA b is part r*gridDim.x + b of the partition; rows that a peer's SpMV gathers
+// are pushed into the peer's memory over NVLink as flagged 16-byte words (HaloPush) and unpacked by
+// the reader before its SpMV; reductions take two hops (CTA -> reducer CTA on the same GPU ->
+// every rank's arena); a solve ends with an all-gather of the solution.  See comm.cu and DESIGN.md §6.
 #include <algorithm>
 
 #include "common.cuh"
