@@ -54,8 +54,16 @@ def local_ranks(nranks: int, max_n: int, devices=None):
 def run_collective(fns):
     """Call ``fns[r]()`` for every rank concurrently (ctypes releases the GIL inside the library);
     returns the results in rank order and re-raises the first exception."""
+    import gc
     out = [None] * len(fns)
     err = [None] * len(fns)
+    # Ranks that share one device (tests) must not meet a device-wide synchronisation while a peer's
+    # persistent kernel is waiting for them: a cyclic-GC pass that finalises old device objects
+    # (cudaFree) in one rank's thread would be exactly that.  Collect now, keep the collector off
+    # until every rank is done.  (With one process per GPU a cudaFree only waits for its own device.)
+    gc.collect()
+    gc_was_enabled = gc.isenabled()
+    gc.disable()
 
     def work(r):
         try:
@@ -68,6 +76,8 @@ def run_collective(fns):
         t.start()
     for t in ts:
         t.join()
+    if gc_was_enabled:
+        gc.enable()
     for e in err:
         if e is not None:
             raise e
