@@ -373,6 +373,10 @@ def main():
                        "cg_us_per_iter": float(1e3 * c_ms.sum() / max(c_iters.sum(), 1)),
                        "initial_inversion_gmres_iters": int(init_gmres),
                        "all_solved": bool(all(r["gmres_solved"] and r["cg_solved"] for r in log))},
+        "scaling_note": ("the h=0.08 system (N=31 395) lives in the shared memory of one GPU and is bound by "
+                         "reduction latency, so `value` stays flat under sharding by construction; the `refined` "
+                         "object times BASELINE configs[2] (h=0.04 inversion-only solve), the configuration quoted "
+                         "at 1/2/4/8 GPUs, in the same run"),
         "clocks": clocks.summary(),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": state_bytes,
                 "d2h_bytes_per_step": state_bytes},
