@@ -67,6 +67,10 @@ int32_t nupgcm_timer_stop(nupgcm_ctx *ctx, float *ms);
 /* number of kernels this context has launched since creation */
 int32_t nupgcm_launch_count(nupgcm_ctx *ctx, int64_t *count);
 
+/* page-locked host buffers (cudaHostAlloc) for the host's copy of the state: the per-step
+ * upload/download of src/model.jl:275,282,312 then runs as plain DMA */
+int32_t nupgcm_host_alloc(nupgcm_ctx *ctx, int64_t bytes, void **out);
+int32_t nupgcm_host_free(nupgcm_ctx *ctx, void *p);
 /* Restrict the persistent solver kernels of this context to `grid` CTAs (1..SM count; default:
  * one per SM).  Lets several contexts share one device, each with a slice of the SMs. */
 int32_t nupgcm_set_grid(nupgcm_ctx *ctx, int32_t grid);

@@ -78,6 +78,22 @@ extern "C" int32_t nupgcm_set_grid(nupgcm_ctx *ctx, int32_t grid) {
     return NUPGCM_OK;
 }
 
+// Page-locked host memory for the buffers a host keeps its copy of the state in: uploads and
+// downloads from/to it are plain DMA transfers (no staging copy inside the driver).
+extern "C" int32_t nupgcm_host_alloc(nupgcm_ctx *ctx, int64_t bytes, void **out) {
+    NUPGCM_REQUIRE(nullptr, ctx, "ctx is NULL");
+    NUPGCM_REQUIRE(ctx, out && bytes > 0, "host_alloc: bad argument");
+    NUPGCM_CUDA(ctx, cudaSetDevice(ctx->device));
+    NUPGCM_CUDA(ctx, cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault));
+    return NUPGCM_OK;
+}
+
+extern "C" int32_t nupgcm_host_free(nupgcm_ctx *ctx, void *p) {
+    NUPGCM_REQUIRE(nullptr, ctx, "ctx is NULL");
+    if (p) NUPGCM_CUDA(ctx, cudaFreeHost(p));
+    return NUPGCM_OK;
+}
+
 extern "C" int32_t nupgcm_synchronize(nupgcm_ctx *ctx) {
     NUPGCM_REQUIRE(nullptr, ctx, "ctx is NULL");
     NUPGCM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

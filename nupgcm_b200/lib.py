@@ -41,6 +41,8 @@ SIGNATURES = {
     "nupgcm_destroy": [_P],
     "nupgcm_synchronize": [_P],
     "nupgcm_set_grid": [_P, c_int32],
+    "nupgcm_host_alloc": [_P, c_int64, POINTER(c_void_p)],
+    "nupgcm_host_free": [_P, c_void_p],
     "nupgcm_comm_create": [_P, c_int32, c_int32, c_int64, POINTER(_P)],
     "nupgcm_comm_destroy": [_P],
     "nupgcm_comm_ipc_handle": [_P, c_void_p],
@@ -153,14 +155,25 @@ class Context:
         _check(self.lib.nupgcm_create(device, byref(h)))
         self.h = h
         self.device = device
+        self._pinned = []
 
     def close(self):
         if self.h:
+            for p in self._pinned:
+                self.lib.nupgcm_host_free(self.h, p)
+            self._pinned = []
             self.lib.nupgcm_destroy(self.h)
             self.h = None
 
     def synchronize(self):
         _check(self.lib.nupgcm_synchronize(self.h), self.h)
+
+    def pinned_array(self, n: int) -> np.ndarray:
+        """float64 array of ``n`` entries in page-locked host memory (freed with the context)."""
+        p = c_void_p()
+        _check(self.lib.nupgcm_host_alloc(self.h, max(int(n), 1) * 8, byref(p)), self.h)
+        self._pinned.append(p)
+        return np.ctypeslib.as_array((c_double * max(int(n), 1)).from_address(p.value))[:int(n)]
 
     def set_grid(self, grid: int):
         """Restrict the persistent solver kernels to ``grid`` CTAs (several contexts on one device)."""

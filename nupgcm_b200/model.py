@@ -148,7 +148,9 @@ def _sync_buffers(model: Model) -> dict:
         N = d.nu + d.np
         sy = {"p_b": ctx.index(d.p_b), "inv_p_b": ctx.index(d.inv_p_b),
               "p_inversion": ctx.index(d.p_inversion), "inv_p_inversion": ctx.index(d.inv_p_inversion),
-              "stage_b": ctx.vector(d.nb), "stage_x": ctx.vector(N), "host_x": np.empty(N)}
+              "stage_b": ctx.vector(d.nb), "stage_x": ctx.vector(N),
+              # page-locked host copies: the per-step transfers are plain DMA
+              "host_x": ctx.pinned_array(N), "host_b": ctx.pinned_array(d.nb)}
         model._sync = sy
     return sy
 
@@ -181,7 +183,8 @@ def run_(model: Model, n_info=10, n_save=float("inf"), n_steps=None, sync_state=
             # host -> device of the state the step starts from: one copy per field in Gridap order,
             # permuted to solver order by a gather kernel (x[p], model.jl:274; inversion.jl:37-39)
             sy = _sync_buffers(model)
-            sy["stage_b"].upload(host_state["b"])
+            sy["host_b"][:] = host_state["b"]
+            sy["stage_b"].upload(sy["host_b"])
             xb.gather_from(sy["stage_b"], sy["p_b"])
             sy["host_x"][:nu] = host_state["u"]
             sy["host_x"][nu:] = host_state["p"]
@@ -208,10 +211,10 @@ def run_(model: Model, n_info=10, n_save=float("inf"), n_steps=None, sync_state=
             # device, one copy per field
             sy = _sync_buffers(model)
             sy["stage_x"].gather_from(xu, sy["inv_p_inversion"])
-            x = sy["stage_x"].download()
-            host_state["u"], host_state["p"] = x[:nu], x[nu:]
+            x = sy["stage_x"].download(out=sy["host_x"])
+            host_state["u"], host_state["p"] = x[:nu].copy(), x[nu:].copy()
             sy["stage_b"].gather_from(xb, sy["inv_p_b"])
-            host_state["b"] = sy["stage_b"].download()
+            host_state["b"] = sy["stage_b"].download(out=sy["host_b"]).copy()
         rec = {"i": i, "t": ts.t, "cg_iters": model.evolution.solver.stats.niter,
                "gmres_iters": model.inversion.solver.stats.niter,
                "cg_ms": model.evolution.solver.stats.timer * 1e3,
