@@ -395,11 +395,14 @@ __device__ __forceinline__ bool comm_mr(CommMailbox *mb, const KrylovArgs &a, LL
             const int npw = (grid + 31) >> 5;
             double total = 0.0;
             for (int g = 0; g < npw; ++g) total += mb->part[0][g];
-            // Publishing reductions: the rows pushed to the peers were fenced at system scope by the
-            // threads that stored them (GridReduce), and this reducer has acquired every CTA's slot, so
-            // they are performed at the peers before this flag is even issued — a relaxed store is
-            // enough (the NCCL pattern: writers fence, then the flag).  xfence = 1 uses formal
-            // release.sys / acquire.sys instead, at +1.6 us per hop (tools/xrank_latency.py).
+            // Publishing reductions.  Rows of this rank's own CTAs follow a gpu-scope release/acquire
+            // chain (value 0: slot -> this reducer -> its word in the own arena -> every CTA).  Halo rows
+            // of the Krylov vectors need nothing: they travel as self-validating flagged words.  The
+            // plain remote stores of the closing all-gather were fenced at system scope by their CTA
+            // (GridReduce::fence_remote) before this reducer could acquire that CTA's slot, so they are
+            // performed at the peers before this flag is even issued — a relaxed store is enough (the
+            // NCCL pattern: writers fence, then the flag).  xfence = 1 uses formal release.sys /
+            // acquire.sys flags instead, at +1.6 us per hop (tools/xrank_latency.py).
             LLSlot *dst = xr_slot(a.arena[ct % P], xbank, bid, ct / P, a.rank);
             if (PUBLISH && bid == 0 && a.xfence) ll_store<true, true>(dst, total, xgen);
             else if (PUBLISH && bid == 0 && ct % P == a.rank) ll_store<true, false>(dst, total, xgen);   // rows of this rank's own CTAs
