@@ -231,6 +231,14 @@ int32_t nupgcm_gmres_solve_prec(const nupgcm_csr *A, nupgcm_blockprec *M, const 
                                 int32_t memory, double *resid_hist, int64_t hist_cap,
                                 nupgcm_solve_stats *stats);
 
+/* diagnostics, host only (no device needed): y = A x computed by walking the streaming-SpMV tables
+ * (tiles, footprints, per-warp entry streams) that nupgcm_csr_prepare builds for `grid` CTAs, exactly as
+ * the persistent kernels walk them; 0-based CSR as given, T = 4 or 8 lanes per row, fmax = footprint cap.
+ * Fails if any row is not produced exactly once.  Used by the CPU tests of the table builder. */
+int32_t nupgcm_diag_stream_spmv_host(int64_t n, const int64_t *rowptr, const int64_t *colidx,
+                                     const double *vals, const double *x, int32_t grid, int32_t T,
+                                     int32_t fmax, double *y, int64_t *n_tiles, int64_t *n_entries);
+
 /* diagnostics: average latency (µs) of the grid-wide reduction the persistent solvers use.
  * mode 0: flagged-slot exchange only; 1: + block reduction; 2: + release/acquire fences. */
 int32_t nupgcm_diag_reduce_latency(nupgcm_ctx *ctx, int32_t mode, int32_t reps, int32_t grid,

@@ -9,6 +9,10 @@
 
 #include "../../include/nupgcm_b200.h"
 
+struct NupgcmTileDesc;
+struct NupgcmWarpDesc;
+struct NupgcmTileWarp;
+
 // -------------------------------------------------------------------------------------------
 // host-side handle layouts
 // -------------------------------------------------------------------------------------------
@@ -106,10 +110,21 @@ struct nupgcm_csr {
     double *d_pvals;               // [nnz] reordered values, refreshed when vals_version moves
     int32_t *h_prow, *h_pcol;
     long long vals_version, pvals_version;
-    // streaming form: per-CTA chunk tables (built by nupgcm_csr_prepare for the current grid)
-    int32_t *d_chunk_ptr;          // [grid+1]
-    int32_t *d_chunk_rowend;       // per chunk: first row starting at or after the chunk's end
-    int str_max_rows, str_max_chunks;
+    // streaming form (matrix slice larger than shared memory): tiled, per-warp entry streams built by
+    // nupgcm_csr_prepare for the current grid — see "streaming SpMV tables" below
+    double *d_svals;               // [stream entries] values in stream order (refreshed with pvals)
+    uint16_t *d_scols;             // [stream entries] column = position in the tile's footprint
+    int32_t *d_ssrc;               // [stream entries] position in d_pvals, -1 for alignment padding
+    int64_t stream_entries;
+    NupgcmTileDesc *d_tiles;       // tiles of this rank's CTAs
+    int32_t *d_tile_ptr;           // [grid_per_rank+1]
+    NupgcmWarpDesc *d_wdesc;       // [grid_per_rank][kMainWarps]
+    NupgcmTileWarp *d_tw;          // [tiles][kMainWarps]
+    uint32_t *d_srp;               // row tables: entry offsets relative to the warp's stream start
+    int32_t *d_srow;               //             internal row ids
+    int32_t *d_sfoot;              // footprints of all tiles (internal column ids, sorted per tile)
+    int str_T, str_fmax, str_max_rows;   // lanes per row, footprint cap and largest row block of the tables (0: none)
+    long long svals_version;
     // sharded solves: the communicator, and for every peer the range of THIS rank's rows that the
     // peer's SpMV gathers (bounding range of the peer's column footprint inside this rank's block)
     nupgcm_comm *comm;
@@ -154,7 +169,23 @@ struct nupgcm_mesh {
     int64_t nu_nnz;
 };
 
-static const int kStreamChunk = 4096;  // matrix entries per TMA pipeline stage of the streaming SpMV
+// ---- streaming SpMV tables ------------------------------------------------------------------
+// A CTA whose matrix slice does not fit in shared memory walks its rows tile by tile.  A tile is a
+// run of consecutive rows whose distinct columns (its "footprint") number at most str_fmax: the
+// footprint entries of the multiplied vector are staged in shared memory once per tile and every
+// matrix entry carries a 16-bit position in that list instead of a 32-bit column.  Inside a tile the
+// rows are sorted by length and dealt to the kMainWarps solver warps in units of 32/T rows (rows
+// longer than kLongRow singly), so every warp owns ONE contiguous entry stream per CTA — values and
+// 16-bit columns, no padding — which it pulls through a private shared-memory ring with TMA bulk
+// copies of kPieceEntries entries.
+static const int kMainWarps = 11;      // solver warps of the persistent kernels (krylov.cu)
+static const int kPieceEntries = 256;  // entries per TMA piece: 2 KB of values + 512 B of columns
+static const int kRingPieces = 4;      // pieces per warp ring (power of two)
+static const int kLongRow = 96;        // rows longer than this are processed by a whole warp
+
+struct NupgcmTileDesc { int32_t row0, nrows, foot_off, foot_len; };
+struct NupgcmWarpDesc { int32_t estart, elen, rtab, pad; };     // stream start (multiple of 8) / length, row table offset
+struct NupgcmTileWarp { int32_t rbeg, nlong, nrows, pad; };     // rows of one warp in one tile (relative to rtab)
 static const int kPartialSlots = 24;   // >= memory+2 of GMRES
 static const int kMaxMemory = 20;
 

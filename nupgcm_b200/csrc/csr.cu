@@ -7,6 +7,7 @@
 // evolution matrix: ~23 per row -> T = 4).  Summation order inside a row is fixed (lane-strided
 // partial sums, then an xor-shuffle tree), so results are run-to-run reproducible.
 #include <algorithm>
+#include <cmath>
 #include <vector>
 
 #include "common.cuh"
@@ -195,6 +196,156 @@ static void permute_structure(int64_t n, const int32_t *rowptr, const int32_t *c
     }
 }
 
+
+// ---- streaming SpMV tables (common.cuh) ------------------------------------------------------
+// Built for the CTAs [cta0, cta0 + ncta) of the partition (this rank's CTAs).  Returns false when a
+// single row touches more than fmax distinct columns (then the solvers fall back to direct loads).
+struct StreamTables {
+    std::vector<NupgcmTileDesc> tiles;
+    std::vector<int32_t> tile_ptr;
+    std::vector<NupgcmWarpDesc> wdesc;
+    std::vector<NupgcmTileWarp> tw;
+    std::vector<uint32_t> srp;
+    std::vector<int32_t> srow, foot, ssrc;
+    std::vector<uint16_t> scols;
+};
+
+static bool build_stream_tables(const int32_t *rowptr, const int32_t *col, int64_t n_cols,
+                                const std::vector<int32_t> &part, int cta0, int ncta, int T, int fmax,
+                                StreamTables &st) {
+    const int W = kMainWarps, R = 32 / T;
+    st.tile_ptr.assign(ncta + 1, 0);
+    st.wdesc.assign((size_t)ncta * W, NupgcmWarpDesc{0, 0, 0, 0});
+    std::vector<int32_t> mark(n_cols, -1), loc_of(n_cols, 0), tile_cols, order;
+    std::vector<std::vector<int32_t>> wrows(W);                 // per warp: rows of the CTA in stream order
+    std::vector<std::vector<NupgcmTileWarp>> wtw(W);            // per warp: its slice of every tile
+    int32_t stamp = 0;
+    for (int b = 0; b < ncta; ++b) {
+        const int32_t ra = part[cta0 + b], rb = part[cta0 + b + 1];
+        for (int w = 0; w < W; ++w) { wrows[w].clear(); wtw[w].clear(); }
+        struct LocalTile { int32_t row0, nrows, foot_off, foot_len; };
+        std::vector<LocalTile> ltiles;
+        std::vector<std::vector<uint16_t>> wcols(W);
+        std::vector<std::vector<int32_t>> wsrc(W);
+        std::vector<std::vector<uint32_t>> wrp(W);
+        for (int32_t start = ra; start < rb;) {
+            // grow the tile row by row while its footprint stays within fmax
+            ++stamp;
+            tile_cols.clear();
+            int32_t r = start;
+            for (; r < rb; ++r) {
+                int fresh = 0;
+                for (int32_t k = rowptr[r]; k < rowptr[r + 1]; ++k)
+                    if (mark[col[k]] != stamp) ++fresh;
+                // duplicates inside the row were counted once each: recount exactly while marking
+                if ((int)tile_cols.size() + fresh > fmax) {
+                    // exact test (a row may list a column twice)
+                    int exact = 0;
+                    for (int32_t k = rowptr[r]; k < rowptr[r + 1]; ++k)
+                        if (mark[col[k]] != stamp) { mark[col[k]] = stamp; ++exact; tile_cols.push_back(col[k]); }
+                    if ((int)tile_cols.size() > fmax) {
+                        for (int e = 0; e < exact; ++e) { mark[tile_cols.back()] = -1; tile_cols.pop_back(); }
+                        break;
+                    }
+                    continue;
+                }
+                for (int32_t k = rowptr[r]; k < rowptr[r + 1]; ++k)
+                    if (mark[col[k]] != stamp) { mark[col[k]] = stamp; tile_cols.push_back(col[k]); }
+            }
+            if (r == start) return false;                       // one row alone exceeds the footprint cap
+            std::sort(tile_cols.begin(), tile_cols.end());
+            for (size_t i = 0; i < tile_cols.size(); ++i) loc_of[tile_cols[i]] = (int32_t)i;
+            while (st.foot.size() % 4) st.foot.push_back(0);
+            ltiles.push_back({start, r - start, (int32_t)st.foot.size(), (int32_t)tile_cols.size()});
+            st.foot.insert(st.foot.end(), tile_cols.begin(), tile_cols.end());
+            // rows by decreasing length (ties by row id), dealt to the warps in units
+            order.resize(r - start);
+            for (int32_t i = 0; i < r - start; ++i) order[i] = start + i;
+            std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
+                return rowptr[x + 1] - rowptr[x] > rowptr[y + 1] - rowptr[y];
+            });
+            std::vector<NupgcmTileWarp> cur(W);
+            for (int w = 0; w < W; ++w) cur[w] = NupgcmTileWarp{(int32_t)wrows[w].size(), 0, 0, 0};
+            size_t i = 0;
+            int unit = 0;
+            while (i < order.size()) {
+                const int w = unit % W;
+                const bool is_long = rowptr[order[i] + 1] - rowptr[order[i]] > kLongRow;
+                const size_t take = is_long ? 1 : std::min<size_t>(R, order.size() - i);
+                for (size_t j = 0; j < take; ++j) {
+                    const int32_t row = order[i + j];
+                    wrp[w].push_back((uint32_t)wcols[w].size());
+                    wrows[w].push_back(row);
+                    for (int32_t k = rowptr[row]; k < rowptr[row + 1]; ++k) {
+                        wcols[w].push_back((uint16_t)loc_of[col[k]]);
+                        wsrc[w].push_back(k);
+                    }
+                }
+                if (is_long) cur[w].nlong++;
+                cur[w].nrows += (int32_t)take;
+                i += take;
+                ++unit;
+            }
+            for (int w = 0; w < W; ++w) wtw[w].push_back(cur[w]);
+            start = r;
+        }
+        st.tile_ptr[b] = (int32_t)st.tiles.size();
+        for (size_t t = 0; t < ltiles.size(); ++t) {
+            st.tiles.push_back(NupgcmTileDesc{ltiles[t].row0, ltiles[t].nrows, ltiles[t].foot_off, ltiles[t].foot_len});
+            for (int w = 0; w < W; ++w) st.tw.push_back(wtw[w][t]);
+        }
+        for (int w = 0; w < W; ++w) {
+            while (st.scols.size() % 8) { st.scols.push_back(0); st.ssrc.push_back(-1); }   // 16-byte aligned streams
+            NupgcmWarpDesc &d = st.wdesc[(size_t)b * W + w];
+            d.estart = (int32_t)st.scols.size();
+            d.elen = (int32_t)wcols[w].size();
+            d.rtab = (int32_t)st.srp.size();
+            st.scols.insert(st.scols.end(), wcols[w].begin(), wcols[w].end());
+            st.ssrc.insert(st.ssrc.end(), wsrc[w].begin(), wsrc[w].end());
+            st.srp.insert(st.srp.end(), wrp[w].begin(), wrp[w].end());
+            st.srp.push_back((uint32_t)wcols[w].size());
+            st.srow.insert(st.srow.end(), wrows[w].begin(), wrows[w].end());
+            st.srow.push_back(0);                               // keeps srow aligned with srp
+        }
+    }
+    st.tile_ptr[ncta] = (int32_t)st.tiles.size();
+    // whole pieces are always copied: pad the tail
+    for (int i = 0; i < kPieceEntries + 8; ++i) { st.scols.push_back(0); st.ssrc.push_back(-1); }
+    return true;
+}
+
+__global__ void k_scatter_stream(double *svals, const double *pvals, const int32_t *ssrc, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t s = ssrc[i];
+        svals[i] = s >= 0 ? pvals[s] : 0.0;
+    }
+}
+
+static void free_stream_tables(nupgcm_csr *A) {
+    cudaFree(A->d_svals); A->d_svals = nullptr;
+    cudaFree(A->d_scols); A->d_scols = nullptr;
+    cudaFree(A->d_ssrc); A->d_ssrc = nullptr;
+    cudaFree(A->d_tiles); A->d_tiles = nullptr;
+    cudaFree(A->d_tile_ptr); A->d_tile_ptr = nullptr;
+    cudaFree(A->d_wdesc); A->d_wdesc = nullptr;
+    cudaFree(A->d_tw); A->d_tw = nullptr;
+    cudaFree(A->d_srp); A->d_srp = nullptr;
+    cudaFree(A->d_srow); A->d_srow = nullptr;
+    cudaFree(A->d_sfoot); A->d_sfoot = nullptr;
+    A->stream_entries = 0;
+    A->str_T = A->str_fmax = A->str_max_rows = 0;
+    A->svals_version = -1;
+}
+
+template <class V>
+static cudaError_t upload_vec(void **dst, const std::vector<V> &v, size_t extra = 8) {
+    cudaError_t e = cudaMalloc(dst, (v.size() + extra) * sizeof(V));
+    if (e != cudaSuccess) return e;
+    e = cudaMemset(*dst, 0, (v.size() + extra) * sizeof(V));
+    if (e != cudaSuccess || v.empty()) return e;
+    return cudaMemcpy(*dst, v.data(), v.size() * sizeof(V), cudaMemcpyHostToDevice);
+}
+
 // Internal (reordered) copy of the structure: built once per matrix.
 static int32_t build_internal_order(nupgcm_csr *A) {
     nupgcm_ctx *ctx = A->ctx;
@@ -221,8 +372,8 @@ static int32_t build_internal_order(nupgcm_csr *A) {
     NUPGCM_CUDA(ctx, cudaMalloc(&A->d_prow, (size_t)(n + 1 + 8) * sizeof(int32_t)));
     NUPGCM_CUDA(ctx, cudaMemset(A->d_prow, 0, (size_t)(n + 1 + 8) * sizeof(int32_t)));
     NUPGCM_CUDA(ctx, cudaMemcpy(A->d_prow, prow.data(), (size_t)(n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
-    // values / columns are padded to whole streaming chunks (+1) so that bulk copies never run out
-    const size_t nzpad = ((nz + kStreamChunk - 1) / kStreamChunk + 1) * (size_t)kStreamChunk;
+    // a little padding lets the persistent kernels bulk-copy 16-byte aligned windows
+    const size_t nzpad = nz + 64;
     NUPGCM_CUDA(ctx, cudaMalloc(&A->d_pcol, nzpad * sizeof(int32_t)));
     NUPGCM_CUDA(ctx, cudaMemset(A->d_pcol, 0, nzpad * sizeof(int32_t)));
     NUPGCM_CUDA(ctx, cudaMalloc(&A->d_psrc, nz * sizeof(int32_t)));
@@ -255,8 +406,19 @@ int32_t nupgcm_csr_prepare(nupgcm_csr *A, int grid_per_rank) {
         NUPGCM_CUDA(ctx, cudaGetLastError());
         A->pvals_version = A->vals_version;
     }
-    if (A->prepared_grid == grid && A->prepared_ranks == nranks) return NUPGCM_OK;
+    auto refresh_stream_values = [&]() -> int32_t {
+        if (A->d_svals && A->svals_version != A->pvals_version) {
+            int g = (int)std::min<int64_t>((A->stream_entries + 255) / 256, (int64_t)ctx->sm_count * 8);
+            k_scatter_stream<<<g, 256, 0, ctx->stream>>>(A->d_svals, A->d_pvals, A->d_ssrc, A->stream_entries);
+            ctx->launches++;
+            NUPGCM_CUDA(ctx, cudaGetLastError());
+            A->svals_version = A->pvals_version;
+        }
+        return NUPGCM_OK;
+    };
+    if (A->prepared_grid == grid && A->prepared_ranks == nranks) return refresh_stream_values();
     NUPGCM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    free_stream_tables(A);
     cudaFree(A->d_part); A->d_part = nullptr;
     cudaFree(A->d_loc); A->d_loc = nullptr;
     cudaFree(A->d_foot_ptr); A->d_foot_ptr = nullptr;
@@ -267,37 +429,6 @@ int32_t nupgcm_csr_prepare(nupgcm_csr *A, int grid_per_rank) {
     build_partition(h_rowptr, n_rows, grid, part);
     NUPGCM_CUDA(ctx, cudaMalloc(&A->d_part, part.size() * sizeof(int32_t)));
     NUPGCM_CUDA(ctx, cudaMemcpy(A->d_part, part.data(), part.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    {   // streaming chunk tables
-        cudaFree(A->d_chunk_ptr); A->d_chunk_ptr = nullptr;
-        cudaFree(A->d_chunk_rowend); A->d_chunk_rowend = nullptr;
-        std::vector<int32_t> cptr(grid + 1, 0), rowend;
-        int max_rows = 0, max_chunks = 0;
-        for (int p = 0; p < grid; ++p) {
-            const int32_t ra = part[p], rb = part[p + 1];
-            const int64_t k0 = h_rowptr[ra], k1 = h_rowptr[rb];
-            const int64_t kbase = (k0 / kStreamChunk) * kStreamChunk;
-            const int nch = k1 > k0 ? (int)((k1 - kbase + kStreamChunk - 1) / kStreamChunk) : 0;
-            while (rowend.size() % 4) rowend.push_back(0);      // 16-byte aligned bulk copies
-            cptr[p] = (int32_t)rowend.size();
-            int32_t row = ra;
-            for (int ci = 0; ci < nch; ++ci) {
-                const int64_t c1 = kbase + (int64_t)(ci + 1) * kStreamChunk;
-                while (row < rb && h_rowptr[row] < c1) ++row;
-                rowend.push_back(row);
-            }
-            max_rows = std::max(max_rows, (int)(rb - ra));
-            max_chunks = std::max(max_chunks, nch);
-        }
-        cptr[grid] = (int32_t)rowend.size();
-        NUPGCM_CUDA(ctx, cudaMalloc(&A->d_chunk_ptr, cptr.size() * sizeof(int32_t)));
-        NUPGCM_CUDA(ctx, cudaMemcpy(A->d_chunk_ptr, cptr.data(), cptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-        NUPGCM_CUDA(ctx, cudaMalloc(&A->d_chunk_rowend, (rowend.size() + 8) * sizeof(int32_t)));
-        NUPGCM_CUDA(ctx, cudaMemset(A->d_chunk_rowend, 0, (rowend.size() + 8) * sizeof(int32_t)));
-        if (!rowend.empty())
-            NUPGCM_CUDA(ctx, cudaMemcpy(A->d_chunk_rowend, rowend.data(), rowend.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-        A->str_max_rows = max_rows;
-        A->str_max_chunks = max_chunks;
-    }
     // SM-resident tables: only worth building when a CTA's slice can possibly fit on chip
     const int64_t slice_bytes = kept * 10 / (grid > 0 ? grid : 1);
     if (A->n_rows == A->n_cols && kept > 0 && slice_bytes < 230 * 1024) {
@@ -340,6 +471,43 @@ int32_t nupgcm_csr_prepare(nupgcm_csr *A, int grid_per_rank) {
             A->res_max_rows = max_rows;
         }
     }
+    // streaming tables: whenever the SM-resident form cannot hold the slice (or is switched off)
+    {
+        const char *env = getenv("NUPGCM_RESIDENT");
+        const bool resident_off = env && atoi(env) == 0;
+        const long long res_bytes = 10LL * A->res_max_nnz + 12LL * A->res_max_foot + 4LL * A->res_max_rows + 256;
+        const bool resident_fits = A->res_max_nnz > 0 && res_bytes <= 215 * 1024;
+        if (A->n_rows == A->n_cols && kept > 0 && (resident_off || !resident_fits)) {
+            const int me = nranks > 1 ? A->comm->rank : 0;
+            int fmax = 4096;
+            if (const char *ef = getenv("NUPGCM_STREAM_FMAX")) {
+                const int v = atoi(ef);
+                if (v >= 256 && v <= 12288) fmax = v & ~3;
+            }
+            const int T = (double)kept / (double)n_rows >= 20.0 ? 8 : 4;
+            StreamTables st;
+            if (build_stream_tables(A->h_prow, A->h_pcol, A->n_cols, part, me * grid_per_rank, grid_per_rank, T, fmax, st)) {
+                A->stream_entries = (int64_t)st.scols.size();
+                NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_scols, st.scols));
+                NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_ssrc, st.ssrc));
+                NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_tiles, st.tiles));
+                NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_tile_ptr, st.tile_ptr));
+                NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_wdesc, st.wdesc));
+                NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_tw, st.tw));
+                NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_srp, st.srp));
+                NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_srow, st.srow));
+                NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_sfoot, st.foot));
+                NUPGCM_CUDA(ctx, cudaMalloc(&A->d_svals, (size_t)(A->stream_entries + 8) * sizeof(double)));
+                A->str_T = T;
+                A->str_fmax = fmax;
+                int max_rows = 0;
+                for (int b = 0; b < grid_per_rank; ++b)
+                    max_rows = std::max(max_rows, (int)(part[me * grid_per_rank + b + 1] - part[me * grid_per_rank + b]));
+                A->str_max_rows = max_rows;
+                A->svals_version = -1;
+            }
+        }
+    }
     // halo push ranges: for every peer, the bounding range of this rank's rows it gathers
     for (int p = 0; p < kMaxRanks; ++p) A->push_lo[p] = A->push_hi[p] = 0;
     if (nranks > 1) {
@@ -380,7 +548,7 @@ int32_t nupgcm_csr_prepare(nupgcm_csr *A, int grid_per_rank) {
     A->prepared_grid = grid;
     A->prepared_ranks = nranks;
     NUPGCM_CUDA(ctx, cudaDeviceSynchronize());   // set-up copies ran on the default stream
-    return NUPGCM_OK;
+    return refresh_stream_values();
 }
 
 extern "C" int32_t nupgcm_csr_shard(nupgcm_csr *A, nupgcm_comm *comm) {
@@ -428,6 +596,73 @@ extern "C" int32_t nupgcm_csr_shard_info(nupgcm_csr *A, int32_t rank, int64_t *r
 }
 
 // ---- C ABI --------------------------------------------------------------------------------
+// Host-only: y = A x computed by walking the streaming tables exactly as the persistent kernels do
+// (tiles, footprint staging, per-warp streams, long rows / units of 32/T rows), for `grid` CTAs on
+// the structure as given (no reordering).  Lets the CPU tests validate the table builder without a
+// device.  Also returns the number of tiles and of stream entries (padding included).
+extern "C" int32_t nupgcm_diag_stream_spmv_host(int64_t n, const int64_t *rowptr, const int64_t *colidx,
+                                                const double *vals, const double *x, int32_t grid,
+                                                int32_t T, int32_t fmax, double *y, int64_t *n_tiles,
+                                                int64_t *n_entries) {
+    if (n < 1 || !rowptr || !colidx || !vals || !x || !y || grid < 1 || (T != 4 && T != 8) || fmax < 4 || fmax > 65536)
+        return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "invalid argument: %s", "diag_stream_spmv_host");
+    const int64_t nnz = rowptr[n];
+    if (nnz < 0 || nnz >= INT32_MAX || n >= INT32_MAX)
+        return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "invalid argument: %s", "diag_stream_spmv_host: size");
+    std::vector<int32_t> rp(n + 1), col(nnz > 0 ? nnz : 1), part;
+    for (int64_t i = 0; i <= n; ++i) rp[i] = (int32_t)rowptr[i];
+    for (int64_t k = 0; k < nnz; ++k) col[k] = (int32_t)colidx[k];
+    build_partition(rp, n, grid, part);
+    StreamTables st;
+    if (!build_stream_tables(rp.data(), col.data(), n, part, 0, grid, T, fmax, st))
+        return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "invalid argument: %s", "a row exceeds the footprint cap");
+    std::vector<double> sv(st.scols.size());
+    for (size_t i = 0; i < sv.size(); ++i) sv[i] = st.ssrc[i] >= 0 ? vals[st.ssrc[i]] : 0.0;
+    for (int64_t i = 0; i < n; ++i) y[i] = std::nan("");         // every row must be written exactly once
+    std::vector<double> xs(fmax);
+    std::vector<int> written(n, 0);
+    const int W = kMainWarps, R = 32 / T;
+    for (int b = 0; b < grid; ++b) {
+        for (int t = st.tile_ptr[b]; t < st.tile_ptr[b + 1]; ++t) {
+            const NupgcmTileDesc td = st.tiles[t];
+            if (td.foot_len > fmax) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "tile footprint exceeds the cap");
+            for (int i = 0; i < td.foot_len; ++i) xs[i] = x[st.foot[td.foot_off + i]];
+            for (int w = 0; w < W; ++w) {
+                const NupgcmWarpDesc wd = st.wdesc[(size_t)b * W + w];
+                const NupgcmTileWarp tw = st.tw[(size_t)t * W + w];
+                const uint32_t *srp = st.srp.data() + wd.rtab;
+                const int32_t *srow = st.srow.data() + wd.rtab;
+                auto row_sum = [&](int ri) {
+                    double acc = 0.0;
+                    for (uint32_t k = srp[ri]; k < srp[ri + 1]; ++k) {
+                        if ((int)k >= wd.elen) return std::nan("");
+                        acc += sv[(size_t)wd.estart + k] * xs[st.scols[(size_t)wd.estart + k]];
+                    }
+                    return acc;
+                };
+                int ri = tw.rbeg;
+                for (; ri < tw.rbeg + tw.nlong; ++ri) {
+                    if ((int)(srp[ri + 1] - srp[ri]) <= kLongRow) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "short row among the long ones");
+                    y[srow[ri]] = row_sum(ri); written[srow[ri]]++;
+                }
+                for (; ri < tw.rbeg + tw.nrows; ri += R)
+                    for (int g = 0; g < R && ri + g < tw.rbeg + tw.nrows; ++g) {
+                        const int r = ri + g;
+                        if ((int)(srp[r + 1] - srp[r]) > kLongRow) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "long row among the short ones");
+                        if (srow[r] < td.row0 || srow[r] >= td.row0 + td.nrows) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "row outside its tile");
+                        y[srow[r]] = row_sum(r); written[srow[r]]++;
+                    }
+                if (wd.estart % 8) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "misaligned stream");
+            }
+        }
+    }
+    for (int64_t i = 0; i < n; ++i)
+        if (written[i] != 1) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "a row was not written exactly once");
+    if (n_tiles) *n_tiles = (int64_t)st.tiles.size();
+    if (n_entries) *n_entries = (int64_t)st.scols.size();
+    return NUPGCM_OK;
+}
+
 
 // Host-only utility: the reordering the solvers apply internally, for callers that want it too
 // (the reference computes its per-field orderings with CuthillMcKee.symrcm, src/dofs.jl:98-100).
@@ -579,8 +814,7 @@ extern "C" int32_t nupgcm_csr_destroy(nupgcm_csr *A) {
     cudaFree(A->d_pcol);
     cudaFree(A->d_psrc);
     cudaFree(A->d_pvals);
-    cudaFree(A->d_chunk_ptr);
-    cudaFree(A->d_chunk_rowend);
+    free_stream_tables(A);
     cudaFree(A->d_halo_ptr);
     cudaFree(A->d_halo_idx);
     free(A->h_rowptr);

@@ -40,12 +40,16 @@ static const int kThreads = 512;       // 16 warps: up to 128 registers per thre
 struct ResidentLayout {       // byte offsets into dynamic shared memory (all multiples of 16)
     int vals, cols, xs, foot, rp, bar, vec, total;
     int vec_rows;             // row capacity of one vector slice (0: vectors stay in global memory)
-    // streaming form (matrix does not fit on chip): kStreamStages buffers of kStreamChunk entries
-    int st_vals, st_cols, st_info, st_misc;
-    int streaming;            // 1: SpmvEngine<T,false> uses the TMA pipeline described by st_*
+    // streaming form (matrix does not fit on chip, common.cuh "streaming SpMV tables"): per-warp rings of
+    // kRingPieces x kPieceEntries entries, their mbarriers, and two footprint buffers of st_fmax doubles
+    int st_ring_v, st_ring_c, st_bars, st_xs, st_fmax;
+    int streaming;            // 1: SpmvEngine<T,false> runs the tiled TMA streams described by st_*
 };
 
-static const int kStreamStages = 3;        // kStreamChunk (common.cuh) entries per stage: 32 KB values + 16 KB columns
+static const int kRingEntries = kPieceEntries * kRingPieces;
+static const uint32_t kPieceBytes = kPieceEntries * (sizeof(double) + sizeof(uint16_t));
+static_assert((kRingPieces & (kRingPieces - 1)) == 0 && (kPieceEntries & (kPieceEntries - 1)) == 0, "ring sizes must be powers of two");
+static_assert((32 / 4) * kLongRow + kPieceEntries <= kRingEntries, "a unit of rows must fit in the ring next to one piece");
 
 struct KrylovArgs {
     const int32_t *rowptr;
@@ -56,8 +60,16 @@ struct KrylovArgs {
     const int32_t *foot_ptr; // [grid][2]: start (multiple of 4) and length of each CTA's footprint
     const int32_t *foot;
     const int32_t *perm;     // [n] internal row -> caller row (vectors cross the ABI in caller order)
-    const int32_t *chunk_ptr;    // streaming form: [grid+1] offsets into chunk_rowend
-    const int32_t *chunk_rowend; // per chunk: first row that starts at or after the chunk's end
+    // streaming form (common.cuh "streaming SpMV tables"; indexed by blockIdx.x: this rank's CTAs only)
+    const double *svals;
+    const uint16_t *scols;
+    const NupgcmTileDesc *tiles;
+    const int32_t *tile_ptr;
+    const NupgcmWarpDesc *wdesc;
+    const NupgcmTileWarp *tw;
+    const uint32_t *srp;
+    const int32_t *srow;
+    const int32_t *sfoot;
     ResidentLayout lay;
     int n;
     const double *dinv;      // diagonal preconditioner or NULL
@@ -72,7 +84,6 @@ struct KrylovArgs {
     int poll_depth;          // replicas of the reduction slots (GridReduce)
     int xmode;               // sharded solves: 1 = gather / multi-rank broadcast reductions, 0 = two-level
     int xfence;              // 1: release.sys / acquire.sys on the inter-rank flags of publishing reductions
-    int debug_skip;          // timing experiments only (NUPGCM_DEBUG_SKIP): 1 = no footprint staging, 2 = no row loop
     unsigned long long *trace;   // debug: arrival/completion stamps of a window of reductions
     unsigned long long *barrier;
     double *partials;        // LLSlot [2][kPartialSlots][grid]
@@ -98,6 +109,50 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+
+// ---- mbarrier / TMA bulk-copy primitives ---------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Waits for the phase with the given parity.  Watchdog: a copy or partner that never arrives raises
+// the abort word (if given) after kWaitTimeoutNs and the wait returns false instead of hanging the GPU.
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, unsigned long long *abort_word = nullptr) {
+    uint32_t done;
+    unsigned spins = 0;
+    unsigned long long t0 = 0;
+    for (;;) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) return true;
+        if ((++spins & 1023u) == 0) {
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > kWaitTimeoutNs) {
+                if (abort_word) atomicExch(abort_word, 1ULL);
+                return false;
+            }
+        }
+    }
+}
+// 1-D TMA bulk copy global -> shared; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 
 // ---- grid-wide reductions ---------------------------------------------------------------------
 // All-to-all exchange of per-CTA partial sums without atomics and without a separate barrier
@@ -161,7 +216,7 @@ static const int kMaxV = 12;       // values one polling lane keeps in flight (l
 // earlier single-role version spilled 0.6-2 KB per thread, and every acquire (which invalidates
 // L1) turned the spill reloads into L2 round trips.  Main and comm warps meet at two named
 // barriers (request / response); main warps synchronise among themselves on a third.
-static const int kMainWarps = 11, kCommWarps = 5;
+static const int kCommWarps = 5;            // kMainWarps = 11 (common.cuh)
 static const int kMainThreads = 32 * kMainWarps, kCommThreads = 32 * kCommWarps;
 static_assert(kMainThreads + kCommThreads == kThreads, "role split must cover the CTA");
 #define NUPGCM_BAR_MAIN 1
@@ -177,8 +232,11 @@ __device__ __forceinline__ void named_arrive(int id, int nthreads) {
 }
 __device__ __forceinline__ void main_sync() { named_sync(NUPGCM_BAR_MAIN, kMainThreads); }
 
+static const int kReqExit = -1, kReqGather = -2;
 struct CommMailbox {
-    int count;                       // > 0: values to reduce; 0: barrier only; < 0: exit
+    int count;                       // > 0: values to reduce; 0: barrier only; kReqExit; kReqGather: stage the
+                                     // footprints of `xin` for the streaming SpMV (no response)
+    const double *xin;
     int from_warps;                  // 1: the single value is the sum of wpart[0..kMainWarps)
     int publish;                     // release/acquire: also publishes the CTA's global rows
     int dead;                        // set by the comm warps when the watchdog fired
@@ -429,18 +487,25 @@ __device__ __forceinline__ bool comm_mr(CommMailbox *mb, const KrylovArgs &a, LL
 
 // Service loop of the comm warps: one request per grid-wide reduction, until the main warps post
 // the exit request.
+__device__ __forceinline__ bool stream_gather_service(const KrylovArgs &a, unsigned char *smem, const double *xin,
+                                                      unsigned &tseq, unsigned long long *abort_word);
+
 template <bool MR = false>
-__device__ __forceinline__ void comm_warp_loop(CommMailbox *mb, const KrylovArgs &a, int nrep) {
+__device__ __forceinline__ void comm_warp_loop(CommMailbox *mb, const KrylovArgs &a, int nrep, unsigned char *smem = nullptr) {
     LLSlot *slots = reinterpret_cast<LLSlot *>(a.partials);
     // sharded solves watch the arena's abort word, which every rank can raise
     unsigned long long *abort_word = MR ? reinterpret_cast<unsigned long long *>(a.arena[a.rank]) : a.barrier + 1;
     const int grid = gridDim.x, gpad = (grid + 7) & ~7;
     const int ct = threadIdx.x - kMainThreads;
-    unsigned gen = 0;
+    unsigned gen = 0, tseq = 0;
     bool dead = false;
     for (;;) {
         named_sync(NUPGCM_BAR_REQ, kThreads);
         const int count = mb->count;
+        if (count == kReqGather) {                               // streaming SpMV: stage the footprints, no response
+            if (!stream_gather_service(a, smem, mb->xin, tseq, abort_word)) mb->dead = 1;
+            continue;
+        }
         if (count < 0) break;
         gen += 1;
         if (!dead) {
@@ -531,7 +596,7 @@ struct GridReduce {
     }
     // Tell the comm warps to leave (call once, at the end, by all main threads).
     __device__ __forceinline__ void finish() {
-        if (threadIdx.x == 0) mb->count = -1;
+        if (threadIdx.x == 0) mb->count = kReqExit;
         named_arrive(NUPGCM_BAR_REQ, kThreads);
     }
 };
@@ -547,32 +612,6 @@ static size_t reduce_scratch_bytes(int grid) { return 2 * exch_bank_slots((grid 
 //    solve; each SpMV first stages the CTA's column footprint of the multiplied vector into
 //    shared memory (one ld.cg sweep) and then runs entirely out of shared memory.
 // f(row, (A xin)[row]) is called by one lane per row.
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-// 1-D TMA bulk copy global -> shared; bytes % 16 == 0, both addresses 16-byte aligned
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 
 // Shared-memory layout of the SM-resident form.  n_vec vector slices of vec_rows rows follow the
 // matrix when they fit as well.
@@ -608,7 +647,9 @@ struct SpmvEngine {
     double *xs;
     int nfoot;
 
-    __device__ __forceinline__ SpmvEngine(const KrylovArgs &args, int r0_, int r1_, unsigned char *smem)
+    __device__ __forceinline__ void finish() {}
+
+    __device__ __forceinline__ SpmvEngine(const KrylovArgs &args, int r0_, int r1_, unsigned char *smem, CommMailbox *)
         : a(args), r0(r0_), r1(r1_) {
         if constexpr (RES) {
             const ResidentLayout &L = a.lay;
@@ -627,25 +668,22 @@ struct SpmvEngine {
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             }
             __syncthreads();
-            // One bulk copy per barrier phase: with several copies outstanding on one mbarrier the
-            // streaming kernels faulted on B200 ("unspecified launch failure", round-1 notes in
-            // DESIGN.md), so each piece is issued, awaited, then the next one.  Once per solve.
-            uint32_t parity = 0;
-            auto copy_piece = [&](void *dst, const void *src, uint32_t bytes) {
-                if (bytes == 0) return;                                  // uniform over the CTA
-                if (threadIdx.x == 0) {
-                    mbar_expect_tx(bar, bytes);
-                    bulk_g2s(dst, src, bytes, bar);
-                }
-                mbar_wait(bar, parity);
-                parity ^= 1u;
-            };
-            for (uint32_t done = 0; done < bv; done += 32768u)
-                copy_piece(smem + L.vals + done, reinterpret_cast<const unsigned char *>(a.vals + ka) + done,
-                           min(bv - done, 32768u));
-            copy_piece(smem + L.cols, a.loc + kc, bc);
-            copy_piece(smem + L.rp, a.rowptr + ra, br);
-            copy_piece(smem + L.foot, a.foot + f0, bf);
+            // All pieces ride on ONE phase of the barrier: a single arrive.expect_tx with the total byte
+            // count, then the copies (values in pieces of 32 KB).  Round 1 issued one arrive.expect_tx
+            // PER copy on a barrier of count 1 — the second arrival could land in the next phase and
+            // the waits went out of step (the "fault with several copies outstanding"); it was never
+            // the hardware.  Thread 0 alone waits (with the watchdog); the CTA barrier publishes.
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(bar, bv + bc + br + bf);
+                for (uint32_t done = 0; done < bv; done += 32768u)
+                    bulk_g2s(smem + L.vals + done, reinterpret_cast<const unsigned char *>(a.vals + ka) + done,
+                             min(bv - done, 32768u), bar);
+                if (bc) bulk_g2s(smem + L.cols, a.loc + kc, bc, bar);
+                if (br) bulk_g2s(smem + L.rp, a.rowptr + ra, br, bar);
+                if (bf) bulk_g2s(smem + L.foot, a.foot + f0, bf, bar);
+                mbar_wait(bar, 0, a.barrier + 1);
+            }
+            __syncthreads();
             vs = reinterpret_cast<const double *>(smem + L.vals) - ka;
             cs = reinterpret_cast<const uint16_t *>(smem + L.cols) - kc;
             rp = reinterpret_cast<const int32_t *>(smem + L.rp) - ra;
@@ -661,7 +699,6 @@ struct SpmvEngine {
         const int G = kMainThreads / T;
         if constexpr (RES) {
             main_sync();                                     // previous readers of xs are done
-            if (!(a.debug_skip & 1))
             {   // stage the footprint of xin.  The gathers are L2 round trips (~0.7 us under load) and a
                 // thread owns up to ~14 footprint entries: issue up to 16 of them before the first use
                 // so that the whole footprint costs one round trip instead of one per group of four.
@@ -682,7 +719,7 @@ struct SpmvEngine {
                 }
             }
             main_sync();
-            for (int base = r0; base < r1; base += ((a.debug_skip & 2) ? (r1 - r0 + 1) * G : G)) {      // uniform trip count over the CTA
+            for (int base = r0; base < r1; base += G) {      // uniform trip count over the CTA
                 const int row = base + g;
                 const bool active = row < r1;
                 double acc = 0.0, acc2 = 0.0;
@@ -732,101 +769,147 @@ struct SpmvEngine {
 };
 
 
-// Streaming form: the CTA's slice of the (reordered) matrix is pulled through shared memory in
-// chunks of kStreamChunk entries by TMA bulk copies (cp.async.bulk + mbarrier), kStreamStages deep,
-// so the HBM/L2 latency of the matrix stream is hidden by the copy engine instead of by registers.
-// Per chunk: (A) every main thread multiplies its entries by the gathered vector entries (all of a
-// thread's ~12 ld.cg gathers are in flight together) and stores the products in place; (B) groups
-// of T lanes add up the products row by row; a row cut by the chunk boundary carries its partial
-// sum into the next chunk.  Chunks are aligned to multiples of kStreamChunk in the global entry
-// index, so neighbouring CTAs' chunks overlap harmlessly at the ends of their row ranges.
+// Streaming form (common.cuh "streaming SpMV tables"): the CTA's slice of the reordered matrix does not
+// fit on chip and is pulled from HBM every SpMV — by the copy engine, not by the threads:
+//   * every solver warp owns one contiguous stream of entries (values + 16-bit columns, no padding)
+//     and a private ring of kRingPieces x kPieceEntries entries in shared memory; lane 0 keeps the
+//     ring full with TMA bulk copies (one mbarrier phase per piece: a single arrive.expect_tx, then
+//     the value and the column copy).  Warps never synchronise with each other inside a tile, and the
+//     first pieces of the NEXT SpMV are already in flight when one ends (the matrix is immutable);
+//   * the multiplied vector is read from shared memory: the comm warps, idle during an SpMV, stage
+//     the footprint of tile t+1 (one ld.cg gather per distinct column) into the second of two
+//     buffers while the solver warps work on tile t (full / empty mbarriers per buffer);
+//   * rows are processed by groups of T lanes, 32/T rows of (nearly) equal length at a time — the
+//     tables deal length-sorted rows to the warps — and rows longer than kLongRow by the whole warp.
+// f(row, (A xin)[row]) is called once per row, by one lane, in no particular order.
+struct StreamShared {                        // pointers into dynamic shared memory, same for all threads
+    double *ring_v;                          // [kMainWarps][kRingEntries]
+    uint16_t *ring_c;                        // [kMainWarps][kRingEntries]
+    uint64_t *full;                          // [kMainWarps][kRingPieces]
+    uint64_t *xs_full, *xs_empty;            // [2] each
+    double *xs;                              // [2][st_fmax]
+    __device__ __forceinline__ StreamShared(const ResidentLayout &L, unsigned char *smem) {
+        ring_v = reinterpret_cast<double *>(smem + L.st_ring_v);
+        ring_c = reinterpret_cast<uint16_t *>(smem + L.st_ring_c);
+        full = reinterpret_cast<uint64_t *>(smem + L.st_bars);
+        xs_full = full + kMainWarps * kRingPieces;
+        xs_empty = xs_full + 2;
+        xs = reinterpret_cast<double *>(smem + L.st_xs);
+    }
+};
+
+// Comm-warp side of one streaming SpMV: stage the footprint of every tile of this CTA.  `tseq` is the
+// running tile counter (buffer = tseq & 1), kept in step with the solver warps' copy.
+__device__ __forceinline__ bool stream_gather_service(const KrylovArgs &a, unsigned char *smem, const double *xin,
+                                                      unsigned &tseq, unsigned long long *abort_word) {
+    const StreamShared sh(a.lay, smem);
+    const int ct = threadIdx.x - kMainThreads;
+    const int t0 = a.tile_ptr[blockIdx.x], t1 = a.tile_ptr[blockIdx.x + 1];
+    bool ok = true;
+    for (int t = t0; t < t1; ++t, ++tseq) {
+        const unsigned buf = tseq & 1u;
+        if (tseq >= 2) ok = mbar_wait(sh.xs_empty + buf, ((tseq >> 1) - 1u) & 1u, abort_word) && ok;
+        const NupgcmTileDesc td = a.tiles[t];
+        const int32_t *foot = a.sfoot + td.foot_off;
+        double *dst = sh.xs + (size_t)buf * a.lay.st_fmax;
+        constexpr int U = 8;
+        for (int base = ct; base < td.foot_len; base += U * kCommThreads) {
+            double xv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * kCommThreads;
+                xv[u] = i < td.foot_len ? ld_cg(xin + __ldg(foot + i)) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * kCommThreads;
+                if (i < td.foot_len) dst[i] = xv[u];
+            }
+        }
+        mbar_arrive(sh.xs_full + buf);                           // release: the stores above
+    }
+    return ok;
+}
+
 template <int T>
 struct SpmvEngine<T, false> {
     const KrylovArgs &a;
     int r0, r1;
-    const int32_t *rp;            // CTA's row pointers in shared memory, biased by the global row id
-    double *svals;                // [stages][chunk]
-    int32_t *scols;               // [stages][chunk]
-    const int32_t *rowend;        // per chunk (shared memory copy)
-    uint64_t *bars;               // [stages] full barriers
-    double *carry;                // 2 doubles
-    int kbase, nch;
-    unsigned phases;              // expected parity of each stage's barrier (persists across run() calls)
     bool legacy;
+    CommMailbox *mb;
+    // this warp's stream
+    double *rv;
+    uint16_t *rc;
+    uint64_t *full;
+    const double *gv;
+    const uint16_t *gc;
+    const uint32_t *srp;
+    const int32_t *srow;
+    uint64_t *xs_full, *xs_empty;
+    const double *xs;
+    int elen, npieces, t0, t1;
+    unsigned gp;              // pieces consumed by earlier run() calls (slot = piece & (kRingPieces-1))
+    unsigned tseq;            // tiles consumed by earlier run() calls
+    bool failed;
 
-    __device__ __forceinline__ SpmvEngine(const KrylovArgs &args, int r0_, int r1_, unsigned char *smem)
-        : a(args), r0(r0_), r1(r1_) {
+    __device__ __forceinline__ void issue(int p) const {          // lane 0 of the warp
+        const unsigned slot = (gp + (unsigned)p) & (kRingPieces - 1);
+        uint64_t *bar = full + slot;
+        mbar_expect_tx(bar, kPieceBytes);
+        bulk_g2s(rv + slot * kPieceEntries, gv + (size_t)p * kPieceEntries, kPieceEntries * 8, bar);
+        bulk_g2s(rc + slot * kPieceEntries, gc + (size_t)p * kPieceEntries, kPieceEntries * 2, bar);
+    }
+
+    __device__ __forceinline__ SpmvEngine(const KrylovArgs &args, int r0_, int r1_, unsigned char *smem, CommMailbox *mailbox)
+        : a(args), r0(r0_), r1(r1_), mb(mailbox) {
         legacy = a.lay.streaming == 0;
-        phases = 0;
+        gp = 0;
+        tseq = 0;
+        failed = false;
         if (legacy) return;
-        const ResidentLayout &L = a.lay;
-        svals = reinterpret_cast<double *>(smem + L.st_vals);
-        scols = reinterpret_cast<int32_t *>(smem + L.st_cols);
-        bars = reinterpret_cast<uint64_t *>(smem + L.st_misc);
-        carry = reinterpret_cast<double *>(smem + L.st_misc + 64);
-        const int k0 = a.rowptr[r0], k1 = a.rowptr[r1];
-        kbase = (k0 / kStreamChunk) * kStreamChunk;
-        nch = k1 > k0 ? (k1 - kbase + kStreamChunk - 1) / kStreamChunk : 0;
-        const int ra = r0 & ~3;
-        const uint32_t br = (uint32_t)(((r1 + 1 - ra + 3) & ~3) * 4);
-        const int cp0 = a.chunk_ptr[a.rank * gridDim.x + blockIdx.x];
-        const int ca = cp0 & ~3;
-        const uint32_t bi = (uint32_t)(((cp0 + nch - ca + 3) & ~3) * 4);
-        uint64_t *setup_bar = bars + 2 * kStreamStages;
+        const StreamShared sh(a.lay, smem);
         if (threadIdx.x == 0) {
-            for (int s = 0; s <= 2 * kStreamStages; ++s) mbar_init(bars + s, 1);
+            for (int i = 0; i < kMainWarps * kRingPieces; ++i) mbar_init(sh.full + i, 1);
+            for (int i = 0; i < 2; ++i) { mbar_init(sh.xs_full + i, kCommThreads); mbar_init(sh.xs_empty + i, kMainWarps); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
-        // row pointers by TMA, chunk table by plain loads (a few dozen ints)
-        if (threadIdx.x == 0) {
-            mbar_expect_tx(setup_bar, br);
-            bulk_g2s(smem + L.rp, a.rowptr + ra, br, setup_bar);
-        }
-        {
-            int32_t *d1 = reinterpret_cast<int32_t *>(smem + L.st_info);
-            for (int i = threadIdx.x; i < (int)(bi / 4); i += blockDim.x) d1[i] = a.chunk_rowend[ca + i];
-        }
-        mbar_wait(setup_bar, 0);
-        __syncthreads();
-        rp = reinterpret_cast<const int32_t *>(smem + L.rp) - ra;
-        rowend = reinterpret_cast<const int32_t *>(smem + L.st_info) + (cp0 - ca);
+        t0 = a.tile_ptr[blockIdx.x];
+        t1 = a.tile_ptr[blockIdx.x + 1];
+        xs_full = sh.xs_full;
+        xs_empty = sh.xs_empty;
+        xs = sh.xs;
+        const int wid = threadIdx.x >> 5;
+        if (wid >= kMainWarps) return;
+        const NupgcmWarpDesc wd = a.wdesc[(size_t)blockIdx.x * kMainWarps + wid];
+        rv = sh.ring_v + (size_t)wid * kRingEntries;
+        rc = sh.ring_c + (size_t)wid * kRingEntries;
+        full = sh.full + wid * kRingPieces;
+        gv = a.svals + wd.estart;
+        gc = a.scols + wd.estart;
+        srp = a.srp + wd.rtab;
+        srow = a.srow + wd.rtab;
+        elen = wd.elen;
+        npieces = (elen + kPieceEntries - 1) / kPieceEntries;
+        if ((threadIdx.x & 31) == 0)
+            for (int p = 0; p < npieces && p < kRingPieces; ++p) issue(p);      // prime the ring
     }
 
-    __device__ __forceinline__ void issue(int ci) {          // one thread
-        const int st = ci % kStreamStages;
-        const size_t k = (size_t)kbase + (size_t)ci * kStreamChunk;
-        // one bulk copy per barrier (values: bars[st], columns: bars[stages + st])
-        mbar_expect_tx(bars + st, kStreamChunk * 8);
-        bulk_g2s(svals + (size_t)st * kStreamChunk, a.vals + k, kStreamChunk * 8, bars + st);
-        mbar_expect_tx(bars + kStreamStages + st, kStreamChunk * 4);
-        bulk_g2s(scols + (size_t)st * kStreamChunk, a.colidx + k, kStreamChunk * 4, bars + kStreamStages + st);
+    // Before the CTA exits: the pieces prefetched for an SpMV that never came must have landed.
+    __device__ __forceinline__ void finish() {
+        if (legacy) return;
+        for (int p = 0; p < npieces && p < kRingPieces; ++p) {
+            const unsigned g = gp + (unsigned)p;
+            mbar_wait(full + (g & (kRingPieces - 1)), (g / kRingPieces) & 1u, a.barrier + 1);
+        }
     }
 
     template <class F>
     __device__ __forceinline__ void run(const double *xin, F &&f) {
-        const int lane = threadIdx.x & (T - 1);
-        const int g = threadIdx.x / T;
-        const int G = kMainThreads / T;
-        if (!legacy && a.lay.streaming == 3) {               // debug: exercise the pipeline only
-            main_sync();
-            if (threadIdx.x == 0) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                for (int ci = 0; ci < nch && ci < kStreamStages; ++ci) issue(ci);
-            }
-            for (int ci = 0; ci < nch; ++ci) {
-                const int st = ci % kStreamStages;
-                mbar_wait(bars + st, (phases >> st) & 1u);
-                mbar_wait(bars + kStreamStages + st, (phases >> st) & 1u);
-                phases ^= 1u << st;
-                main_sync();
-                if (threadIdx.x == 0 && ci + kStreamStages < nch) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    issue(ci + kStreamStages);
-                }
-            }
-        }
-        if (legacy || a.lay.streaming >= 2) {
+        if (legacy) {
+            const int lane = threadIdx.x & (T - 1);
+            const int g = threadIdx.x / T;
+            const int G = kMainThreads / T;
             for (int base = r0; base < r1; base += G) {      // uniform trip count over the CTA
                 const int row = base + g;
                 const bool active = row < r1;
@@ -841,74 +924,101 @@ struct SpmvEngine<T, false> {
             }
             return;
         }
-        main_sync();                                         // previous run() is completely finished
-        if (threadIdx.x == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            for (int ci = 0; ci < nch && ci < kStreamStages; ++ci) issue(ci);
-        }
-        int cursor = r0;
-        double carry_in = 0.0;
-        for (int ci = 0; ci < nch; ++ci) {
-            const int st = ci % kStreamStages;
-            double *pv = svals + (size_t)st * kStreamChunk;
-            const int32_t *pc = scols + (size_t)st * kStreamChunk;
-            mbar_wait(bars + st, (phases >> st) & 1u);
-            mbar_wait(bars + kStreamStages + st, (phases >> st) & 1u);
-            phases ^= 1u << st;
-            // (A) products, in place
-            {
-                constexpr int PER = (kStreamChunk + kMainThreads - 1) / kMainThreads;
-                double xv[PER];
-#pragma unroll
-                for (int i = 0; i < PER; ++i) {
-                    const int e = threadIdx.x + i * kMainThreads;
-                    xv[i] = e < kStreamChunk ? ld_cg(xin + pc[e]) : 0.0;
-                }
-#pragma unroll
-                for (int i = 0; i < PER; ++i) {
-                    const int e = threadIdx.x + i * kMainThreads;
-                    if (e < kStreamChunk) pv[e] *= xv[i];
-                }
+        if (t0 == t1) return;                                    // a CTA without rows posts nothing (both roles know)
+        // ask the comm warps to stage the footprints of xin (no response: the buffers' mbarriers pace us)
+        if (threadIdx.x == 0) { mb->count = kReqGather; mb->xin = xin; }
+        named_arrive(NUPGCM_BAR_REQ, kThreads);
+        unsigned long long *abort_word = a.barrier + 1;
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        const int tl = lane & (T - 1), g = lane / T;
+        constexpr int R = 32 / T;
+        const unsigned ebase = gp * kPieceEntries;               // ring index of stream entry e: (ebase + e) & (kRingEntries-1)
+        int landed = 0;                                          // pieces of this call known to have arrived
+        int issued = npieces < kRingPieces ? npieces : kRingPieces;
+        auto ensure = [&](int need) {                            // entries [0, need) of the stream are in the ring
+            while (landed * kPieceEntries < need) {
+                const unsigned gi = gp + (unsigned)landed;
+                if (!mbar_wait(full + (gi & (kRingPieces - 1)), (gi / kRingPieces) & 1u, abort_word)) failed = true;
+                ++landed;
             }
-            main_sync();
-            // (B) row sums
-            const int c0 = kbase + ci * kStreamChunk, c1 = c0 + kStreamChunk;
-            int rend = rowend[ci];
-            if (rend > r1) rend = r1;
-            for (int base = cursor; base < rend; base += G) {
-                const int row = base + g;
-                const bool active = row < rend;
+        };
+        auto release = [&](int cons) {                           // entries [0, cons) are consumed: refill freed slots
+            __syncwarp();                                        // every lane is done reading them
+            const int lim = min(npieces, kRingPieces + cons / kPieceEntries);
+            if (issued < lim) {
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    for (int p = issued; p < lim; ++p) issue(p);
+                }
+                issued = lim;
+            }
+        };
+        for (int t = t0; t < t1; ++t, ++tseq) {
+            const NupgcmTileWarp tw = a.tw[(size_t)t * kMainWarps + wid];
+            const unsigned buf = tseq & 1u;
+            if (!mbar_wait(xs_full + buf, (tseq >> 1) & 1u, abort_word)) failed = true;
+            const double *x = xs + (size_t)buf * a.lay.st_fmax;
+            // long rows: the whole warp per row, piece by piece
+            int ri = tw.rbeg;
+            for (const int rl_end = tw.rbeg + tw.nlong; ri < rl_end; ++ri) {
+                const int beg = (int)__ldg(srp + ri), end = (int)__ldg(srp + ri + 1);
+                const int row = __ldg(srow + ri);
                 double acc = 0.0;
-                int rbeg = 0, rfin = 0;
-                if (active) {
-                    rbeg = rp[row];
-                    rfin = rp[row + 1];
-                    const int beg = max(rbeg, c0) - c0, end = min(rfin, c1) - c0;
-                    for (int k = beg + lane; k < end; k += T) acc += pv[k];
+                for (int k0 = beg; k0 < end; k0 += 8 * 32) {
+                    const int k1 = min(end, k0 + 8 * 32);
+                    ensure(k1);
+                    for (int k = k0 + lane; k < k1; k += 32) {
+                        const unsigned idx = (ebase + (unsigned)k) & (kRingEntries - 1);
+                        acc = fma(rv[idx], x[rc[idx]], acc);
+                    }
+                    release(k1);
+                }
+                acc = warp_sum(acc);
+                if (lane == 0) f(row, acc);
+            }
+            // short rows: R rows at a time, T lanes each; the next unit's table entries are loaded early
+            const int rend = tw.rbeg + tw.nrows;
+            int my = ri + g;
+            int beg = 0, end = 0, row = -1;
+            if (my < rend) { beg = (int)__ldg(srp + my); end = (int)__ldg(srp + my + 1); row = __ldg(srow + my); }
+            for (; ri < rend; ri += R) {
+                const int cbeg = beg, cend = end, crow = row;
+                const int ulast = min(ri + R, rend);
+                const int need = (int)__ldg(srp + ulast);
+                my += R;
+                row = -1;
+                if (my < rend) { beg = (int)__ldg(srp + my); end = (int)__ldg(srp + my + 1); row = __ldg(srow + my); }
+                ensure(need);
+                double acc = 0.0, acc2 = 0.0;
+                if (crow >= 0) {
+                    int k = cbeg + tl;
+                    for (; k + T < cend; k += 2 * T) {
+                        const unsigned i0 = (ebase + (unsigned)k) & (kRingEntries - 1);
+                        const unsigned i1 = (ebase + (unsigned)(k + T)) & (kRingEntries - 1);
+                        acc = fma(rv[i0], x[rc[i0]], acc);
+                        acc2 = fma(rv[i1], x[rc[i1]], acc2);
+                    }
+                    if (k < cend) {
+                        const unsigned i0 = (ebase + (unsigned)k) & (kRingEntries - 1);
+                        acc = fma(rv[i0], x[rc[i0]], acc);
+                    }
+                    acc += acc2;
                 }
                 acc = group_sum<T>(acc);
-                if (active && lane == 0) {
-                    if (row == cursor) acc += carry_in;
-                    if (rfin <= c1) f(row, acc);
-                    else carry[ci & 1] = acc;                 // row continues in the next chunk
-                }
+                if (crow >= 0 && tl == 0) f(crow, acc);
+                release(need);
             }
-            main_sync();
-            // rows [cursor, rend) were touched; the last one may be unfinished
-            if (rend > cursor && rp[rend] > c1) {
-                cursor = rend - 1;
-                carry_in = carry[ci & 1];
-            } else {
-                cursor = rend;
-                carry_in = 0.0;
-            }
-            if (threadIdx.x == 0 && ci + kStreamStages < nch) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                issue(ci + kStreamStages);
-            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(xs_empty + buf);
         }
-        // rows that start exactly at the end of the last chunk (only empty rows can)
-        for (int row = cursor + threadIdx.x; row < r1; row += kMainThreads) f(row, row == cursor ? carry_in : 0.0);
+        // this SpMV is done: start pulling the first pieces of the next one
+        gp += (unsigned)npieces;
+        __syncwarp();
+        if (lane == 0 && npieces > 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            for (int p = 0; p < npieces && p < kRingPieces; ++p) issue(p);
+        }
+        if (failed) mb->dead = 1;
     }
 };
 
@@ -1049,12 +1159,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg(const __grid_constant__ Kryl
     if (threadIdx.x == 0) mailbox.dead = 0;
     const int lb = a.rank * gridDim.x + blockIdx.x;       // position in the partition (all ranks)
     const int r0 = a.part[lb], r1 = a.part[lb + 1];
-    SpmvEngine<T, RES> eng(a, r0, r1, dyn_smem);          // all warps take part in the bulk copy
+    SpmvEngine<T, RES> eng(a, r0, r1, dyn_smem, &mailbox);
     HaloPush<MR> hp;
     hp.init(a, r0, r1, s_prange, s_pdest);
     __syncthreads();
     if (threadIdx.x >= kMainThreads) {                     // comm warps: exchange service only
-        comm_warp_loop<MR>(&mailbox, a, a.poll_depth);
+        comm_warp_loop<MR>(&mailbox, a, a.poll_depth, dyn_smem);
         return;
     }
     GridReduce gr;
@@ -1172,6 +1282,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cg(const __grid_constant__ Kryl
     }
     if (lead) a.result[13] = (double)gr.gen;
     gr.finish();
+    eng.finish();
     if (lead) {
         a.result[0] = (double)iter;
         a.result[1] = solved ? 1.0 : 0.0;
@@ -1272,12 +1383,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
     if (threadIdx.x == 0) mailbox.dead = 0;
     const int lb = a.rank * gridDim.x + blockIdx.x;       // position in the partition (all ranks)
     const int r0 = a.part[lb], r1 = a.part[lb + 1];
-    SpmvEngine<T, RES> eng(a, r0, r1, dyn_smem);          // all warps take part in the bulk copy
+    SpmvEngine<T, RES> eng(a, r0, r1, dyn_smem, &mailbox);
     HaloPush<MR> hp;
     hp.init(a, r0, r1, s_prange, s_pdest);
     __syncthreads();
     if (threadIdx.x >= kMainThreads) {                     // comm warps: exchange service only
-        comm_warp_loop<MR>(&mailbox, a, a.poll_depth);
+        comm_warp_loop<MR>(&mailbox, a, a.poll_depth, dyn_smem);
         return;
     }
     GridReduce gr;
@@ -1649,6 +1760,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
     }
     if (lead) a.result[13] = (double)gr.gen;
     gr.finish();
+    eng.finish();
     if (lead) {
         a.result[0] = (double)iter;
         a.result[1] = solved ? 1.0 : 0.0;
@@ -1768,22 +1880,22 @@ static ResidentLayout plan_resident(const nupgcm_csr *A, bool gmres, int memory)
     return L.total <= limit ? L : none;
 }
 
-// Shared-memory plan of the streaming form (TMA pipeline); total == 0 if even that does not fit
-// (then the legacy direct-load loop runs).
+// Shared-memory plan of the streaming form (tiled TMA streams); total == 0 when the matrix has no
+// streaming tables (then the legacy direct-load loop runs).
 static ResidentLayout plan_streaming(const nupgcm_csr *A, bool gmres, int memory) {
     ResidentLayout L;
     memset(&L, 0, sizeof(L));
     const char *env = getenv("NUPGCM_STREAM_TMA");
     if (env && atoi(env) == 0) return L;
-    if (!A->d_chunk_ptr) return L;
+    if (!A->d_svals || A->str_fmax <= 0) return L;
     const int static_smem = gmres ? 8704 : 4096;
     const int limit = 227 * 1024 - static_smem;
     int off = 0;
-    L.st_vals = off; off += kStreamStages * kStreamChunk * 8;
-    L.st_cols = off; off += kStreamStages * kStreamChunk * 4;
-    L.rp = off;      off += ((A->str_max_rows + 1 + 4 + 3) & ~3) * 4;
-    L.st_info = off; off += ((A->str_max_chunks + 4 + 3) & ~3) * 4;
-    L.st_misc = off; off += 128;
+    L.st_ring_v = off; off += kMainWarps * kRingEntries * 8;
+    L.st_ring_c = off; off += kMainWarps * kRingEntries * 2;
+    L.st_bars = off;   off += ((kMainWarps * kRingPieces + 4) * 8 + 15) & ~15;
+    L.st_xs = off;     off += 2 * A->str_fmax * 8;
+    L.st_fmax = A->str_fmax;
     L.vec = off;
     const long long vec_bytes = (long long)(gmres ? memory + 1 : 5) * ((A->str_max_rows + 1) & ~1) * 8;
     if (off + vec_bytes <= limit) {
@@ -1792,7 +1904,6 @@ static ResidentLayout plan_streaming(const nupgcm_csr *A, bool gmres, int memory
     }
     L.total = off;
     L.streaming = 1;
-    if (const char *ed = getenv("NUPGCM_STREAM_DEBUG")) L.streaming = atoi(ed);   // 2: set-up only, 3: + pipeline
     if (L.total > limit) memset(&L, 0, sizeof(L));
     return L;
 }
@@ -1860,8 +1971,15 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
     args.lay = plan_resident(A, gmres, memory);
     const bool resident = args.lay.total > 0;
     if (!resident) args.lay = plan_streaming(A, gmres, memory);
-    args.chunk_ptr = A->d_chunk_ptr;
-    args.chunk_rowend = A->d_chunk_rowend;
+    args.svals = A->d_svals;
+    args.scols = A->d_scols;
+    args.tiles = A->d_tiles;
+    args.tile_ptr = A->d_tile_ptr;
+    args.wdesc = A->d_wdesc;
+    args.tw = A->d_tw;
+    args.srp = A->d_srp;
+    args.srow = A->d_srow;
+    args.sfoot = A->d_sfoot;
     args.n = (int)n;
     args.dinv = dinv ? dinv->d : nullptr;
     args.pscale = pscale;
@@ -1874,7 +1992,6 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
     args.xmode = 1;
     if (const char *ex = getenv("NUPGCM_XMODE")) args.xmode = atoi(ex) != 0;
     if (const char *ex = getenv("NUPGCM_XFENCE")) args.xfence = atoi(ex) != 0;
-    if (const char *ex = getenv("NUPGCM_DEBUG_SKIP")) args.debug_skip = atoi(ex);
     args.halo_ptr = A->d_halo_ptr;
     args.halo_idx = A->d_halo_idx;
     args.ll_off = comm ? (long long)(kArenaVecOffset + 3 * (size_t)comm->n_pad * sizeof(double)) : 0;
@@ -1908,7 +2025,7 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
     NUPGCM_CUDA(ctx, cudaEventRecord(ctx->sev0, ctx->stream));
     cudaError_t e;
     const size_t smem = (size_t)args.lay.total;
-    switch (persistent_tpr(A, resident || args.lay.streaming, grid * nranks)) {
+    switch (args.lay.streaming ? A->str_T : persistent_tpr(A, resident, grid * nranks)) {
         case 32: e = launch<32>(gmres, args, ctx, smem, grid, resident); break;
         case 16: e = launch<16>(gmres, args, ctx, smem, grid, resident); break;
         case 8: e = launch<8>(gmres, args, ctx, smem, grid, resident); break;

@@ -78,6 +78,7 @@ SIGNATURES = {
     "nupgcm_csr_inv_diag": [_P, _P],
     "nupgcm_rcm_order": [c_int64, _ip, _ip, c_int32, _ip],
     "nupgcm_shard_plan": [c_int64, _ip, _ip, c_int32, c_int32, c_int32, _ip, _ip, _ip, _ip],
+    "nupgcm_diag_stream_spmv_host": [c_int64, _ip, _ip, _dp, _dp, c_int32, c_int32, c_int32, _dp, _ip, _ip],
     "nupgcm_spmv": [_P, _P, _P, c_double, c_double],
     "nupgcm_cg_solve": [_P, _P, c_double, _P, _P, c_double, c_double, c_int64, _dp, c_int64,
                         POINTER(SolveStats)],
@@ -453,6 +454,23 @@ def rcm_order(mat):
     out = np.empty(m.shape[0], dtype=np.int64)
     _check(load().nupgcm_rcm_order(m.shape[0], _ptr(rowptr, _ip), _ptr(col, _ip), 0, _ptr(out, _ip)))
     return out
+
+
+def stream_spmv_host(mat, x, grid: int = 148, T: int = 8, fmax: int = 4096):
+    """Host-only: ``y = mat @ x`` computed by walking the streaming-SpMV tables the persistent
+    kernels use (``nupgcm_diag_stream_spmv_host``).  Returns ``(y, n_tiles, n_stream_entries)``."""
+    import scipy.sparse as sp
+    m = sp.csr_matrix(mat)
+    m.sort_indices()
+    rowptr = np.ascontiguousarray(m.indptr, dtype=np.int64)
+    col = np.ascontiguousarray(m.indices, dtype=np.int64)
+    vals, xv = _f64(m.data), _f64(x)
+    y = np.empty(m.shape[0])
+    nt, ne = np.zeros(1, dtype=np.int64), np.zeros(1, dtype=np.int64)
+    _check(load().nupgcm_diag_stream_spmv_host(m.shape[0], _ptr(rowptr, _ip), _ptr(col, _ip), _ptr(vals),
+                                               _ptr(xv), int(grid), int(T), int(fmax), _ptr(y),
+                                               _ptr(nt, _ip), _ptr(ne, _ip)))
+    return y, int(nt[0]), int(ne[0])
 
 
 def shard_plan(mat, nranks: int, grid_per_rank: int = 148):

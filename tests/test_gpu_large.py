@@ -1,6 +1,7 @@
 """Streaming form of the persistent solvers (matrix too large for shared memory): parity on a
-once-refined bowl3D mesh (N ~ 1.3e5, ~7e6 non-zeros), where the SpMV runs through the TMA chunk
-pipeline instead of the SM-resident path."""
+once-refined bowl3D mesh (N ~ 1.3e5, ~7e6 non-zeros), where the SpMV runs through the tiled TMA
+streams (per-warp rings + staged footprints) instead of the SM-resident path; and the same form
+forced onto the shipped meshes with small footprint caps (many tiles per CTA)."""
 import os
 
 import numpy as np
@@ -65,3 +66,54 @@ def test_streaming_cg_matches_oracle(ctx):
         os.environ.pop("NUPGCM_RESIDENT")
     assert st.solved and abs(st.niter - so.niter) <= 1
     assert rel(x.download(), xo) < 1e-6
+
+
+@pytest.mark.parametrize("orth,name", [(lib.ORTH_MGS, "mgs"), (lib.ORTH_CGS2_FUSED, "cgs2f")])
+@pytest.mark.parametrize("fmax", ["512", "1536"])
+def test_forced_streaming_many_tiles_per_cta(ctx, orth, name, fmax):
+    """h=0.1 3-D inversion matrix through the streaming form with a tiny footprint cap: several tiles
+    per CTA, both footprint buffers and every ring slot are recycled many times per SpMV."""
+    _, ops = workload("bowl_mixing")
+    A = ops["A"]
+    rng = np.random.default_rng(5)
+    y = rng.uniform(-1, 1, A.shape[0])
+    x0 = rng.uniform(-1, 1, A.shape[0])
+    M = np.full(y.size, ops["pscale"])
+    xo, so = krylov.gmres(A, y, x0=x0, M=M, atol=0.0, rtol=1e-30, memory=20, itmax=45, orth=name)
+    os.environ["NUPGCM_RESIDENT"] = "0"
+    os.environ["NUPGCM_STREAM_FMAX"] = fmax
+    try:
+        dA = ctx.csr(A, drop_zeros=True)
+        runs = []
+        for _ in range(2):
+            x = ctx.vector(x0)
+            st, hist = lib.gmres_solve(dA, ctx.vector(y), x, pscale=ops["pscale"], atol=0.0, rtol=1e-30,
+                                       itmax=45, memory=20, orth=orth, history=64)
+            runs.append((hist.copy(), x.download()))
+    finally:
+        os.environ.pop("NUPGCM_RESIDENT")
+        os.environ.pop("NUPGCM_STREAM_FMAX")
+    assert st.niter == 45
+    assert np.allclose(runs[0][0], so.residuals, rtol=1e-9)
+    assert rel(runs[0][1], xo) < 1e-9
+    assert np.array_equal(runs[0][1], runs[1][1]), "run-to-run reproducible"
+
+
+def test_forced_streaming_cg_small_rows(ctx):
+    """Evolution matrix (23 entries per row on average): T = 8 lanes per row leave lanes idle, rows of
+    every length from 5 to 100; Jacobi CG to convergence against the oracle."""
+    _, ops = workload("bowl_mixing")
+    A = (ops["M"] + 0.05 * (ops["Kh"] + ops["Kv"])).tocsr()
+    b = np.random.default_rng(1).uniform(-1, 1, A.shape[0])
+    dinv = 1.0 / A.diagonal()
+    xo, so = krylov.cg(A, b, x0=np.zeros(b.size), M=dinv, atol=1e-10, rtol=1e-10)
+    os.environ["NUPGCM_RESIDENT"] = "0"
+    os.environ["NUPGCM_STREAM_FMAX"] = "256"
+    try:
+        x = ctx.vector(b.size)
+        st, hist = lib.cg_solve(ctx.csr(A), ctx.vector(b), x, dinv=ctx.vector(dinv), atol=1e-10, rtol=1e-10, history=512)
+    finally:
+        os.environ.pop("NUPGCM_RESIDENT")
+        os.environ.pop("NUPGCM_STREAM_FMAX")
+    assert st.solved and abs(st.niter - so.niter) <= 1
+    assert rel(x.download(), xo) < 1e-9

@@ -182,6 +182,34 @@ def test_inversion_3d_sharded_first_iterations(ctx):
         assert rel(x, ref[2]) < 1e-6
 
 
+def test_inversion_3d_sharded_streaming_form(ctx):
+    """Same system through the STREAMING form (forced: small footprint cap, several tiles per CTA) on 2
+    ranks: the halo unpack feeds the comm warps' footprint gathers; fused CGS2 and MGS."""
+    _, ops = workload("bowl_mixing")
+    A = ops["A"].tocsr()
+    b = np.random.default_rng(4).uniform(-1, 1, A.shape[0])
+    ps = ops["pscale"]
+    os.environ["NUPGCM_RESIDENT"] = "0"
+    os.environ["NUPGCM_STREAM_FMAX"] = "1024"
+    try:
+        for orth in (lib.ORTH_CGS2_FUSED, lib.ORTH_MGS):
+            def solve(c, dA):
+                x = c.vector(A.shape[0])
+                st, hist = lib.gmres_solve(dA, c.vector(b), x, pscale=ps, atol=1e-6, rtol=1e-6, itmax=130,
+                                           memory=20, orth=orth, history=4096)
+                return st.niter, hist, x.download()
+
+            ref = solve(ctx, ctx.csr(A, drop_zeros=True))
+            res, _, _ = _sharded(2, A, solve, drop_zeros=True)
+            for niter, hist, x in res:
+                assert niter == ref[0]
+                assert np.allclose(hist[:100], ref[1][:100], rtol=1e-6)
+                assert rel(x, ref[2]) < 1e-6
+    finally:
+        os.environ.pop("NUPGCM_RESIDENT")
+        os.environ.pop("NUPGCM_STREAM_FMAX")
+
+
 def test_model_steps_sharded_match_single_rank(ctx):
     """Three timesteps of the 2-D bowl with both solves sharded over 2 ranks (state replicated,
     element RHS replicated) against the single-GPU model."""
