@@ -232,12 +232,25 @@ int32_t nupgcm_gmres_solve_prec(const nupgcm_csr *A, nupgcm_blockprec *M, const 
                                 nupgcm_solve_stats *stats);
 
 /* diagnostics, host only (no device needed): y = A x computed by walking the streaming-SpMV tables
- * (tiles, footprints, per-warp entry streams) that nupgcm_csr_prepare builds for `grid` CTAs, exactly as
- * the persistent kernels walk them; 0-based CSR as given, T = 4 or 8 lanes per row, fmax = footprint cap.
- * Fails if any row is not produced exactly once.  Used by the CPU tests of the table builder. */
+ * (tiles, footprints, per-warp streams of jagged-diagonal slices) that nupgcm_csr_prepare builds for
+ * `grid` CTAs, exactly as the persistent kernels walk them; 0-based CSR as given, fmax = footprint cap
+ * (<= 8192).  Fails if any row is not produced exactly once.  Used by the CPU tests of the table builder. */
 int32_t nupgcm_diag_stream_spmv_host(int64_t n, const int64_t *rowptr, const int64_t *colidx,
-                                     const double *vals, const double *x, int32_t grid, int32_t T,
+                                     const double *vals, const double *x, int32_t grid,
                                      int32_t fmax, double *y, int64_t *n_tiles, int64_t *n_entries);
+
+/* diagnostics: y = A x computed `reps` times by the STREAMING SpMV engine of the persistent solvers
+ * alone (same tables, CTAs and warp roles, no grid-wide wait); reports the average device time of one
+ * product.  mode 0 = the real product; 1 = pieces pulled through the rings untouched (copy pipeline
+ * only), 2 = no footprint gather (timing experiments; y is then meaningless).  Fails when the matrix is
+ * SM-resident (no streaming tables). */
+int32_t nupgcm_diag_stream_spmv(nupgcm_csr *A, const nupgcm_vec *x, nupgcm_vec *y, int32_t reps,
+                                int32_t mode, float *us_per_spmv);
+
+/* diagnostics: GB/s at which cp.async.bulk alone pulls `total_bytes` of HBM into shared memory when
+ * every one of `warps` warps per CTA (one CTA per SM) keeps `slots` copies of `piece` bytes in flight. */
+int32_t nupgcm_diag_tma_stream(nupgcm_ctx *ctx, int64_t total_bytes, int32_t piece, int32_t slots,
+                               int32_t warps, int32_t reps, float *gb_per_s);
 
 /* diagnostics: average latency (µs) of the grid-wide reduction the persistent solvers use.
  * mode 0: flagged-slot exchange only; 1: + block reduction; 2: + release/acquire fences. */

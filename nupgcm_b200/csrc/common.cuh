@@ -12,6 +12,7 @@
 struct NupgcmTileDesc;
 struct NupgcmWarpDesc;
 struct NupgcmTileWarp;
+struct NupgcmSlice;
 
 // -------------------------------------------------------------------------------------------
 // host-side handle layouts
@@ -120,8 +121,9 @@ struct nupgcm_csr {
     int32_t *d_tile_ptr;           // [grid_per_rank+1]
     NupgcmWarpDesc *d_wdesc;       // [grid_per_rank][kMainWarps]
     NupgcmTileWarp *d_tw;          // [tiles][kMainWarps]
-    uint32_t *d_srp;               // row tables: entry offsets relative to the warp's stream start
-    int32_t *d_srow;               //             internal row ids
+    NupgcmSlice *d_slices;         // slice tables of all warps
+    int32_t *d_srow;               // row tables: internal row ids ...
+    int32_t *d_slen;               //             ... and row lengths, in slice order
     int32_t *d_sfoot;              // footprints of all tiles (internal column ids, sorted per tile)
     int str_T, str_fmax, str_max_rows;   // lanes per row, footprint cap and largest row block of the tables (0: none)
     long long svals_version;
@@ -173,19 +175,24 @@ struct nupgcm_mesh {
 // A CTA whose matrix slice does not fit in shared memory walks its rows tile by tile.  A tile is a
 // run of consecutive rows whose distinct columns (its "footprint") number at most str_fmax: the
 // footprint entries of the multiplied vector are staged in shared memory once per tile and every
-// matrix entry carries a 16-bit position in that list instead of a 32-bit column.  Inside a tile the
-// rows are sorted by length and dealt to the kMainWarps solver warps in units of 32/T rows (rows
-// longer than kLongRow singly), so every warp owns ONE contiguous entry stream per CTA — values and
-// 16-bit columns, no padding — which it pulls through a private shared-memory ring with TMA bulk
-// copies of kPieceEntries entries.
+// matrix entry carries a 16-bit BYTE offset into that staging buffer instead of a 32-bit column.
+// Inside a tile the rows are sorted by decreasing length and cut into slices of 32 rows, one row
+// per lane; a slice is stored in jagged-diagonal order (entry j of every row that has one, rows in
+// slice order, then entry j+1, ...): consecutive lanes read consecutive addresses, there is no
+// padding, no cross-lane reduction and no divergence beyond the last few positions.  Slices are
+// dealt to the kMainWarps solver warps (least-loaded first), so every warp owns ONE contiguous
+// entry stream per CTA — values and 16-bit offsets — which it pulls through a private
+// shared-memory ring with TMA bulk copies of kPieceEntries entries.
 static const int kMainWarps = 11;      // solver warps of the persistent kernels (krylov.cu)
-static const int kPieceEntries = 256;  // entries per TMA piece: 2 KB of values + 512 B of columns
-static const int kRingPieces = 4;      // pieces per warp ring (power of two)
-static const int kLongRow = 96;        // rows longer than this are processed by a whole warp
+static const int kPieceEntries = 512;  // entries per TMA piece: 4 KB of values + 1 KB of offsets (sized from
+                                       // profiles/tma_piece_size_r02.txt: >= 2 KB copies reach the HBM rate)
+static const int kRingPieces = 3;      // pieces per warp ring
 
 struct NupgcmTileDesc { int32_t row0, nrows, foot_off, foot_len; };
-struct NupgcmWarpDesc { int32_t estart, elen, rtab, pad; };     // stream start (multiple of 8) / length, row table offset
-struct NupgcmTileWarp { int32_t rbeg, nlong, nrows, pad; };     // rows of one warp in one tile (relative to rtab)
+struct NupgcmWarpDesc { int32_t estart, elen, stab, rtab; };    // stream start (multiple of 8) / length, slice and row table offsets
+struct NupgcmTileWarp { int32_t sbeg, nsl; };                   // slices of one warp in one tile (relative to stab)
+struct NupgcmSlice { int32_t eoff, roff, nrows, lmax; };        // entry offset in the warp's stream, rows (relative to rtab), longest row
+
 static const int kPartialSlots = 24;   // >= memory+2 of GMRES
 static const int kMaxMemory = 20;
 

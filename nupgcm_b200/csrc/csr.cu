@@ -205,93 +205,81 @@ struct StreamTables {
     std::vector<int32_t> tile_ptr;
     std::vector<NupgcmWarpDesc> wdesc;
     std::vector<NupgcmTileWarp> tw;
-    std::vector<uint32_t> srp;
-    std::vector<int32_t> srow, foot, ssrc;
+    std::vector<NupgcmSlice> slices;
+    std::vector<int32_t> srow, slen, foot, ssrc;
     std::vector<uint16_t> scols;
 };
 
 static bool build_stream_tables(const int32_t *rowptr, const int32_t *col, int64_t n_cols,
-                                const std::vector<int32_t> &part, int cta0, int ncta, int T, int fmax,
+                                const std::vector<int32_t> &part, int cta0, int ncta, int fmax,
                                 StreamTables &st) {
-    const int W = kMainWarps, R = 32 / T;
+    const int W = kMainWarps;
     st.tile_ptr.assign(ncta + 1, 0);
     st.wdesc.assign((size_t)ncta * W, NupgcmWarpDesc{0, 0, 0, 0});
     std::vector<int32_t> mark(n_cols, -1), loc_of(n_cols, 0), tile_cols, order;
-    std::vector<std::vector<int32_t>> wrows(W);                 // per warp: rows of the CTA in stream order
-    std::vector<std::vector<NupgcmTileWarp>> wtw(W);            // per warp: its slice of every tile
     int32_t stamp = 0;
     for (int b = 0; b < ncta; ++b) {
         const int32_t ra = part[cta0 + b], rb = part[cta0 + b + 1];
-        for (int w = 0; w < W; ++w) { wrows[w].clear(); wtw[w].clear(); }
-        struct LocalTile { int32_t row0, nrows, foot_off, foot_len; };
-        std::vector<LocalTile> ltiles;
+        std::vector<NupgcmTileDesc> ltiles;
+        std::vector<std::vector<NupgcmTileWarp>> wtw(W);
+        std::vector<std::vector<NupgcmSlice>> wsl(W);
+        std::vector<std::vector<int32_t>> wrow(W), wlen(W), wsrc(W);
         std::vector<std::vector<uint16_t>> wcols(W);
-        std::vector<std::vector<int32_t>> wsrc(W);
-        std::vector<std::vector<uint32_t>> wrp(W);
         for (int32_t start = ra; start < rb;) {
             // grow the tile row by row while its footprint stays within fmax
             ++stamp;
             tile_cols.clear();
             int32_t r = start;
             for (; r < rb; ++r) {
-                int fresh = 0;
-                for (int32_t k = rowptr[r]; k < rowptr[r + 1]; ++k)
-                    if (mark[col[k]] != stamp) ++fresh;
-                // duplicates inside the row were counted once each: recount exactly while marking
-                if ((int)tile_cols.size() + fresh > fmax) {
-                    // exact test (a row may list a column twice)
-                    int exact = 0;
-                    for (int32_t k = rowptr[r]; k < rowptr[r + 1]; ++k)
-                        if (mark[col[k]] != stamp) { mark[col[k]] = stamp; ++exact; tile_cols.push_back(col[k]); }
-                    if ((int)tile_cols.size() > fmax) {
-                        for (int e = 0; e < exact; ++e) { mark[tile_cols.back()] = -1; tile_cols.pop_back(); }
-                        break;
-                    }
-                    continue;
-                }
+                const size_t before = tile_cols.size();
                 for (int32_t k = rowptr[r]; k < rowptr[r + 1]; ++k)
                     if (mark[col[k]] != stamp) { mark[col[k]] = stamp; tile_cols.push_back(col[k]); }
+                if ((int)tile_cols.size() > fmax) {              // this row does not fit any more: undo it
+                    while (tile_cols.size() > before) { mark[tile_cols.back()] = -1; tile_cols.pop_back(); }
+                    break;
+                }
             }
             if (r == start) return false;                       // one row alone exceeds the footprint cap
             std::sort(tile_cols.begin(), tile_cols.end());
             for (size_t i = 0; i < tile_cols.size(); ++i) loc_of[tile_cols[i]] = (int32_t)i;
             while (st.foot.size() % 4) st.foot.push_back(0);
-            ltiles.push_back({start, r - start, (int32_t)st.foot.size(), (int32_t)tile_cols.size()});
+            ltiles.push_back(NupgcmTileDesc{start, r - start, (int32_t)st.foot.size(), (int32_t)tile_cols.size()});
             st.foot.insert(st.foot.end(), tile_cols.begin(), tile_cols.end());
-            // rows by decreasing length (ties by row id), dealt to the warps in units
+            // rows by decreasing length (ties by row id), cut into slices of 32
             order.resize(r - start);
             for (int32_t i = 0; i < r - start; ++i) order[i] = start + i;
             std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
                 return rowptr[x + 1] - rowptr[x] > rowptr[y + 1] - rowptr[y];
             });
             std::vector<NupgcmTileWarp> cur(W);
-            for (int w = 0; w < W; ++w) cur[w] = NupgcmTileWarp{(int32_t)wrows[w].size(), 0, 0, 0};
-            size_t i = 0;
-            int unit = 0;
-            while (i < order.size()) {
-                const int w = unit % W;
-                const bool is_long = rowptr[order[i] + 1] - rowptr[order[i]] > kLongRow;
-                const size_t take = is_long ? 1 : std::min<size_t>(R, order.size() - i);
-                for (size_t j = 0; j < take; ++j) {
-                    const int32_t row = order[i + j];
-                    wrp[w].push_back((uint32_t)wcols[w].size());
-                    wrows[w].push_back(row);
-                    for (int32_t k = rowptr[row]; k < rowptr[row + 1]; ++k) {
-                        wcols[w].push_back((uint16_t)loc_of[col[k]]);
+            for (int w = 0; w < W; ++w) cur[w] = NupgcmTileWarp{(int32_t)wsl[w].size(), 0};
+            for (size_t i = 0; i < order.size(); i += 32) {
+                const int nr = (int)std::min<size_t>(32, order.size() - i);
+                int w = 0;                                       // least-loaded warp of the CTA so far
+                for (int v = 1; v < W; ++v)
+                    if (wcols[v].size() + 16 * wrow[v].size() < wcols[w].size() + 16 * wrow[w].size()) w = v;
+                const int lmax = rowptr[order[i] + 1] - rowptr[order[i]];
+                wsl[w].push_back(NupgcmSlice{(int32_t)wcols[w].size(), (int32_t)wrow[w].size(), nr, lmax});
+                for (int q = 0; q < nr; ++q) {
+                    wrow[w].push_back(order[i + q]);
+                    wlen[w].push_back(rowptr[order[i + q] + 1] - rowptr[order[i + q]]);
+                }
+                for (int j = 0; j < lmax; ++j)                   // jagged-diagonal order
+                    for (int q = 0; q < nr; ++q) {
+                        const int32_t row = order[i + q];
+                        if (rowptr[row + 1] - rowptr[row] <= j) break;      // rows are sorted: the rest is shorter
+                        const int32_t k = rowptr[row] + j;
+                        wcols[w].push_back((uint16_t)(8 * loc_of[col[k]]));
                         wsrc[w].push_back(k);
                     }
-                }
-                if (is_long) cur[w].nlong++;
-                cur[w].nrows += (int32_t)take;
-                i += take;
-                ++unit;
+                cur[w].nsl++;
             }
             for (int w = 0; w < W; ++w) wtw[w].push_back(cur[w]);
             start = r;
         }
         st.tile_ptr[b] = (int32_t)st.tiles.size();
         for (size_t t = 0; t < ltiles.size(); ++t) {
-            st.tiles.push_back(NupgcmTileDesc{ltiles[t].row0, ltiles[t].nrows, ltiles[t].foot_off, ltiles[t].foot_len});
+            st.tiles.push_back(ltiles[t]);
             for (int w = 0; w < W; ++w) st.tw.push_back(wtw[w][t]);
         }
         for (int w = 0; w < W; ++w) {
@@ -299,18 +287,19 @@ static bool build_stream_tables(const int32_t *rowptr, const int32_t *col, int64
             NupgcmWarpDesc &d = st.wdesc[(size_t)b * W + w];
             d.estart = (int32_t)st.scols.size();
             d.elen = (int32_t)wcols[w].size();
-            d.rtab = (int32_t)st.srp.size();
+            d.stab = (int32_t)st.slices.size();
+            d.rtab = (int32_t)st.srow.size();
             st.scols.insert(st.scols.end(), wcols[w].begin(), wcols[w].end());
             st.ssrc.insert(st.ssrc.end(), wsrc[w].begin(), wsrc[w].end());
-            st.srp.insert(st.srp.end(), wrp[w].begin(), wrp[w].end());
-            st.srp.push_back((uint32_t)wcols[w].size());
-            st.srow.insert(st.srow.end(), wrows[w].begin(), wrows[w].end());
-            st.srow.push_back(0);                               // keeps srow aligned with srp
+            st.slices.insert(st.slices.end(), wsl[w].begin(), wsl[w].end());
+            st.srow.insert(st.srow.end(), wrow[w].begin(), wrow[w].end());
+            st.slen.insert(st.slen.end(), wlen[w].begin(), wlen[w].end());
         }
     }
     st.tile_ptr[ncta] = (int32_t)st.tiles.size();
     // whole pieces are always copied: pad the tail
     for (int i = 0; i < kPieceEntries + 8; ++i) { st.scols.push_back(0); st.ssrc.push_back(-1); }
+    for (int i = 0; i < 32; ++i) { st.srow.push_back(0); st.slen.push_back(0); }
     return true;
 }
 
@@ -329,8 +318,9 @@ static void free_stream_tables(nupgcm_csr *A) {
     cudaFree(A->d_tile_ptr); A->d_tile_ptr = nullptr;
     cudaFree(A->d_wdesc); A->d_wdesc = nullptr;
     cudaFree(A->d_tw); A->d_tw = nullptr;
-    cudaFree(A->d_srp); A->d_srp = nullptr;
+    cudaFree(A->d_slices); A->d_slices = nullptr;
     cudaFree(A->d_srow); A->d_srow = nullptr;
+    cudaFree(A->d_slen); A->d_slen = nullptr;
     cudaFree(A->d_sfoot); A->d_sfoot = nullptr;
     A->stream_entries = 0;
     A->str_T = A->str_fmax = A->str_max_rows = 0;
@@ -479,14 +469,14 @@ int32_t nupgcm_csr_prepare(nupgcm_csr *A, int grid_per_rank) {
         const bool resident_fits = A->res_max_nnz > 0 && res_bytes <= 215 * 1024;
         if (A->n_rows == A->n_cols && kept > 0 && (resident_off || !resident_fits)) {
             const int me = nranks > 1 ? A->comm->rank : 0;
-            int fmax = 4096;
+            int fmax = 2560;                                     // two staging buffers of 20 KB next to 165 KB of rings
             if (const char *ef = getenv("NUPGCM_STREAM_FMAX")) {
                 const int v = atoi(ef);
-                if (v >= 256 && v <= 12288) fmax = v & ~3;
+                if (v >= 256 && v <= 3328) fmax = v & ~3;      // two buffers of fmax doubles must fit next to the rings
             }
-            const int T = (double)kept / (double)n_rows >= 20.0 ? 8 : 4;
+            const int T = 8;
             StreamTables st;
-            if (build_stream_tables(A->h_prow, A->h_pcol, A->n_cols, part, me * grid_per_rank, grid_per_rank, T, fmax, st)) {
+            if (build_stream_tables(A->h_prow, A->h_pcol, A->n_cols, part, me * grid_per_rank, grid_per_rank, fmax, st)) {
                 A->stream_entries = (int64_t)st.scols.size();
                 NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_scols, st.scols));
                 NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_ssrc, st.ssrc));
@@ -494,8 +484,9 @@ int32_t nupgcm_csr_prepare(nupgcm_csr *A, int grid_per_rank) {
                 NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_tile_ptr, st.tile_ptr));
                 NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_wdesc, st.wdesc));
                 NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_tw, st.tw));
-                NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_srp, st.srp));
+                NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_slices, st.slices));
                 NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_srow, st.srow));
+                NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_slen, st.slen));
                 NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_sfoot, st.foot));
                 NUPGCM_CUDA(ctx, cudaMalloc(&A->d_svals, (size_t)(A->stream_entries + 8) * sizeof(double)));
                 A->str_T = T;
@@ -597,14 +588,14 @@ extern "C" int32_t nupgcm_csr_shard_info(nupgcm_csr *A, int32_t rank, int64_t *r
 
 // ---- C ABI --------------------------------------------------------------------------------
 // Host-only: y = A x computed by walking the streaming tables exactly as the persistent kernels do
-// (tiles, footprint staging, per-warp streams, long rows / units of 32/T rows), for `grid` CTAs on
-// the structure as given (no reordering).  Lets the CPU tests validate the table builder without a
+// (tiles, footprint staging, per-warp streams of jagged-diagonal slices), for `grid` CTAs on the
+// structure as given (no reordering).  Lets the CPU tests validate the table builder without a
 // device.  Also returns the number of tiles and of stream entries (padding included).
 extern "C" int32_t nupgcm_diag_stream_spmv_host(int64_t n, const int64_t *rowptr, const int64_t *colidx,
                                                 const double *vals, const double *x, int32_t grid,
-                                                int32_t T, int32_t fmax, double *y, int64_t *n_tiles,
+                                                int32_t fmax, double *y, int64_t *n_tiles,
                                                 int64_t *n_entries) {
-    if (n < 1 || !rowptr || !colidx || !vals || !x || !y || grid < 1 || (T != 4 && T != 8) || fmax < 4 || fmax > 65536)
+    if (n < 1 || !rowptr || !colidx || !vals || !x || !y || grid < 1 || fmax < 4 || fmax > 8192)
         return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "invalid argument: %s", "diag_stream_spmv_host");
     const int64_t nnz = rowptr[n];
     if (nnz < 0 || nnz >= INT32_MAX || n >= INT32_MAX)
@@ -614,15 +605,16 @@ extern "C" int32_t nupgcm_diag_stream_spmv_host(int64_t n, const int64_t *rowptr
     for (int64_t k = 0; k < nnz; ++k) col[k] = (int32_t)colidx[k];
     build_partition(rp, n, grid, part);
     StreamTables st;
-    if (!build_stream_tables(rp.data(), col.data(), n, part, 0, grid, T, fmax, st))
+    if (!build_stream_tables(rp.data(), col.data(), n, part, 0, grid, fmax, st))
         return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "invalid argument: %s", "a row exceeds the footprint cap");
     std::vector<double> sv(st.scols.size());
     for (size_t i = 0; i < sv.size(); ++i) sv[i] = st.ssrc[i] >= 0 ? vals[st.ssrc[i]] : 0.0;
     for (int64_t i = 0; i < n; ++i) y[i] = std::nan("");         // every row must be written exactly once
     std::vector<double> xs(fmax);
     std::vector<int> written(n, 0);
-    const int W = kMainWarps, R = 32 / T;
+    const int W = kMainWarps;
     for (int b = 0; b < grid; ++b) {
+        std::vector<int64_t> walked(W, 0);                       // a warp's slices must tile its stream in order
         for (int t = st.tile_ptr[b]; t < st.tile_ptr[b + 1]; ++t) {
             const NupgcmTileDesc td = st.tiles[t];
             if (td.foot_len > fmax) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "tile footprint exceeds the cap");
@@ -630,31 +622,39 @@ extern "C" int32_t nupgcm_diag_stream_spmv_host(int64_t n, const int64_t *rowptr
             for (int w = 0; w < W; ++w) {
                 const NupgcmWarpDesc wd = st.wdesc[(size_t)b * W + w];
                 const NupgcmTileWarp tw = st.tw[(size_t)t * W + w];
-                const uint32_t *srp = st.srp.data() + wd.rtab;
-                const int32_t *srow = st.srow.data() + wd.rtab;
-                auto row_sum = [&](int ri) {
-                    double acc = 0.0;
-                    for (uint32_t k = srp[ri]; k < srp[ri + 1]; ++k) {
-                        if ((int)k >= wd.elen) return std::nan("");
-                        acc += sv[(size_t)wd.estart + k] * xs[st.scols[(size_t)wd.estart + k]];
-                    }
-                    return acc;
-                };
-                int ri = tw.rbeg;
-                for (; ri < tw.rbeg + tw.nlong; ++ri) {
-                    if ((int)(srp[ri + 1] - srp[ri]) <= kLongRow) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "short row among the long ones");
-                    y[srow[ri]] = row_sum(ri); written[srow[ri]]++;
-                }
-                for (; ri < tw.rbeg + tw.nrows; ri += R)
-                    for (int g = 0; g < R && ri + g < tw.rbeg + tw.nrows; ++g) {
-                        const int r = ri + g;
-                        if ((int)(srp[r + 1] - srp[r]) > kLongRow) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "long row among the short ones");
-                        if (srow[r] < td.row0 || srow[r] >= td.row0 + td.nrows) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "row outside its tile");
-                        y[srow[r]] = row_sum(r); written[srow[r]]++;
-                    }
                 if (wd.estart % 8) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "misaligned stream");
+                for (int si = tw.sbeg; si < tw.sbeg + tw.nsl; ++si) {
+                    const NupgcmSlice sl = st.slices[(size_t)wd.stab + si];
+                    if (sl.eoff != walked[w]) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "slices do not tile the stream");
+                    const int32_t *rows = st.srow.data() + wd.rtab + sl.roff, *lens = st.slen.data() + wd.rtab + sl.roff;
+                    double acc[32] = {0};
+                    int64_t off = sl.eoff;
+                    if (sl.nrows < 1 || sl.nrows > 32 || lens[0] != sl.lmax) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "bad slice header");
+                    for (int j = 0; j < sl.lmax; ++j) {
+                        int cnt = 0;
+                        for (int q = 0; q < sl.nrows; ++q) {
+                            if (q + 1 < sl.nrows && lens[q] < lens[q + 1]) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "slice rows not sorted");
+                            if (lens[q] > j) {
+                                const size_t e = (size_t)wd.estart + off + cnt;
+                                if (off + cnt >= wd.elen || st.scols[e] % 8 || st.scols[e] / 8 >= td.foot_len)
+                                    return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "entry outside its stream or footprint");
+                                acc[q] += sv[e] * xs[st.scols[e] / 8];
+                                ++cnt;
+                            }
+                        }
+                        off += cnt;
+                    }
+                    walked[w] = off;
+                    for (int q = 0; q < sl.nrows; ++q) {
+                        if (rows[q] < td.row0 || rows[q] >= td.row0 + td.nrows) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "row outside its tile");
+                        y[rows[q]] = acc[q];
+                        written[rows[q]]++;
+                    }
+                }
             }
         }
+        for (int w = 0; w < W; ++w)
+            if (walked[w] != st.wdesc[(size_t)b * W + w].elen) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "stream not consumed completely");
     }
     for (int64_t i = 0; i < n; ++i)
         if (written[i] != 1) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "a row was not written exactly once");
@@ -662,7 +662,6 @@ extern "C" int32_t nupgcm_diag_stream_spmv_host(int64_t n, const int64_t *rowptr
     if (n_entries) *n_entries = (int64_t)st.scols.size();
     return NUPGCM_OK;
 }
-
 
 // Host-only utility: the reordering the solvers apply internally, for callers that want it too
 // (the reference computes its per-field orderings with CuthillMcKee.symrcm, src/dofs.jl:98-100).

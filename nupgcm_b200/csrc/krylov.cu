@@ -48,8 +48,8 @@ struct ResidentLayout {       // byte offsets into dynamic shared memory (all mu
 
 static const int kRingEntries = kPieceEntries * kRingPieces;
 static const uint32_t kPieceBytes = kPieceEntries * (sizeof(double) + sizeof(uint16_t));
-static_assert((kRingPieces & (kRingPieces - 1)) == 0 && (kPieceEntries & (kPieceEntries - 1)) == 0, "ring sizes must be powers of two");
-static_assert((32 / 4) * kLongRow + kPieceEntries <= kRingEntries, "a unit of rows must fit in the ring next to one piece");
+static_assert((kPieceEntries & (kPieceEntries - 1)) == 0, "piece size must be a power of two");
+static_assert(8 * 32 + kPieceEntries <= kRingEntries, "a block of 8 slice positions must fit in the ring next to one piece");
 
 struct KrylovArgs {
     const int32_t *rowptr;
@@ -67,8 +67,9 @@ struct KrylovArgs {
     const int32_t *tile_ptr;
     const NupgcmWarpDesc *wdesc;
     const NupgcmTileWarp *tw;
-    const uint32_t *srp;
+    const NupgcmSlice *slices;
     const int32_t *srow;
+    const int32_t *slen;
     const int32_t *sfoot;
     ResidentLayout lay;
     int n;
@@ -779,8 +780,11 @@ struct SpmvEngine {
 //   * the multiplied vector is read from shared memory: the comm warps, idle during an SpMV, stage
 //     the footprint of tile t+1 (one ld.cg gather per distinct column) into the second of two
 //     buffers while the solver warps work on tile t (full / empty mbarriers per buffer);
-//   * rows are processed by groups of T lanes, 32/T rows of (nearly) equal length at a time — the
-//     tables deal length-sorted rows to the warps — and rows longer than kLongRow by the whole warp.
+//   * a warp works through slices of 32 length-sorted rows in jagged-diagonal order, one row per lane:
+//     consecutive lanes read consecutive ring entries, no cross-lane reduction, and lanes only drop
+//     out over the last few positions of a slice.  (The first version of this engine processed CSR
+//     rows with groups of T lanes and spent 52 warp instructions per 32 entries on divergent unrolled
+//     row loops, ring-index arithmetic and shuffles — profiles/ncu_stream_spmv_r02.txt.)
 // f(row, (A xin)[row]) is called once per row, by one lane, in no particular order.
 struct StreamShared {                        // pointers into dynamic shared memory, same for all threads
     double *ring_v;                          // [kMainWarps][kRingEntries]
@@ -843,27 +847,35 @@ struct SpmvEngine<T, false> {
     uint64_t *full;
     const double *gv;
     const uint16_t *gc;
-    const uint32_t *srp;
-    const int32_t *srow;
+    const NupgcmSlice *slices;
+    const int32_t *srow, *slen;
     uint64_t *xs_full, *xs_empty;
-    const double *xs;
-    int elen, npieces, t0, t1;
-    unsigned gp;              // pieces consumed by earlier run() calls (slot = piece & (kRingPieces-1))
+    const unsigned char *xs;
+    int npieces, t0, t1;
+    // pieces go through the ring slots round-robin, across run() calls: slot / parity of the next wait
+    // (all lanes) and slot of the next issue (lane 0)
+    int wslot, islot;
+    unsigned wpar;
     unsigned tseq;            // tiles consumed by earlier run() calls
     bool failed;
 
-    __device__ __forceinline__ void issue(int p) const {          // lane 0 of the warp
-        const unsigned slot = (gp + (unsigned)p) & (kRingPieces - 1);
-        uint64_t *bar = full + slot;
+    __device__ __forceinline__ void issue(int p) {                // lane 0 of the warp
+        uint64_t *bar = full + islot;
         mbar_expect_tx(bar, kPieceBytes);
-        bulk_g2s(rv + slot * kPieceEntries, gv + (size_t)p * kPieceEntries, kPieceEntries * 8, bar);
-        bulk_g2s(rc + slot * kPieceEntries, gc + (size_t)p * kPieceEntries, kPieceEntries * 2, bar);
+        bulk_g2s(rv + islot * kPieceEntries, gv + (size_t)p * kPieceEntries, kPieceEntries * 8, bar);
+        bulk_g2s(rc + islot * kPieceEntries, gc + (size_t)p * kPieceEntries, kPieceEntries * 2, bar);
+        islot = islot + 1 == kRingPieces ? 0 : islot + 1;
+    }
+    __device__ __forceinline__ void wait_piece(unsigned long long *abort_word) {
+        if (!mbar_wait(full + wslot, wpar, abort_word)) failed = true;
+        if (++wslot == kRingPieces) { wslot = 0; wpar ^= 1u; }
     }
 
     __device__ __forceinline__ SpmvEngine(const KrylovArgs &args, int r0_, int r1_, unsigned char *smem, CommMailbox *mailbox)
         : a(args), r0(r0_), r1(r1_), mb(mailbox) {
         legacy = a.lay.streaming == 0;
-        gp = 0;
+        wslot = islot = 0;
+        wpar = 0;
         tseq = 0;
         failed = false;
         if (legacy) return;
@@ -878,7 +890,7 @@ struct SpmvEngine<T, false> {
         t1 = a.tile_ptr[blockIdx.x + 1];
         xs_full = sh.xs_full;
         xs_empty = sh.xs_empty;
-        xs = sh.xs;
+        xs = reinterpret_cast<const unsigned char *>(sh.xs);
         const int wid = threadIdx.x >> 5;
         if (wid >= kMainWarps) return;
         const NupgcmWarpDesc wd = a.wdesc[(size_t)blockIdx.x * kMainWarps + wid];
@@ -887,10 +899,10 @@ struct SpmvEngine<T, false> {
         full = sh.full + wid * kRingPieces;
         gv = a.svals + wd.estart;
         gc = a.scols + wd.estart;
-        srp = a.srp + wd.rtab;
+        slices = a.slices + wd.stab;
         srow = a.srow + wd.rtab;
-        elen = wd.elen;
-        npieces = (elen + kPieceEntries - 1) / kPieceEntries;
+        slen = a.slen + wd.rtab;
+        npieces = (wd.elen + kPieceEntries - 1) / kPieceEntries;
         if ((threadIdx.x & 31) == 0)
             for (int p = 0; p < npieces && p < kRingPieces; ++p) issue(p);      // prime the ring
     }
@@ -898,13 +910,12 @@ struct SpmvEngine<T, false> {
     // Before the CTA exits: the pieces prefetched for an SpMV that never came must have landed.
     __device__ __forceinline__ void finish() {
         if (legacy) return;
-        for (int p = 0; p < npieces && p < kRingPieces; ++p) {
-            const unsigned g = gp + (unsigned)p;
-            mbar_wait(full + (g & (kRingPieces - 1)), (g / kRingPieces) & 1u, a.barrier + 1);
-        }
+        for (int p = 0; p < npieces && p < kRingPieces; ++p) wait_piece(a.barrier + 1);
     }
 
-    template <class F>
+    // DBG (diagnostics only, nupgcm_diag_stream_spmv): 1 = pull the pieces through the ring without
+    // touching them, 2 = multiply by x[lane] instead of the gathered entry (no bank conflicts)
+    template <int DBG = 0, class F>
     __device__ __forceinline__ void run(const double *xin, F &&f) {
         if (legacy) {
             const int lane = threadIdx.x & (T - 1);
@@ -930,22 +941,16 @@ struct SpmvEngine<T, false> {
         named_arrive(NUPGCM_BAR_REQ, kThreads);
         unsigned long long *abort_word = a.barrier + 1;
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        const int tl = lane & (T - 1), g = lane / T;
-        constexpr int R = 32 / T;
-        const unsigned ebase = gp * kPieceEntries;               // ring index of stream entry e: (ebase + e) & (kRingEntries-1)
+        int rpos = wslot * kPieceEntries;                        // ring position of the next entry to consume
         int landed = 0;                                          // pieces of this call known to have arrived
         int issued = npieces < kRingPieces ? npieces : kRingPieces;
         auto ensure = [&](int need) {                            // entries [0, need) of the stream are in the ring
-            while (landed * kPieceEntries < need) {
-                const unsigned gi = gp + (unsigned)landed;
-                if (!mbar_wait(full + (gi & (kRingPieces - 1)), (gi / kRingPieces) & 1u, abort_word)) failed = true;
-                ++landed;
-            }
+            while (landed * kPieceEntries < need) { wait_piece(abort_word); ++landed; }
         };
         auto release = [&](int cons) {                           // entries [0, cons) are consumed: refill freed slots
-            __syncwarp();                                        // every lane is done reading them
             const int lim = min(npieces, kRingPieces + cons / kPieceEntries);
             if (issued < lim) {
+                __syncwarp();                                    // every lane is done reading them
                 if (lane == 0) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     for (int p = issued; p < lim; ++p) issue(p);
@@ -953,66 +958,81 @@ struct SpmvEngine<T, false> {
                 issued = lim;
             }
         };
+        auto entry = [&](int idx) -> double {                    // product of ring entry idx with its vector entry
+            if (idx >= kRingEntries) idx -= kRingEntries;
+            const double xv = DBG == 2 ? *reinterpret_cast<const double *>(xs + 8 * lane)
+                                       : *reinterpret_cast<const double *>(xs + rc[idx]);
+            return rv[idx] * xv;
+        };
         for (int t = t0; t < t1; ++t, ++tseq) {
             const NupgcmTileWarp tw = a.tw[(size_t)t * kMainWarps + wid];
             const unsigned buf = tseq & 1u;
+            // the first slice's tables are fetched while the footprint is still being staged
+            NupgcmSlice sl = NupgcmSlice{0, 0, 0, 0};
+            int mylen = 0, myrow = -1;
+            if (tw.nsl > 0) {
+                sl = slices[tw.sbeg];
+                if (lane < sl.nrows) { mylen = __ldg(slen + sl.roff + lane); myrow = __ldg(srow + sl.roff + lane); }
+            }
             if (!mbar_wait(xs_full + buf, (tseq >> 1) & 1u, abort_word)) failed = true;
-            const double *x = xs + (size_t)buf * a.lay.st_fmax;
-            // long rows: the whole warp per row, piece by piece
-            int ri = tw.rbeg;
-            for (const int rl_end = tw.rbeg + tw.nlong; ri < rl_end; ++ri) {
-                const int beg = (int)__ldg(srp + ri), end = (int)__ldg(srp + ri + 1);
-                const int row = __ldg(srow + ri);
-                double acc = 0.0;
-                for (int k0 = beg; k0 < end; k0 += 8 * 32) {
-                    const int k1 = min(end, k0 + 8 * 32);
-                    ensure(k1);
-                    for (int k = k0 + lane; k < k1; k += 32) {
-                        const unsigned idx = (ebase + (unsigned)k) & (kRingEntries - 1);
-                        acc = fma(rv[idx], x[rc[idx]], acc);
-                    }
-                    release(k1);
+            const unsigned char *xsave = xs;
+            xs = xsave + (size_t)buf * a.lay.st_fmax * 8;
+            for (int si = 0; si < tw.nsl; ++si) {
+                const NupgcmSlice cs = sl;
+                const int clen = mylen, crow = myrow;
+                if (si + 1 < tw.nsl) {                           // next slice's tables: in flight during this one
+                    sl = slices[tw.sbeg + si + 1];
+                    mylen = 0;
+                    myrow = -1;
+                    if (lane < sl.nrows) { mylen = __ldg(slen + sl.roff + lane); myrow = __ldg(srow + sl.roff + lane); }
                 }
-                acc = warp_sum(acc);
-                if (lane == 0) f(row, acc);
-            }
-            // short rows: R rows at a time, T lanes each; the next unit's table entries are loaded early
-            const int rend = tw.rbeg + tw.nrows;
-            int my = ri + g;
-            int beg = 0, end = 0, row = -1;
-            if (my < rend) { beg = (int)__ldg(srp + my); end = (int)__ldg(srp + my + 1); row = __ldg(srow + my); }
-            for (; ri < rend; ri += R) {
-                const int cbeg = beg, cend = end, crow = row;
-                const int ulast = min(ri + R, rend);
-                const int need = (int)__ldg(srp + ulast);
-                my += R;
-                row = -1;
-                if (my < rend) { beg = (int)__ldg(srp + my); end = (int)__ldg(srp + my + 1); row = __ldg(srow + my); }
-                ensure(need);
-                double acc = 0.0, acc2 = 0.0;
-                if (crow >= 0) {
-                    int k = cbeg + tl;
-                    for (; k + T < cend; k += 2 * T) {
-                        const unsigned i0 = (ebase + (unsigned)k) & (kRingEntries - 1);
-                        const unsigned i1 = (ebase + (unsigned)(k + T)) & (kRingEntries - 1);
-                        acc = fma(rv[i0], x[rc[i0]], acc);
-                        acc2 = fma(rv[i1], x[rc[i1]], acc2);
+                const int nr = cs.nrows;
+                const bool act = lane < nr;
+                const int lmin = __shfl_sync(0xffffffffu, clen, nr - 1);
+                int off = cs.eoff, j = 0;
+                double acc0 = 0.0, acc1 = 0.0;
+                // positions every row of the slice has: nr entries each, lane q reads entry q
+                for (; j + 8 <= lmin; j += 8) {
+                    ensure(off + 8 * nr);
+                    if (DBG != 1 && act) {
+#pragma unroll
+                        for (int p = 0; p < 8; p += 2) {
+                            acc0 += entry(rpos + p * nr + lane);
+                            acc1 += entry(rpos + (p + 1) * nr + lane);
+                        }
                     }
-                    if (k < cend) {
-                        const unsigned i0 = (ebase + (unsigned)k) & (kRingEntries - 1);
-                        acc = fma(rv[i0], x[rc[i0]], acc);
-                    }
-                    acc += acc2;
+                    off += 8 * nr;
+                    rpos += 8 * nr;
+                    if (rpos >= kRingEntries) rpos -= kRingEntries;
+                    release(off);
                 }
-                acc = group_sum<T>(acc);
-                if (crow >= 0 && tl == 0) f(crow, acc);
-                release(need);
+                if (j < lmin) {
+                    const int m = lmin - j;
+                    ensure(off + m * nr);
+                    if (DBG != 1 && act)
+                        for (int p = 0; p < m; ++p) acc0 += entry(rpos + p * nr + lane);
+                    off += m * nr;
+                    rpos += m * nr;
+                    if (rpos >= kRingEntries) rpos -= kRingEntries;
+                    j = lmin;
+                }
+                // the jagged end: rows are sorted by length, so position j is held by lanes 0 .. cnt-1
+                for (; j < cs.lmax; ++j) {
+                    const int cnt = __popc(__ballot_sync(0xffffffffu, clen > j));
+                    ensure(off + cnt);
+                    if (DBG != 1 && clen > j) acc0 += entry(rpos + lane);
+                    off += cnt;
+                    rpos += cnt;
+                    if (rpos >= kRingEntries) rpos -= kRingEntries;
+                }
+                release(off);
+                if (act) f(crow, acc0 + acc1);
             }
+            xs = xsave;
             __syncwarp();
             if (lane == 0) mbar_arrive(xs_empty + buf);
         }
         // this SpMV is done: start pulling the first pieces of the next one
-        gp += (unsigned)npieces;
         __syncwarp();
         if (lane == 0 && npieces > 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1977,8 +1997,9 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
     args.tile_ptr = A->d_tile_ptr;
     args.wdesc = A->d_wdesc;
     args.tw = A->d_tw;
-    args.srp = A->d_srp;
+    args.slices = A->d_slices;
     args.srow = A->d_srow;
+    args.slen = A->d_slen;
     args.sfoot = A->d_sfoot;
     args.n = (int)n;
     args.dinv = dinv ? dinv->d : nullptr;
@@ -2088,6 +2109,154 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
             stats->sm_mhz = (float)res[12];
         }
     }
+    return NUPGCM_OK;
+}
+
+
+// ---- diagnostics: the streaming SpMV engine alone ------------------------------------------------
+// y = A x computed `reps` times by the persistent kernels' streaming engine (one CTA per SM, same
+// tables, same warp roles) without any grid-wide wait: a plain kernel that ncu can replay, the unit
+// test of the engine, and the SpMV leg of the roofline report.  x / y are in caller order; the kernel
+// gathers x through the internal ordering into `xi` first (a separate launch).
+__global__ void k_diag_permute_in(double *xi, const double *x, const int32_t *perm, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) xi[i] = x[perm[i]];
+}
+
+template <int T, int DBG>
+__global__ void __launch_bounds__(kThreads, 1) k_diag_stream_spmv(const __grid_constant__ KrylovArgs a, const double *xi,
+                                                                  double *y, int reps) {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    __shared__ CommMailbox mailbox;
+    if (threadIdx.x == 0) mailbox.dead = 0;
+    const int r0 = a.part[blockIdx.x], r1 = a.part[blockIdx.x + 1];
+    SpmvEngine<T, false> eng(a, r0, r1, dyn_smem, &mailbox);
+    __syncthreads();
+    if (threadIdx.x >= kMainThreads) {
+        comm_warp_loop<false>(&mailbox, a, 1, dyn_smem);
+        return;
+    }
+    for (int rep = 0; rep < reps; ++rep) {
+        eng.template run<DBG>(xi, [&](int row, double v) { y[a.perm[row]] = v; });
+        main_sync();
+    }
+    if (threadIdx.x == 0) mailbox.count = kReqExit;
+    named_arrive(NUPGCM_BAR_REQ, kThreads);
+    eng.finish();
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.result[7] = mailbox.dead ? 1.0 : 0.0;
+}
+
+extern "C" int32_t nupgcm_diag_stream_spmv(nupgcm_csr *A, const nupgcm_vec *x, nupgcm_vec *y, int32_t reps,
+                                           int32_t mode, float *us_per_spmv) {
+    NUPGCM_REQUIRE(nullptr, A && x && y, "diag_stream_spmv: NULL argument");
+    nupgcm_ctx *ctx = A->ctx;
+    NUPGCM_REQUIRE(ctx, A->n_rows == A->n_cols && x->n == A->n_rows && y->n == A->n_rows && x->d != y->d,
+                   "diag_stream_spmv: square matrix and distinct vectors of its size");
+    NUPGCM_REQUIRE(ctx, reps >= 1 && mode >= 0 && mode <= 2 && !A->comm, "diag_stream_spmv: bad argument");
+    NUPGCM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int grid = ctx->coop_grid;
+    int32_t rc = nupgcm_csr_prepare(A, grid);
+    if (rc) return rc;
+    KrylovArgs args;
+    memset(&args, 0, sizeof(args));
+    args.lay = plan_streaming(A, false, 0);
+    NUPGCM_REQUIRE(ctx, args.lay.streaming == 1, "diag_stream_spmv: the matrix has no streaming tables (it is SM-resident; set NUPGCM_RESIDENT=0)");
+    rc = ensure_workspace(ctx, (size_t)A->n_rows * sizeof(double));
+    if (rc) return rc;
+    args.rowptr = A->d_prow; args.colidx = A->d_pcol; args.vals = A->d_pvals; args.perm = A->d_perm; args.part = A->d_part;
+    args.svals = A->d_svals; args.scols = A->d_scols; args.tiles = A->d_tiles; args.tile_ptr = A->d_tile_ptr;
+    args.wdesc = A->d_wdesc; args.tw = A->d_tw; args.slices = A->d_slices; args.srow = A->d_srow; args.slen = A->d_slen; args.sfoot = A->d_sfoot;
+    args.n = (int)A->n_rows;
+    args.nranks = 1;
+    args.barrier = ctx->d_barrier;
+    args.result = ctx->d_scalars;
+    NUPGCM_CUDA(ctx, cudaMemsetAsync(ctx->d_barrier, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    k_diag_permute_in<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->d_ws, x->d, A->d_perm, (int)A->n_rows);
+    const void *fn;
+    fn = mode == 0 ? (const void *)k_diag_stream_spmv<8, 0> : mode == 1 ? (const void *)k_diag_stream_spmv<8, 1> : (const void *)k_diag_stream_spmv<8, 2>;
+    NUPGCM_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, args.lay.total));
+    const double *xi = ctx->d_ws;
+    double *yd = y->d;
+    int r = reps;
+    void *params[] = {&args, &xi, &yd, &r};
+    NUPGCM_CUDA(ctx, cudaEventRecord(ctx->sev0, ctx->stream));
+    NUPGCM_CUDA(ctx, cudaLaunchKernel(fn, dim3(grid), dim3(kThreads), params, (size_t)args.lay.total, ctx->stream));
+    NUPGCM_CUDA(ctx, cudaEventRecord(ctx->sev1, ctx->stream));
+    ctx->launches += 2;
+    NUPGCM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NUPGCM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_scalars[7] != 0.0) return nupgcm_fail(ctx, NUPGCM_ERR_CUDA, "%s", "diag_stream_spmv: a shared-memory pipeline wait timed out");
+    float ms = 0.f;
+    NUPGCM_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->sev0, ctx->sev1));
+    if (us_per_spmv) *us_per_spmv = 1e3f * ms / reps;
+    return NUPGCM_OK;
+}
+
+
+// ---- diagnostics: throughput of TMA bulk copies as a function of their size ------------------------
+// Every warp of every CTA streams its own contiguous region of `src` through `slots` shared-memory
+// buffers of `piece` bytes with cp.async.bulk (one mbarrier phase per piece), touching nothing: the
+// rate at which the copy engine alone can pull HBM into shared memory.  The streaming SpMV sizes its
+// pieces from this measurement (profiles/tma_piece_size_r02.txt).
+__global__ void __launch_bounds__(512, 1) k_diag_tma_stream(const unsigned char *src, long long per_warp, int piece, int slots, int reps) {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    const int nw = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(dyn_smem);
+    unsigned char *buf = dyn_smem + 1024 + (size_t)wid * slots * piece;
+    uint64_t *bar = bars + wid * slots;
+    if (lane == 0) {
+        for (int i = 0; i < slots; ++i) mbar_init(bar + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (lane != 0) return;
+    const unsigned char *mine = src + ((size_t)blockIdx.x * nw + wid) * (size_t)per_warp;
+    const int np = (int)(per_warp / piece);
+    unsigned g = 0;                                              // pieces waited so far
+    for (int rep = 0; rep < reps; ++rep) {
+        int issued = 0;
+        for (; issued < np && issued < slots; ++issued) {
+            const unsigned sl = (g + issued) % slots;
+            mbar_expect_tx(bar + sl, piece);
+            bulk_g2s(buf + (size_t)sl * piece, mine + (size_t)issued * piece, piece, bar + sl);
+        }
+        for (int p = 0; p < np; ++p, ++g) {
+            const unsigned sl = g % slots;
+            mbar_wait(bar + sl, (g / slots) & 1u);
+            if (issued < np) {
+                mbar_expect_tx(bar + sl, piece);
+                bulk_g2s(buf + (size_t)sl * piece, mine + (size_t)issued * piece, piece, bar + sl);
+                ++issued;
+            }
+        }
+    }
+}
+
+extern "C" int32_t nupgcm_diag_tma_stream(nupgcm_ctx *ctx, int64_t total_bytes, int32_t piece, int32_t slots,
+                                          int32_t warps, int32_t reps, float *gb_per_s) {
+    NUPGCM_REQUIRE(nullptr, ctx, "ctx is NULL");
+    NUPGCM_REQUIRE(ctx, piece >= 16 && piece % 16 == 0 && slots >= 1 && slots <= 32 && warps >= 1 && warps <= 16 &&
+                            reps >= 1 && gb_per_s && total_bytes > 0, "diag_tma_stream: bad argument");
+    const size_t smem = 1024 + (size_t)warps * slots * piece;
+    NUPGCM_REQUIRE(ctx, smem <= 227 * 1024 && (size_t)warps * slots * 8 <= 1024, "diag_tma_stream: does not fit in shared memory");
+    NUPGCM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int grid = ctx->coop_grid;
+    long long per_warp = total_bytes / ((long long)grid * warps) / piece * piece;
+    NUPGCM_REQUIRE(ctx, per_warp >= piece, "diag_tma_stream: total_bytes too small");
+    unsigned char *src = nullptr;
+    NUPGCM_CUDA(ctx, cudaMalloc(&src, (size_t)per_warp * grid * warps));
+    NUPGCM_CUDA(ctx, cudaMemsetAsync(src, 1, (size_t)per_warp * grid * warps, ctx->stream));
+    NUPGCM_CUDA(ctx, cudaFuncSetAttribute((const void *)k_diag_tma_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_diag_tma_stream<<<grid, 32 * warps, smem, ctx->stream>>>(src, per_warp, piece, slots, 1);     // warm-up
+    NUPGCM_CUDA(ctx, cudaEventRecord(ctx->sev0, ctx->stream));
+    k_diag_tma_stream<<<grid, 32 * warps, smem, ctx->stream>>>(src, per_warp, piece, slots, reps);
+    NUPGCM_CUDA(ctx, cudaEventRecord(ctx->sev1, ctx->stream));
+    ctx->launches += 2;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(src);
+    NUPGCM_CUDA(ctx, e);
+    float ms = 0.f;
+    NUPGCM_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->sev0, ctx->sev1));
+    *gb_per_s = (float)((double)per_warp * grid * warps * reps / (ms * 1e-3) / 1e9);
     return NUPGCM_OK;
 }
 

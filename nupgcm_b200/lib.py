@@ -78,7 +78,9 @@ SIGNATURES = {
     "nupgcm_csr_inv_diag": [_P, _P],
     "nupgcm_rcm_order": [c_int64, _ip, _ip, c_int32, _ip],
     "nupgcm_shard_plan": [c_int64, _ip, _ip, c_int32, c_int32, c_int32, _ip, _ip, _ip, _ip],
-    "nupgcm_diag_stream_spmv_host": [c_int64, _ip, _ip, _dp, _dp, c_int32, c_int32, c_int32, _dp, _ip, _ip],
+    "nupgcm_diag_stream_spmv_host": [c_int64, _ip, _ip, _dp, _dp, c_int32, c_int32, _dp, _ip, _ip],
+    "nupgcm_diag_stream_spmv": [_P, _P, _P, c_int32, c_int32, POINTER(c_float)],
+    "nupgcm_diag_tma_stream": [_P, c_int64, c_int32, c_int32, c_int32, c_int32, POINTER(c_float)],
     "nupgcm_spmv": [_P, _P, _P, c_double, c_double],
     "nupgcm_cg_solve": [_P, _P, c_double, _P, _P, c_double, c_double, c_int64, _dp, c_int64,
                         POINTER(SolveStats)],
@@ -210,6 +212,13 @@ class Context:
         us = c_float()
         _check(self.lib.nupgcm_diag_pingpong(self.h, peer, variant, reps, byref(us)), self.h)
         return us.value
+
+    def tma_stream(self, total_bytes, piece, slots, warps, reps=3) -> float:
+        """GB/s of bulk copies of `piece` bytes, `slots` in flight per warp, `warps` warps per CTA."""
+        out = c_float()
+        _check(self.lib.nupgcm_diag_tma_stream(self.h, int(total_bytes), int(piece), int(slots), int(warps),
+                                               int(reps), C.byref(out)), self.h)
+        return float(out.value)
 
     def launch_count(self) -> int:
         n = c_int64()
@@ -440,6 +449,12 @@ class CsrMatrix:
         _check(self.lib.nupgcm_csr_inv_diag(self.h, out.h), self.ctx.h)
         return out
 
+    def stream_spmv(self, x: Vector, y: Vector, reps=1, mode=0) -> float:
+        """``y = A x`` by the persistent solvers' streaming SpMV engine alone; µs per product."""
+        us = c_float()
+        _check(self.lib.nupgcm_diag_stream_spmv(self.h, x.h, y.h, int(reps), int(mode), C.byref(us)), self.ctx.h)
+        return float(us.value)
+
     def spmv(self, x: Vector, y: Vector, alpha=1.0, beta=0.0):
         _check(self.lib.nupgcm_spmv(self.h, x.h, y.h, float(alpha), float(beta)), self.ctx.h)
         return y
@@ -456,7 +471,7 @@ def rcm_order(mat):
     return out
 
 
-def stream_spmv_host(mat, x, grid: int = 148, T: int = 8, fmax: int = 4096):
+def stream_spmv_host(mat, x, grid: int = 148, fmax: int = 2560):
     """Host-only: ``y = mat @ x`` computed by walking the streaming-SpMV tables the persistent
     kernels use (``nupgcm_diag_stream_spmv_host``).  Returns ``(y, n_tiles, n_stream_entries)``."""
     import scipy.sparse as sp
@@ -468,7 +483,7 @@ def stream_spmv_host(mat, x, grid: int = 148, T: int = 8, fmax: int = 4096):
     y = np.empty(m.shape[0])
     nt, ne = np.zeros(1, dtype=np.int64), np.zeros(1, dtype=np.int64)
     _check(load().nupgcm_diag_stream_spmv_host(m.shape[0], _ptr(rowptr, _ip), _ptr(col, _ip), _ptr(vals),
-                                               _ptr(xv), int(grid), int(T), int(fmax), _ptr(y),
+                                               _ptr(xv), int(grid), int(fmax), _ptr(y),
                                                _ptr(nt, _ip), _ptr(ne, _ip)))
     return y, int(nt[0]), int(ne[0])
 

@@ -23,7 +23,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--level", type=int, default=1)
     ap.add_argument("--iters", type=int, default=400)
-    ap.add_argument("--fmax", type=int, nargs="*", default=[4096])
+    ap.add_argument("--fmax", type=int, nargs="*", default=[2560])
     ap.add_argument("--orth", nargs="*", default=["mgs", "cgs2f"])
     ap.add_argument("--no-spmv", action="store_true")
     args = ap.parse_args()
