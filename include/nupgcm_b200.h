@@ -232,20 +232,26 @@ int32_t nupgcm_gmres_solve_prec(const nupgcm_csr *A, nupgcm_blockprec *M, const 
                                 nupgcm_solve_stats *stats);
 
 /* diagnostics, host only (no device needed): y = A x computed by walking the streaming-SpMV tables
- * (tiles, footprints, per-warp streams of jagged-diagonal slices) that nupgcm_csr_prepare builds for
- * `grid` CTAs, exactly as the persistent kernels walk them; 0-based CSR as given, fmax = footprint cap
- * (<= 8192).  Fails if any row is not produced exactly once.  Used by the CPU tests of the table builder. */
+ * (tiles, footprints staged in an arena of `arena` entries, per-warp streams of jagged-diagonal slices)
+ * that nupgcm_csr_prepare builds for `grid` CTAs, exactly as the persistent kernels walk them; 0-based
+ * CSR as given.  Fails if any row is not produced exactly once or an arena slot is reused too early.
+ * gather_wavefronts / positions: shared-memory wavefronts the vector gathers need (2 per position when
+ * free of bank conflicts).  Used by the CPU tests of the table builder. */
 int32_t nupgcm_diag_stream_spmv_host(int64_t n, const int64_t *rowptr, const int64_t *colidx,
                                      const double *vals, const double *x, int32_t grid,
-                                     int32_t fmax, double *y, int64_t *n_tiles, int64_t *n_entries);
+                                     int32_t arena, double *y, int64_t *n_tiles, int64_t *n_entries,
+                                     int64_t *gather_wavefronts, int64_t *positions);
 
 /* diagnostics: y = A x computed `reps` times by the STREAMING SpMV engine of the persistent solvers
  * alone (same tables, CTAs and warp roles, no grid-wide wait); reports the average device time of one
  * product.  mode 0 = the real product; 1 = pieces pulled through the rings untouched (copy pipeline
- * only), 2 = no footprint gather (timing experiments; y is then meaningless).  Fails when the matrix is
+ * only), 2 = no footprint gather (timing experiments; y is then meaningless), 3 = the real product with
+ * per-warp activity clocks: warp_cycles[148 CTAs][11 warps][8] receives SM cycles per product spent
+ * waiting for the footprint / for ring pieces / in table loads and bookkeeping / in full positions / in
+ * the jagged ends / in the row callback / at the closing CTA barrier.  Fails when the matrix is
  * SM-resident (no streaming tables). */
 int32_t nupgcm_diag_stream_spmv(nupgcm_csr *A, const nupgcm_vec *x, nupgcm_vec *y, int32_t reps,
-                                int32_t mode, float *us_per_spmv);
+                                int32_t mode, float *us_per_spmv, double *warp_cycles);
 
 /* diagnostics: GB/s at which cp.async.bulk alone pulls `total_bytes` of HBM into shared memory when
  * every one of `warps` warps per CTA (one CTA per SM) keeps `slots` copies of `piece` bytes in flight. */

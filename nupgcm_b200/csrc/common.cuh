@@ -11,7 +11,6 @@
 
 struct NupgcmTileDesc;
 struct NupgcmWarpDesc;
-struct NupgcmTileWarp;
 struct NupgcmSlice;
 
 // -------------------------------------------------------------------------------------------
@@ -120,12 +119,11 @@ struct nupgcm_csr {
     NupgcmTileDesc *d_tiles;       // tiles of this rank's CTAs
     int32_t *d_tile_ptr;           // [grid_per_rank+1]
     NupgcmWarpDesc *d_wdesc;       // [grid_per_rank][kMainWarps]
-    NupgcmTileWarp *d_tw;          // [tiles][kMainWarps]
     NupgcmSlice *d_slices;         // slice tables of all warps
     int32_t *d_srow;               // row tables: internal row ids ...
     int32_t *d_slen;               //             ... and row lengths, in slice order
     int32_t *d_sfoot;              // footprints of all tiles (internal column ids, sorted per tile)
-    int str_T, str_fmax, str_max_rows;   // lanes per row, footprint cap and largest row block of the tables (0: none)
+    int str_T, str_fmax, str_max_rows;   // str_fmax: largest tile footprint of the tables (0: no tables); largest row block
     long long svals_version;
     // sharded solves: the communicator, and for every peer the range of THIS rank's rows that the
     // peer's SpMV gathers (bounding range of the peer's column footprint inside this rank's block)
@@ -173,24 +171,30 @@ struct nupgcm_mesh {
 
 // ---- streaming SpMV tables ------------------------------------------------------------------
 // A CTA whose matrix slice does not fit in shared memory walks its rows tile by tile.  A tile is a
-// run of consecutive rows whose distinct columns (its "footprint") number at most str_fmax: the
-// footprint entries of the multiplied vector are staged in shared memory once per tile and every
-// matrix entry carries a 16-bit BYTE offset into that staging buffer instead of a 32-bit column.
-// Inside a tile the rows are sorted by decreasing length and cut into slices of 32 rows, one row
-// per lane; a slice is stored in jagged-diagonal order (entry j of every row that has one, rows in
-// slice order, then entry j+1, ...): consecutive lanes read consecutive addresses, there is no
-// padding, no cross-lane reduction and no divergence beyond the last few positions.  Slices are
-// dealt to the kMainWarps solver warps (least-loaded first), so every warp owns ONE contiguous
-// entry stream per CTA — values and 16-bit offsets — which it pulls through a private
+// run of kTileRows consecutive rows — one slice of 32 rows for each of the kMainWarps solver warps.
+// The entries of the multiplied vector a tile touches (its "footprint", the distinct columns of its
+// rows) are staged in a shared-memory arena by the comm warps, several tiles ahead of the solver
+// warps, and every matrix entry carries a 16-bit BYTE offset into its tile's staged footprint instead
+// of a 32-bit column.  Inside a tile the rows are sorted by decreasing length and cut into slices of
+// 32 rows, one row per lane, stored in jagged-diagonal order (position j of every row that has one,
+// rows in slice order, then position j+1, ...): consecutive lanes read consecutive addresses, no
+// padding, no cross-lane reduction, no divergence beyond the last few positions.  WHICH entry of a row
+// sits at which position is free, and chosen so that the 16 lanes of a half-warp hit 16 different
+// shared-memory banks when they gather the vector (round-2 profile: random placement cost 22 of 78 us
+// in bank conflicts).  Slice s of tile t belongs to warp (s + t) mod kMainWarps, so every warp owns ONE
+// contiguous entry stream per CTA — values and 16-bit offsets — which it pulls through a private
 // shared-memory ring with TMA bulk copies of kPieceEntries entries.
 static const int kMainWarps = 11;      // solver warps of the persistent kernels (krylov.cu)
 static const int kPieceEntries = 512;  // entries per TMA piece: 4 KB of values + 1 KB of offsets (sized from
                                        // profiles/tma_piece_size_r02.txt: >= 2 KB copies reach the HBM rate)
 static const int kRingPieces = 3;      // pieces per warp ring
+static const int kTileRows = 32 * kMainWarps;   // rows per tile (times a multiplier when a CTA would exceed kMaxTiles)
+static const int kMaxTiles = 64;       // tiles per CTA: one pair of mbarriers each
+static const int kArenaEntries = 6656; // staged footprint entries in flight (52 KB next to 165 KB of rings)
 
-struct NupgcmTileDesc { int32_t row0, nrows, foot_off, foot_len; };
+struct NupgcmTileDesc { int32_t row0, nrows, foot_off, foot_len, xs_off, dep, pad0, pad1; };   // xs_off: arena offset (entries);
+                                       // dep: tile of the same CTA that must be finished before this one is staged (-1: none)
 struct NupgcmWarpDesc { int32_t estart, elen, stab, rtab; };    // stream start (multiple of 8) / length, slice and row table offsets
-struct NupgcmTileWarp { int32_t sbeg, nsl; };                   // slices of one warp in one tile (relative to stab)
 struct NupgcmSlice { int32_t eoff, roff, nrows, lmax; };        // entry offset in the warp's stream, rows (relative to rtab), longest row
 
 static const int kPartialSlots = 24;   // >= memory+2 of GMRES

@@ -7,7 +7,9 @@
 // evolution matrix: ~23 per row -> T = 4).  Summation order inside a row is fixed (lane-strided
 // partial sums, then an xor-shuffle tree), so results are run-to-run reproducible.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -199,107 +201,203 @@ static void permute_structure(int64_t n, const int32_t *rowptr, const int32_t *c
 
 // ---- streaming SpMV tables (common.cuh) ------------------------------------------------------
 // Built for the CTAs [cta0, cta0 + ncta) of the partition (this rank's CTAs).  Returns false when a
-// single row touches more than fmax distinct columns (then the solvers fall back to direct loads).
+// tile's footprint does not fit the arena / 16-bit offsets (then the solvers fall back to direct loads).
 struct StreamTables {
     std::vector<NupgcmTileDesc> tiles;
     std::vector<int32_t> tile_ptr;
     std::vector<NupgcmWarpDesc> wdesc;
-    std::vector<NupgcmTileWarp> tw;
     std::vector<NupgcmSlice> slices;
     std::vector<int32_t> srow, slen, foot, ssrc;
     std::vector<uint16_t> scols;
+    int max_foot = 0;
 };
 
+// Which bank pair does lane q of a half-warp read at one slice position?  avail[q] = bank pairs in which
+// row q still has entries, size[q][b] = how many.  Maximum bipartite matching lanes <-> banks (Kuhn's
+// augmenting paths, fullest bucket first), so that as many lanes as possible gather from distinct banks;
+// lanes left over take their fullest bucket.
+static void assign_banks(int nl, const uint16_t *avail, const int (*size)[16], int *choice) {
+    int owner[16];
+    for (int b = 0; b < 16; ++b) owner[b] = -1;
+    struct Rec {
+        const uint16_t *avail; const int (*size)[16]; int *owner; uint16_t seen;
+        bool go(int q) {
+            uint16_t cand = avail[q] & (uint16_t)~seen;
+            while (cand) {
+                int best = -1;
+                for (uint16_t m = cand; m; m &= (uint16_t)(m - 1)) {
+                    const int b = __builtin_ctz(m);
+                    if (best < 0 || size[q][b] > size[q][best]) best = b;
+                }
+                cand &= (uint16_t)~(1u << best);
+                seen |= (uint16_t)(1u << best);
+                if (owner[best] < 0 || go(owner[best])) { owner[best] = q; return true; }
+            }
+            return false;
+        }
+    } rec{avail, size, owner, 0};
+    for (int q = 0; q < nl; ++q) {
+        choice[q] = -1;
+        if (!avail[q]) continue;
+        rec.seen = 0;
+        rec.go(q);
+    }
+    for (int b = 0; b < 16; ++b)
+        if (owner[b] >= 0) choice[owner[b]] = b;
+    for (int q = 0; q < nl; ++q)
+        if (choice[q] < 0 && avail[q]) {
+            int best = -1;
+            for (uint16_t m = avail[q]; m; m &= (uint16_t)(m - 1)) {
+                const int b = __builtin_ctz(m);
+                if (best < 0 || size[q][b] > size[q][best]) best = b;
+            }
+            choice[q] = best;
+        }
+}
+
+// Tables of one CTA (rows [ra, rb)): tiles, footprints and the kMainWarps entry streams.
+struct CtaStream {
+    std::vector<NupgcmTileDesc> tiles;             // foot_off relative to `foot`
+    std::vector<int32_t> foot;
+    std::vector<NupgcmSlice> wsl[kMainWarps];
+    std::vector<int32_t> wrow[kMainWarps], wlen[kMainWarps], wsrc[kMainWarps];
+    std::vector<uint16_t> wcols[kMainWarps];
+    int max_foot = 0;
+    bool ok = true;
+};
+
+static void build_cta_stream(const int32_t *rowptr, const int32_t *col, int32_t ra, int32_t rb, int arena,
+                             std::vector<int32_t> &mark, std::vector<int32_t> &loc_of, int32_t &stamp, CtaStream &cs) {
+    const int W = kMainWarps;
+    // rows per tile: kTileRows, doubled until the CTA needs at most kMaxTiles tiles
+    int tile_rows = kTileRows;
+    while ((int64_t)(rb - ra) > (int64_t)tile_rows * kMaxTiles) tile_rows *= 2;
+    std::vector<int32_t> tile_cols, order;
+    int32_t arena_pos = 0;
+    int tix = 0;
+    for (int32_t start = ra; start < rb; start += tile_rows, ++tix) {
+        const int32_t r_end = std::min(rb, start + tile_rows);
+        ++stamp;
+        tile_cols.clear();
+        for (int32_t k = rowptr[start]; k < rowptr[r_end]; ++k)
+            if (mark[col[k]] != stamp) { mark[col[k]] = stamp; tile_cols.push_back(col[k]); }
+        if ((int)tile_cols.size() > arena || tile_cols.size() > 8192) { cs.ok = false; return; }
+        std::sort(tile_cols.begin(), tile_cols.end());
+        for (size_t i = 0; i < tile_cols.size(); ++i) loc_of[tile_cols[i]] = (int32_t)i;
+        cs.max_foot = std::max(cs.max_foot, (int)tile_cols.size());
+        // arena slot: first fit going round; `dep` = the youngest earlier tile whose slot it overlaps
+        const int32_t flen = ((int32_t)tile_cols.size() + 15) & ~15;
+        if (arena_pos + flen > arena) arena_pos = 0;
+        int32_t dep = -1;
+        for (int u = (int)cs.tiles.size() - 1; u >= 0; --u) {
+            const int32_t a0 = cs.tiles[u].xs_off, a1 = a0 + ((cs.tiles[u].foot_len + 15) & ~15);
+            if (a0 < arena_pos + flen && arena_pos < a1) { dep = u; break; }
+        }
+        while (cs.foot.size() % 4) cs.foot.push_back(0);
+        cs.tiles.push_back(NupgcmTileDesc{start, r_end - start, (int32_t)cs.foot.size(), (int32_t)tile_cols.size(),
+                                          arena_pos, dep, 0, 0});
+        arena_pos += flen;
+        cs.foot.insert(cs.foot.end(), tile_cols.begin(), tile_cols.end());
+        // rows by decreasing length (ties by row id), cut into slices of 32; slice s -> warp (s + tile) mod W
+        order.resize(r_end - start);
+        for (int32_t i = 0; i < r_end - start; ++i) order[i] = start + i;
+        std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
+            return rowptr[x + 1] - rowptr[x] > rowptr[y + 1] - rowptr[y];
+        });
+        int sidx = 0;
+        for (size_t i = 0; i < order.size(); i += 32, ++sidx) {
+            const int nr = (int)std::min<size_t>(32, order.size() - i);
+            const int w = (sidx + tix) % W;
+            const int lmax = rowptr[order[i] + 1] - rowptr[order[i]];
+            cs.wsl[w].push_back(NupgcmSlice{(int32_t)cs.wcols[w].size(), (int32_t)cs.wrow[w].size(), nr, lmax});
+            // per row: its entries bucketed by the bank pair (position in the staged footprint mod 16)
+            std::vector<int32_t> bucket[32][16];
+            int left[32], size[32][16];
+            uint16_t avail[32];
+            for (int q = 0; q < nr; ++q) {
+                const int32_t row = order[i + q];
+                cs.wrow[w].push_back(row);
+                cs.wlen[w].push_back(rowptr[row + 1] - rowptr[row]);
+                left[q] = rowptr[row + 1] - rowptr[row];
+                for (int32_t k = rowptr[row + 1] - 1; k >= rowptr[row]; --k) bucket[q][loc_of[col[k]] & 15].push_back(k);
+                avail[q] = 0;
+                for (int bk = 0; bk < 16; ++bk) {
+                    size[q][bk] = (int)bucket[q][bk].size();
+                    if (size[q][bk]) avail[q] |= (uint16_t)(1u << bk);
+                }
+            }
+            // jagged-diagonal order, bank-aware: see assign_banks
+            for (int j = 0; j < lmax; ++j) {
+                int cnt = 0;
+                while (cnt < nr && left[cnt] > 0) ++cnt;            // rows are sorted: lanes 0 .. cnt-1 hold position j
+                int choice[32];
+                assign_banks(std::min(cnt, 16), avail, size, choice);
+                if (cnt > 16) assign_banks(cnt - 16, avail + 16, size + 16, choice + 16);
+                for (int q = 0; q < cnt; ++q) {
+                    const int bk = choice[q];
+                    const int32_t k = bucket[q][bk].back();
+                    bucket[q][bk].pop_back();
+                    if (--size[q][bk] == 0) avail[q] &= (uint16_t)~(1u << bk);
+                    --left[q];
+                    cs.wcols[w].push_back((uint16_t)(8 * loc_of[col[k]]));
+                    cs.wsrc[w].push_back(k);
+                }
+            }
+        }
+    }
+}
+
 static bool build_stream_tables(const int32_t *rowptr, const int32_t *col, int64_t n_cols,
-                                const std::vector<int32_t> &part, int cta0, int ncta, int fmax,
+                                const std::vector<int32_t> &part, int cta0, int ncta, int arena,
                                 StreamTables &st) {
     const int W = kMainWarps;
     st.tile_ptr.assign(ncta + 1, 0);
     st.wdesc.assign((size_t)ncta * W, NupgcmWarpDesc{0, 0, 0, 0});
-    std::vector<int32_t> mark(n_cols, -1), loc_of(n_cols, 0), tile_cols, order;
-    int32_t stamp = 0;
+    // the CTAs are independent: build them on all host cores, then concatenate in order
+    std::vector<CtaStream> ctas(ncta);
+    unsigned nthreads = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+    if (const char *e = getenv("NUPGCM_HOST_THREADS")) nthreads = (unsigned)std::max(1, atoi(e));
+    nthreads = std::min<unsigned>(nthreads, (unsigned)std::max(1, ncta));
+    std::atomic<int> next(0);
+    auto worker = [&]() {
+        std::vector<int32_t> mark(n_cols, -1), loc_of(n_cols, 0);
+        int32_t stamp = 0;
+        for (int b = next.fetch_add(1); b < ncta; b = next.fetch_add(1))
+            build_cta_stream(rowptr, col, part[cta0 + b], part[cta0 + b + 1], arena, mark, loc_of, stamp, ctas[b]);
+    };
+    std::vector<std::thread> pool;
+    for (unsigned i = 1; i < nthreads; ++i) pool.emplace_back(worker);
+    worker();
+    for (auto &t : pool) t.join();
     for (int b = 0; b < ncta; ++b) {
-        const int32_t ra = part[cta0 + b], rb = part[cta0 + b + 1];
-        std::vector<NupgcmTileDesc> ltiles;
-        std::vector<std::vector<NupgcmTileWarp>> wtw(W);
-        std::vector<std::vector<NupgcmSlice>> wsl(W);
-        std::vector<std::vector<int32_t>> wrow(W), wlen(W), wsrc(W);
-        std::vector<std::vector<uint16_t>> wcols(W);
-        for (int32_t start = ra; start < rb;) {
-            // grow the tile row by row while its footprint stays within fmax
-            ++stamp;
-            tile_cols.clear();
-            int32_t r = start;
-            for (; r < rb; ++r) {
-                const size_t before = tile_cols.size();
-                for (int32_t k = rowptr[r]; k < rowptr[r + 1]; ++k)
-                    if (mark[col[k]] != stamp) { mark[col[k]] = stamp; tile_cols.push_back(col[k]); }
-                if ((int)tile_cols.size() > fmax) {              // this row does not fit any more: undo it
-                    while (tile_cols.size() > before) { mark[tile_cols.back()] = -1; tile_cols.pop_back(); }
-                    break;
-                }
-            }
-            if (r == start) return false;                       // one row alone exceeds the footprint cap
-            std::sort(tile_cols.begin(), tile_cols.end());
-            for (size_t i = 0; i < tile_cols.size(); ++i) loc_of[tile_cols[i]] = (int32_t)i;
-            while (st.foot.size() % 4) st.foot.push_back(0);
-            ltiles.push_back(NupgcmTileDesc{start, r - start, (int32_t)st.foot.size(), (int32_t)tile_cols.size()});
-            st.foot.insert(st.foot.end(), tile_cols.begin(), tile_cols.end());
-            // rows by decreasing length (ties by row id), cut into slices of 32
-            order.resize(r - start);
-            for (int32_t i = 0; i < r - start; ++i) order[i] = start + i;
-            std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
-                return rowptr[x + 1] - rowptr[x] > rowptr[y + 1] - rowptr[y];
-            });
-            std::vector<NupgcmTileWarp> cur(W);
-            for (int w = 0; w < W; ++w) cur[w] = NupgcmTileWarp{(int32_t)wsl[w].size(), 0};
-            for (size_t i = 0; i < order.size(); i += 32) {
-                const int nr = (int)std::min<size_t>(32, order.size() - i);
-                int w = 0;                                       // least-loaded warp of the CTA so far
-                for (int v = 1; v < W; ++v)
-                    if (wcols[v].size() + 16 * wrow[v].size() < wcols[w].size() + 16 * wrow[w].size()) w = v;
-                const int lmax = rowptr[order[i] + 1] - rowptr[order[i]];
-                wsl[w].push_back(NupgcmSlice{(int32_t)wcols[w].size(), (int32_t)wrow[w].size(), nr, lmax});
-                for (int q = 0; q < nr; ++q) {
-                    wrow[w].push_back(order[i + q]);
-                    wlen[w].push_back(rowptr[order[i + q] + 1] - rowptr[order[i + q]]);
-                }
-                for (int j = 0; j < lmax; ++j)                   // jagged-diagonal order
-                    for (int q = 0; q < nr; ++q) {
-                        const int32_t row = order[i + q];
-                        if (rowptr[row + 1] - rowptr[row] <= j) break;      // rows are sorted: the rest is shorter
-                        const int32_t k = rowptr[row] + j;
-                        wcols[w].push_back((uint16_t)(8 * loc_of[col[k]]));
-                        wsrc[w].push_back(k);
-                    }
-                cur[w].nsl++;
-            }
-            for (int w = 0; w < W; ++w) wtw[w].push_back(cur[w]);
-            start = r;
-        }
+        CtaStream &cs = ctas[b];
+        if (!cs.ok) return false;
+        st.max_foot = std::max(st.max_foot, cs.max_foot);
         st.tile_ptr[b] = (int32_t)st.tiles.size();
-        for (size_t t = 0; t < ltiles.size(); ++t) {
-            st.tiles.push_back(ltiles[t]);
-            for (int w = 0; w < W; ++w) st.tw.push_back(wtw[w][t]);
-        }
+        while (st.foot.size() % 4) st.foot.push_back(0);
+        const int32_t fbase = (int32_t)st.foot.size();
+        for (NupgcmTileDesc td : cs.tiles) { td.foot_off += fbase; st.tiles.push_back(td); }
+        st.foot.insert(st.foot.end(), cs.foot.begin(), cs.foot.end());
         for (int w = 0; w < W; ++w) {
             while (st.scols.size() % 8) { st.scols.push_back(0); st.ssrc.push_back(-1); }   // 16-byte aligned streams
             NupgcmWarpDesc &d = st.wdesc[(size_t)b * W + w];
             d.estart = (int32_t)st.scols.size();
-            d.elen = (int32_t)wcols[w].size();
+            d.elen = (int32_t)cs.wcols[w].size();
             d.stab = (int32_t)st.slices.size();
             d.rtab = (int32_t)st.srow.size();
-            st.scols.insert(st.scols.end(), wcols[w].begin(), wcols[w].end());
-            st.ssrc.insert(st.ssrc.end(), wsrc[w].begin(), wsrc[w].end());
-            st.slices.insert(st.slices.end(), wsl[w].begin(), wsl[w].end());
-            st.srow.insert(st.srow.end(), wrow[w].begin(), wrow[w].end());
-            st.slen.insert(st.slen.end(), wlen[w].begin(), wlen[w].end());
+            st.scols.insert(st.scols.end(), cs.wcols[w].begin(), cs.wcols[w].end());
+            st.ssrc.insert(st.ssrc.end(), cs.wsrc[w].begin(), cs.wsrc[w].end());
+            st.slices.insert(st.slices.end(), cs.wsl[w].begin(), cs.wsl[w].end());
+            st.slices.push_back(NupgcmSlice{0, 0, 0, 0});       // the kernels read one slice header ahead
+            st.srow.insert(st.srow.end(), cs.wrow[w].begin(), cs.wrow[w].end());
+            st.slen.insert(st.slen.end(), cs.wlen[w].begin(), cs.wlen[w].end());
         }
+        cs = CtaStream();                                        // free as we go
     }
     st.tile_ptr[ncta] = (int32_t)st.tiles.size();
     // whole pieces are always copied: pad the tail
     for (int i = 0; i < kPieceEntries + 8; ++i) { st.scols.push_back(0); st.ssrc.push_back(-1); }
-    for (int i = 0; i < 32; ++i) { st.srow.push_back(0); st.slen.push_back(0); }
+    for (int i = 0; i < 64; ++i) { st.srow.push_back(0); st.slen.push_back(0); }
     return true;
 }
 
@@ -317,7 +415,6 @@ static void free_stream_tables(nupgcm_csr *A) {
     cudaFree(A->d_tiles); A->d_tiles = nullptr;
     cudaFree(A->d_tile_ptr); A->d_tile_ptr = nullptr;
     cudaFree(A->d_wdesc); A->d_wdesc = nullptr;
-    cudaFree(A->d_tw); A->d_tw = nullptr;
     cudaFree(A->d_slices); A->d_slices = nullptr;
     cudaFree(A->d_srow); A->d_srow = nullptr;
     cudaFree(A->d_slen); A->d_slen = nullptr;
@@ -469,21 +566,15 @@ int32_t nupgcm_csr_prepare(nupgcm_csr *A, int grid_per_rank) {
         const bool resident_fits = A->res_max_nnz > 0 && res_bytes <= 215 * 1024;
         if (A->n_rows == A->n_cols && kept > 0 && (resident_off || !resident_fits)) {
             const int me = nranks > 1 ? A->comm->rank : 0;
-            int fmax = 2560;                                     // two staging buffers of 20 KB next to 165 KB of rings
-            if (const char *ef = getenv("NUPGCM_STREAM_FMAX")) {
-                const int v = atoi(ef);
-                if (v >= 256 && v <= 3328) fmax = v & ~3;      // two buffers of fmax doubles must fit next to the rings
-            }
-            const int T = 8;
             StreamTables st;
-            if (build_stream_tables(A->h_prow, A->h_pcol, A->n_cols, part, me * grid_per_rank, grid_per_rank, fmax, st)) {
+            if (build_stream_tables(A->h_prow, A->h_pcol, A->n_cols, part, me * grid_per_rank, grid_per_rank, kArenaEntries, st)) {
+                const int T = 8, fmax = st.max_foot;
                 A->stream_entries = (int64_t)st.scols.size();
                 NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_scols, st.scols));
                 NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_ssrc, st.ssrc));
                 NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_tiles, st.tiles));
                 NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_tile_ptr, st.tile_ptr));
                 NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_wdesc, st.wdesc));
-                NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_tw, st.tw));
                 NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_slices, st.slices));
                 NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_srow, st.srow));
                 NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_slen, st.slen));
@@ -588,14 +679,15 @@ extern "C" int32_t nupgcm_csr_shard_info(nupgcm_csr *A, int32_t rank, int64_t *r
 
 // ---- C ABI --------------------------------------------------------------------------------
 // Host-only: y = A x computed by walking the streaming tables exactly as the persistent kernels do
-// (tiles, footprint staging, per-warp streams of jagged-diagonal slices), for `grid` CTAs on the
-// structure as given (no reordering).  Lets the CPU tests validate the table builder without a
-// device.  Also returns the number of tiles and of stream entries (padding included).
+// (tiles, footprints staged in the arena, per-warp streams of jagged-diagonal slices), for `grid` CTAs
+// on the structure as given (no reordering).  Lets the CPU tests validate the table builder without a
+// device.  Also returns the number of tiles, of stream entries (padding included) and the number of
+// shared-memory wavefronts the vector gathers of all positions need (2 per position = conflict-free).
 extern "C" int32_t nupgcm_diag_stream_spmv_host(int64_t n, const int64_t *rowptr, const int64_t *colidx,
                                                 const double *vals, const double *x, int32_t grid,
-                                                int32_t fmax, double *y, int64_t *n_tiles,
-                                                int64_t *n_entries) {
-    if (n < 1 || !rowptr || !colidx || !vals || !x || !y || grid < 1 || fmax < 4 || fmax > 8192)
+                                                int32_t arena, double *y, int64_t *n_tiles,
+                                                int64_t *n_entries, int64_t *gather_wavefronts, int64_t *positions) {
+    if (n < 1 || !rowptr || !colidx || !vals || !x || !y || grid < 1 || arena < 16 || arena % 16)
         return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "invalid argument: %s", "diag_stream_spmv_host");
     const int64_t nnz = rowptr[n];
     if (nnz < 0 || nnz >= INT32_MAX || n >= INT32_MAX)
@@ -605,43 +697,62 @@ extern "C" int32_t nupgcm_diag_stream_spmv_host(int64_t n, const int64_t *rowptr
     for (int64_t k = 0; k < nnz; ++k) col[k] = (int32_t)colidx[k];
     build_partition(rp, n, grid, part);
     StreamTables st;
-    if (!build_stream_tables(rp.data(), col.data(), n, part, 0, grid, fmax, st))
-        return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "invalid argument: %s", "a row exceeds the footprint cap");
+    if (!build_stream_tables(rp.data(), col.data(), n, part, 0, grid, arena, st))
+        return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "invalid argument: %s", "a tile's footprint exceeds the arena");
     std::vector<double> sv(st.scols.size());
     for (size_t i = 0; i < sv.size(); ++i) sv[i] = st.ssrc[i] >= 0 ? vals[st.ssrc[i]] : 0.0;
     for (int64_t i = 0; i < n; ++i) y[i] = std::nan("");         // every row must be written exactly once
-    std::vector<double> xs(fmax);
-    std::vector<int> written(n, 0);
+    std::vector<double> xs(arena);
+    std::vector<int> written(n, 0), owner(arena);
     const int W = kMainWarps;
+    int64_t waves = 0, npos = 0;
     for (int b = 0; b < grid; ++b) {
         std::vector<int64_t> walked(W, 0);                       // a warp's slices must tile its stream in order
-        for (int t = st.tile_ptr[b]; t < st.tile_ptr[b + 1]; ++t) {
-            const NupgcmTileDesc td = st.tiles[t];
-            if (td.foot_len > fmax) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "tile footprint exceeds the cap");
-            for (int i = 0; i < td.foot_len; ++i) xs[i] = x[st.foot[td.foot_off + i]];
+        std::vector<int> next_slice(W, 0);
+        std::fill(owner.begin(), owner.end(), -1);
+        const int nt = st.tile_ptr[b + 1] - st.tile_ptr[b];
+        if (nt > kMaxTiles) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "too many tiles in a CTA");
+        for (int tix = 0; tix < nt; ++tix) {
+            const NupgcmTileDesc td = st.tiles[st.tile_ptr[b] + tix];
+            if (td.xs_off % 16 || td.xs_off + td.foot_len > arena || td.dep >= tix)
+                return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "bad arena slot");
+            // staging tile tix overwrites its slot: every tile that still owns a part of it must be <= dep
+            for (int i = 0; i < td.foot_len; ++i) {
+                if (owner[td.xs_off + i] > td.dep) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "arena slot reused before its dependency");
+                owner[td.xs_off + i] = tix;
+                xs[td.xs_off + i] = x[st.foot[td.foot_off + i]];
+            }
+            const int nsl = (td.nrows + 31) / 32;
             for (int w = 0; w < W; ++w) {
                 const NupgcmWarpDesc wd = st.wdesc[(size_t)b * W + w];
-                const NupgcmTileWarp tw = st.tw[(size_t)t * W + w];
                 if (wd.estart % 8) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "misaligned stream");
-                for (int si = tw.sbeg; si < tw.sbeg + tw.nsl; ++si) {
-                    const NupgcmSlice sl = st.slices[(size_t)wd.stab + si];
+                const int first = ((w - tix) % W + W) % W;
+                for (int sidx = first; sidx < nsl; sidx += W) {
+                    const NupgcmSlice sl = st.slices[(size_t)wd.stab + next_slice[w]++];
                     if (sl.eoff != walked[w]) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "slices do not tile the stream");
                     const int32_t *rows = st.srow.data() + wd.rtab + sl.roff, *lens = st.slen.data() + wd.rtab + sl.roff;
                     double acc[32] = {0};
                     int64_t off = sl.eoff;
                     if (sl.nrows < 1 || sl.nrows > 32 || lens[0] != sl.lmax) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "bad slice header");
                     for (int j = 0; j < sl.lmax; ++j) {
-                        int cnt = 0;
+                        int cnt = 0, load[2][16] = {{0}};
                         for (int q = 0; q < sl.nrows; ++q) {
                             if (q + 1 < sl.nrows && lens[q] < lens[q + 1]) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "slice rows not sorted");
                             if (lens[q] > j) {
                                 const size_t e = (size_t)wd.estart + off + cnt;
                                 if (off + cnt >= wd.elen || st.scols[e] % 8 || st.scols[e] / 8 >= td.foot_len)
                                     return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "entry outside its stream or footprint");
-                                acc[q] += sv[e] * xs[st.scols[e] / 8];
+                                acc[q] += sv[e] * xs[td.xs_off + st.scols[e] / 8];
+                                load[q >> 4][(st.scols[e] / 8) & 15]++;
                                 ++cnt;
                             }
                         }
+                        for (int hw = 0; hw < 2; ++hw) {
+                            int mx = 0;
+                            for (int bk = 0; bk < 16; ++bk) mx = std::max(mx, load[hw][bk]);
+                            waves += mx;
+                        }
+                        ++npos;
                         off += cnt;
                     }
                     walked[w] = off;
@@ -660,6 +771,8 @@ extern "C" int32_t nupgcm_diag_stream_spmv_host(int64_t n, const int64_t *rowptr
         if (written[i] != 1) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "a row was not written exactly once");
     if (n_tiles) *n_tiles = (int64_t)st.tiles.size();
     if (n_entries) *n_entries = (int64_t)st.scols.size();
+    if (gather_wavefronts) *gather_wavefronts = waves;
+    if (positions) *positions = npos;
     return NUPGCM_OK;
 }
 

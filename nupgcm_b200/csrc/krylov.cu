@@ -32,6 +32,7 @@
 // the reader before its SpMV; reductions take two hops (CTA -> reducer CTA on the same GPU ->
 // every rank's arena); a solve ends with an all-gather of the solution.  See comm.cu and DESIGN.md §6.
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 
@@ -41,8 +42,8 @@ struct ResidentLayout {       // byte offsets into dynamic shared memory (all mu
     int vals, cols, xs, foot, rp, bar, vec, total;
     int vec_rows;             // row capacity of one vector slice (0: vectors stay in global memory)
     // streaming form (matrix does not fit on chip, common.cuh "streaming SpMV tables"): per-warp rings of
-    // kRingPieces x kPieceEntries entries, their mbarriers, and two footprint buffers of st_fmax doubles
-    int st_ring_v, st_ring_c, st_bars, st_xs, st_fmax;
+    // kRingPieces x kPieceEntries entries, the mbarriers, and the arena of staged footprints
+    int st_ring_v, st_ring_c, st_bars, st_xs;
     int streaming;            // 1: SpmvEngine<T,false> runs the tiled TMA streams described by st_*
 };
 
@@ -66,7 +67,6 @@ struct KrylovArgs {
     const NupgcmTileDesc *tiles;
     const int32_t *tile_ptr;
     const NupgcmWarpDesc *wdesc;
-    const NupgcmTileWarp *tw;
     const NupgcmSlice *slices;
     const int32_t *srow;
     const int32_t *slen;
@@ -489,7 +489,7 @@ __device__ __forceinline__ bool comm_mr(CommMailbox *mb, const KrylovArgs &a, LL
 // Service loop of the comm warps: one request per grid-wide reduction, until the main warps post
 // the exit request.
 __device__ __forceinline__ bool stream_gather_service(const KrylovArgs &a, unsigned char *smem, const double *xin,
-                                                      unsigned &tseq, unsigned long long *abort_word);
+                                                      unsigned &calls, unsigned long long *abort_word);
 
 template <bool MR = false>
 __device__ __forceinline__ void comm_warp_loop(CommMailbox *mb, const KrylovArgs &a, int nrep, unsigned char *smem = nullptr) {
@@ -498,13 +498,13 @@ __device__ __forceinline__ void comm_warp_loop(CommMailbox *mb, const KrylovArgs
     unsigned long long *abort_word = MR ? reinterpret_cast<unsigned long long *>(a.arena[a.rank]) : a.barrier + 1;
     const int grid = gridDim.x, gpad = (grid + 7) & ~7;
     const int ct = threadIdx.x - kMainThreads;
-    unsigned gen = 0, tseq = 0;
+    unsigned gen = 0, spmv_calls = 0;
     bool dead = false;
     for (;;) {
         named_sync(NUPGCM_BAR_REQ, kThreads);
         const int count = mb->count;
         if (count == kReqGather) {                               // streaming SpMV: stage the footprints, no response
-            if (!stream_gather_service(a, smem, mb->xin, tseq, abort_word)) mb->dead = 1;
+            if (!stream_gather_service(a, smem, mb->xin, spmv_calls, abort_word)) mb->dead = 1;
             continue;
         }
         if (count < 0) break;
@@ -772,66 +772,94 @@ struct SpmvEngine {
 
 // Streaming form (common.cuh "streaming SpMV tables"): the CTA's slice of the reordered matrix does not
 // fit on chip and is pulled from HBM every SpMV — by the copy engine, not by the threads:
-//   * every solver warp owns one contiguous stream of entries (values + 16-bit columns, no padding)
+//   * every solver warp owns one contiguous stream of entries (values + 16-bit offsets, no padding)
 //     and a private ring of kRingPieces x kPieceEntries entries in shared memory; lane 0 keeps the
 //     ring full with TMA bulk copies (one mbarrier phase per piece: a single arrive.expect_tx, then
-//     the value and the column copy).  Warps never synchronise with each other inside a tile, and the
-//     first pieces of the NEXT SpMV are already in flight when one ends (the matrix is immutable);
+//     the value and the offset copy).  Warps never synchronise with each other, and the first pieces
+//     of the NEXT SpMV are already in flight when one ends (the matrix is immutable);
 //   * the multiplied vector is read from shared memory: the comm warps, idle during an SpMV, stage
-//     the footprint of tile t+1 (one ld.cg gather per distinct column) into the second of two
-//     buffers while the solver warps work on tile t (full / empty mbarriers per buffer);
+//     the footprint of each tile (one ld.cg gather per distinct column) into an arena, as many tiles
+//     ahead of the solver warps as the arena holds (one full / one empty mbarrier per tile, each
+//     completing one phase per SpMV; the host plans the arena slots and which tile must be finished
+//     before a slot is overwritten);
 //   * a warp works through slices of 32 length-sorted rows in jagged-diagonal order, one row per lane:
-//     consecutive lanes read consecutive ring entries, no cross-lane reduction, and lanes only drop
-//     out over the last few positions of a slice.  (The first version of this engine processed CSR
-//     rows with groups of T lanes and spent 52 warp instructions per 32 entries on divergent unrolled
-//     row loops, ring-index arithmetic and shuffles — profiles/ncu_stream_spmv_r02.txt.)
+//     consecutive lanes read consecutive ring entries, no cross-lane reduction, lanes only drop out
+//     over the last few positions of a slice, and the table builder places entries so that the gather
+//     of a position is (nearly) free of bank conflicts.  (The first version of this engine processed
+//     CSR rows with groups of T lanes and spent 52 warp instructions per 32 entries on divergent
+//     unrolled row loops, ring-index arithmetic and shuffles; the second staged footprints in two
+//     buffers and lost 55 % of the solver warps' time to footprint waits, per-tile imbalance and bank
+//     conflicts — profiles/stream_spmv_history_r02.txt.)
 // f(row, (A xin)[row]) is called once per row, by one lane, in no particular order.
 struct StreamShared {                        // pointers into dynamic shared memory, same for all threads
     double *ring_v;                          // [kMainWarps][kRingEntries]
     uint16_t *ring_c;                        // [kMainWarps][kRingEntries]
     uint64_t *full;                          // [kMainWarps][kRingPieces]
-    uint64_t *xs_full, *xs_empty;            // [2] each
-    double *xs;                              // [2][st_fmax]
+    uint64_t *xs_full, *xs_empty;            // [kMaxTiles] each
+    double *xs;                              // arena, kArenaEntries
     __device__ __forceinline__ StreamShared(const ResidentLayout &L, unsigned char *smem) {
         ring_v = reinterpret_cast<double *>(smem + L.st_ring_v);
         ring_c = reinterpret_cast<uint16_t *>(smem + L.st_ring_c);
         full = reinterpret_cast<uint64_t *>(smem + L.st_bars);
         xs_full = full + kMainWarps * kRingPieces;
-        xs_empty = xs_full + 2;
+        xs_empty = xs_full + kMaxTiles;
         xs = reinterpret_cast<double *>(smem + L.st_xs);
     }
 };
 
-// Comm-warp side of one streaming SpMV: stage the footprint of every tile of this CTA.  `tseq` is the
-// running tile counter (buffer = tseq & 1), kept in step with the solver warps' copy.
+// Comm-warp side of one streaming SpMV: stage the footprint of every tile of this CTA.  `calls` counts
+// the SpMVs so far (every per-tile mbarrier completes one phase per SpMV: parity = calls & 1).  The
+// gathers are L2 round trips under full HBM load (2-4 us each): the work is cut into rounds of
+// kGatherU entries per thread, all of a round's loads are in flight together, and the column ids of
+// the NEXT round (of this or the next tile) are fetched while the current round's vector entries are
+// on their way, so a round costs one round trip instead of two dependent ones.
+static const int kGatherU = 12;
 __device__ __forceinline__ bool stream_gather_service(const KrylovArgs &a, unsigned char *smem, const double *xin,
-                                                      unsigned &tseq, unsigned long long *abort_word) {
+                                                      unsigned &calls, unsigned long long *abort_word) {
     const StreamShared sh(a.lay, smem);
     const int ct = threadIdx.x - kMainThreads;
     const int t0 = a.tile_ptr[blockIdx.x], t1 = a.tile_ptr[blockIdx.x + 1];
+    const unsigned par = calls & 1u;
     bool ok = true;
-    for (int t = t0; t < t1; ++t, ++tseq) {
-        const unsigned buf = tseq & 1u;
-        if (tseq >= 2) ok = mbar_wait(sh.xs_empty + buf, ((tseq >> 1) - 1u) & 1u, abort_word) && ok;
-        const NupgcmTileDesc td = a.tiles[t];
-        const int32_t *foot = a.sfoot + td.foot_off;
-        double *dst = sh.xs + (size_t)buf * a.lay.st_fmax;
-        constexpr int U = 8;
-        for (int base = ct; base < td.foot_len; base += U * kCommThreads) {
-            double xv[U];
+    constexpr int U = kGatherU, RND = kGatherU * kCommThreads;
+    // round cursor: tile `t`, entries [base, base + RND) of its footprint
+    int t = t0, base = 0;
+    NupgcmTileDesc td = a.tiles[t0];
+    int32_t idx[U];
+    auto load_idx = [&](int32_t *dst, const NupgcmTileDesc &d, int b) {
+        const int32_t *foot = a.sfoot + d.foot_off;
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = base + u * kCommThreads;
-                xv[u] = i < td.foot_len ? ld_cg(xin + __ldg(foot + i)) : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = base + u * kCommThreads;
-                if (i < td.foot_len) dst[i] = xv[u];
-            }
+        for (int u = 0; u < U; ++u) {
+            const int i = b + ct + u * kCommThreads;
+            dst[u] = i < d.foot_len ? __ldg(foot + i) : 0;
         }
-        mbar_arrive(sh.xs_full + buf);                           // release: the stores above
+    };
+    load_idx(idx, td, 0);
+    while (t < t1) {
+        if (base == 0 && td.dep >= 0) ok = mbar_wait(sh.xs_empty + td.dep, par, abort_word) && ok;
+        double xv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) xv[u] = ld_cg(xin + idx[u]);
+        // cursor of the next round, and its column ids
+        const NupgcmTileDesc cur = td;
+        const int cbase = base;
+        int nt = t, nbase = base + RND;
+        if (nbase >= td.foot_len) { nt = t + 1; nbase = 0; }
+        if (nt < t1) {
+            if (nt != t) td = a.tiles[nt];
+            load_idx(idx, td, nbase);
+        }
+        double *dst = sh.xs + cur.xs_off;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = cbase + ct + u * kCommThreads;
+            if (i < cur.foot_len) dst[i] = xv[u];
+        }
+        if (nt != t) mbar_arrive(sh.xs_full + (t - t0));         // the tile is complete (release: the stores above)
+        t = nt;
+        base = nbase;
     }
+    ++calls;
     return ok;
 }
 
@@ -856,7 +884,7 @@ struct SpmvEngine<T, false> {
     // (all lanes) and slot of the next issue (lane 0)
     int wslot, islot;
     unsigned wpar;
-    unsigned tseq;            // tiles consumed by earlier run() calls
+    unsigned calls;           // run() calls so far (parity of the per-tile mbarriers)
     bool failed;
 
     __device__ __forceinline__ void issue(int p) {                // lane 0 of the warp
@@ -876,15 +904,13 @@ struct SpmvEngine<T, false> {
         legacy = a.lay.streaming == 0;
         wslot = islot = 0;
         wpar = 0;
-        tseq = 0;
+        calls = 0;
         failed = false;
         if (legacy) return;
         const StreamShared sh(a.lay, smem);
-        if (threadIdx.x == 0) {
-            for (int i = 0; i < kMainWarps * kRingPieces; ++i) mbar_init(sh.full + i, 1);
-            for (int i = 0; i < 2; ++i) { mbar_init(sh.xs_full + i, kCommThreads); mbar_init(sh.xs_empty + i, kMainWarps); }
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
+        for (int i = threadIdx.x; i < kMainWarps * kRingPieces + 2 * kMaxTiles; i += blockDim.x)
+            mbar_init(sh.full + i, i < kMainWarps * kRingPieces ? 1 : (i < kMainWarps * kRingPieces + kMaxTiles ? kCommThreads : kMainWarps));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncthreads();
         t0 = a.tile_ptr[blockIdx.x];
         t1 = a.tile_ptr[blockIdx.x + 1];
@@ -914,7 +940,8 @@ struct SpmvEngine<T, false> {
     }
 
     // DBG (diagnostics only, nupgcm_diag_stream_spmv): 1 = pull the pieces through the ring without
-    // touching them, 2 = multiply by x[lane] instead of the gathered entry (no bank conflicts)
+    // touching them, 2 = multiply by x[lane] instead of the gathered entry (no bank conflicts),
+    // 3 = per-warp activity clocks
     template <int DBG = 0, class F>
     __device__ __forceinline__ void run(const double *xin, F &&f) {
         if (legacy) {
@@ -936,16 +963,23 @@ struct SpmvEngine<T, false> {
             return;
         }
         if (t0 == t1) return;                                    // a CTA without rows posts nothing (both roles know)
-        // ask the comm warps to stage the footprints of xin (no response: the buffers' mbarriers pace us)
+        long long tk[6] = {0, 0, 0, 0, 0, 0}, tlast = DBG == 3 ? clock64() : 0;   // DBG 3: cycles per activity
+        auto tick = [&](int k) { if (DBG == 3) { const long long now = clock64(); tk[k] += now - tlast; tlast = now; } };
+        // ask the comm warps to stage the footprints of xin (no response: the tiles' mbarriers pace us)
         if (threadIdx.x == 0) { mb->count = kReqGather; mb->xin = xin; }
         named_arrive(NUPGCM_BAR_REQ, kThreads);
         unsigned long long *abort_word = a.barrier + 1;
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        const unsigned par = calls & 1u;
         int rpos = wslot * kPieceEntries;                        // ring position of the next entry to consume
         int landed = 0;                                          // pieces of this call known to have arrived
         int issued = npieces < kRingPieces ? npieces : kRingPieces;
         auto ensure = [&](int need) {                            // entries [0, need) of the stream are in the ring
-            while (landed * kPieceEntries < need) { wait_piece(abort_word); ++landed; }
+            if (landed * kPieceEntries < need) {
+                tick(3);
+                do { wait_piece(abort_word); ++landed; } while (landed * kPieceEntries < need);
+                tick(1);
+            }
         };
         auto release = [&](int cons) {                           // entries [0, cons) are consumed: refill freed slots
             const int lim = min(npieces, kRingPieces + cons / kPieceEntries);
@@ -958,37 +992,41 @@ struct SpmvEngine<T, false> {
                 issued = lim;
             }
         };
+        const unsigned char *xt = xs;                            // staged footprint of the current tile
         auto entry = [&](int idx) -> double {                    // product of ring entry idx with its vector entry
             if (idx >= kRingEntries) idx -= kRingEntries;
-            const double xv = DBG == 2 ? *reinterpret_cast<const double *>(xs + 8 * lane)
-                                       : *reinterpret_cast<const double *>(xs + rc[idx]);
+            const double xv = DBG == 2 ? *reinterpret_cast<const double *>(xt + 8 * lane)
+                                       : *reinterpret_cast<const double *>(xt + rc[idx]);
             return rv[idx] * xv;
         };
-        for (int t = t0; t < t1; ++t, ++tseq) {
-            const NupgcmTileWarp tw = a.tw[(size_t)t * kMainWarps + wid];
-            const unsigned buf = tseq & 1u;
-            // the first slice's tables are fetched while the footprint is still being staged
-            NupgcmSlice sl = NupgcmSlice{0, 0, 0, 0};
-            int mylen = 0, myrow = -1;
-            if (tw.nsl > 0) {
-                sl = slices[tw.sbeg];
-                if (lane < sl.nrows) { mylen = __ldg(slen + sl.roff + lane); myrow = __ldg(srow + sl.roff + lane); }
-            }
-            if (!mbar_wait(xs_full + buf, (tseq >> 1) & 1u, abort_word)) failed = true;
-            const unsigned char *xsave = xs;
-            xs = xsave + (size_t)buf * a.lay.st_fmax * 8;
-            for (int si = 0; si < tw.nsl; ++si) {
+        // the first slice's tables are fetched before anything is waited for; then always one slice ahead
+        int si = 0;                                              // next slice of this warp's list
+        NupgcmSlice sl = slices[0];
+        int mylen = 0, myrow = -1;
+        if (lane < sl.nrows) { mylen = __ldg(slen + sl.roff + lane); myrow = __ldg(srow + sl.roff + lane); }
+        NupgcmTileDesc td = a.tiles[t0];
+        for (int tix = 0; tix < t1 - t0; ++tix) {
+            const int nsl = (td.nrows + 31) >> 5;
+            const int xs_off = td.xs_off;
+            if (tix + 1 < t1 - t0) td = a.tiles[t0 + tix + 1];   // next tile's descriptor: in flight during this one
+            int first = wid - tix % kMainWarps;
+            if (first < 0) first += kMainWarps;
+            tick(2);
+            if (!mbar_wait(xs_full + tix, par, abort_word)) failed = true;
+            tick(0);
+            xt = xs + (size_t)xs_off * 8;
+            for (int s = first; s < nsl; s += kMainWarps) {
                 const NupgcmSlice cs = sl;
                 const int clen = mylen, crow = myrow;
-                if (si + 1 < tw.nsl) {                           // next slice's tables: in flight during this one
-                    sl = slices[tw.sbeg + si + 1];
-                    mylen = 0;
-                    myrow = -1;
-                    if (lane < sl.nrows) { mylen = __ldg(slen + sl.roff + lane); myrow = __ldg(srow + sl.roff + lane); }
-                }
+                ++si;
+                sl = slices[si];                                 // (the table ends with a null slice)
+                mylen = 0;
+                myrow = -1;
+                if (lane < sl.nrows) { mylen = __ldg(slen + sl.roff + lane); myrow = __ldg(srow + sl.roff + lane); }
                 const int nr = cs.nrows;
                 const bool act = lane < nr;
                 const int lmin = __shfl_sync(0xffffffffu, clen, nr - 1);
+                tick(2);
                 int off = cs.eoff, j = 0;
                 double acc0 = 0.0, acc1 = 0.0;
                 // positions every row of the slice has: nr entries each, lane q reads entry q
@@ -1016,6 +1054,7 @@ struct SpmvEngine<T, false> {
                     if (rpos >= kRingEntries) rpos -= kRingEntries;
                     j = lmin;
                 }
+                tick(3);
                 // the jagged end: rows are sorted by length, so position j is held by lanes 0 .. cnt-1
                 for (; j < cs.lmax; ++j) {
                     const int cnt = __popc(__ballot_sync(0xffffffffu, clen > j));
@@ -1024,14 +1063,17 @@ struct SpmvEngine<T, false> {
                     off += cnt;
                     rpos += cnt;
                     if (rpos >= kRingEntries) rpos -= kRingEntries;
+                    release(off);                                // a long jagged end must keep the ring moving too
                 }
                 release(off);
+                tick(4);
                 if (act) f(crow, acc0 + acc1);
+                tick(5);
             }
-            xs = xsave;
             __syncwarp();
-            if (lane == 0) mbar_arrive(xs_empty + buf);
+            if (lane == 0) mbar_arrive(xs_empty + tix);
         }
+        ++calls;
         // this SpMV is done: start pulling the first pieces of the next one
         __syncwarp();
         if (lane == 0 && npieces > 0) {
@@ -1039,6 +1081,11 @@ struct SpmvEngine<T, false> {
             for (int p = 0; p < npieces && p < kRingPieces; ++p) issue(p);
         }
         if (failed) mb->dead = 1;
+        if (DBG == 3 && a.trace && lane == 0) {
+            tick(2);
+            unsigned long long *o = a.trace + ((size_t)blockIdx.x * kMainWarps + wid) * 8;
+            for (int k = 0; k < 6; ++k) o[k] += (unsigned long long)tk[k];
+        }
     }
 };
 
@@ -1913,9 +1960,8 @@ static ResidentLayout plan_streaming(const nupgcm_csr *A, bool gmres, int memory
     int off = 0;
     L.st_ring_v = off; off += kMainWarps * kRingEntries * 8;
     L.st_ring_c = off; off += kMainWarps * kRingEntries * 2;
-    L.st_bars = off;   off += ((kMainWarps * kRingPieces + 4) * 8 + 15) & ~15;
-    L.st_xs = off;     off += 2 * A->str_fmax * 8;
-    L.st_fmax = A->str_fmax;
+    L.st_bars = off;   off += ((kMainWarps * kRingPieces + 2 * kMaxTiles) * 8 + 15) & ~15;
+    L.st_xs = off;     off += kArenaEntries * 8;
     L.vec = off;
     const long long vec_bytes = (long long)(gmres ? memory + 1 : 5) * ((A->str_max_rows + 1) & ~1) * 8;
     if (off + vec_bytes <= limit) {
@@ -1996,7 +2042,6 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
     args.tiles = A->d_tiles;
     args.tile_ptr = A->d_tile_ptr;
     args.wdesc = A->d_wdesc;
-    args.tw = A->d_tw;
     args.slices = A->d_slices;
     args.srow = A->d_srow;
     args.slen = A->d_slen;
@@ -2137,7 +2182,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_diag_stream_spmv(const __grid_c
     }
     for (int rep = 0; rep < reps; ++rep) {
         eng.template run<DBG>(xi, [&](int row, double v) { y[a.perm[row]] = v; });
+        const long long tsync = DBG == 3 ? clock64() : 0;
         main_sync();
+        if (DBG == 3 && a.trace && (threadIdx.x & 31) == 0)
+            a.trace[((size_t)blockIdx.x * kMainWarps + (threadIdx.x >> 5)) * 8 + 6] += (unsigned long long)(clock64() - tsync);
     }
     if (threadIdx.x == 0) mailbox.count = kReqExit;
     named_arrive(NUPGCM_BAR_REQ, kThreads);
@@ -2146,12 +2194,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_diag_stream_spmv(const __grid_c
 }
 
 extern "C" int32_t nupgcm_diag_stream_spmv(nupgcm_csr *A, const nupgcm_vec *x, nupgcm_vec *y, int32_t reps,
-                                           int32_t mode, float *us_per_spmv) {
+                                           int32_t mode, float *us_per_spmv, double *warp_cycles) {
     NUPGCM_REQUIRE(nullptr, A && x && y, "diag_stream_spmv: NULL argument");
     nupgcm_ctx *ctx = A->ctx;
     NUPGCM_REQUIRE(ctx, A->n_rows == A->n_cols && x->n == A->n_rows && y->n == A->n_rows && x->d != y->d,
                    "diag_stream_spmv: square matrix and distinct vectors of its size");
-    NUPGCM_REQUIRE(ctx, reps >= 1 && mode >= 0 && mode <= 2 && !A->comm, "diag_stream_spmv: bad argument");
+    NUPGCM_REQUIRE(ctx, reps >= 1 && mode >= 0 && mode <= 3 && !A->comm && (mode != 3 || warp_cycles), "diag_stream_spmv: bad argument");
     NUPGCM_CUDA(ctx, cudaSetDevice(ctx->device));
     const int grid = ctx->coop_grid;
     int32_t rc = nupgcm_csr_prepare(A, grid);
@@ -2164,7 +2212,7 @@ extern "C" int32_t nupgcm_diag_stream_spmv(nupgcm_csr *A, const nupgcm_vec *x, n
     if (rc) return rc;
     args.rowptr = A->d_prow; args.colidx = A->d_pcol; args.vals = A->d_pvals; args.perm = A->d_perm; args.part = A->d_part;
     args.svals = A->d_svals; args.scols = A->d_scols; args.tiles = A->d_tiles; args.tile_ptr = A->d_tile_ptr;
-    args.wdesc = A->d_wdesc; args.tw = A->d_tw; args.slices = A->d_slices; args.srow = A->d_srow; args.slen = A->d_slen; args.sfoot = A->d_sfoot;
+    args.wdesc = A->d_wdesc; args.slices = A->d_slices; args.srow = A->d_srow; args.slen = A->d_slen; args.sfoot = A->d_sfoot;
     args.n = (int)A->n_rows;
     args.nranks = 1;
     args.barrier = ctx->d_barrier;
@@ -2172,7 +2220,15 @@ extern "C" int32_t nupgcm_diag_stream_spmv(nupgcm_csr *A, const nupgcm_vec *x, n
     NUPGCM_CUDA(ctx, cudaMemsetAsync(ctx->d_barrier, 0, 4 * sizeof(unsigned long long), ctx->stream));
     k_diag_permute_in<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->d_ws, x->d, A->d_perm, (int)A->n_rows);
     const void *fn;
-    fn = mode == 0 ? (const void *)k_diag_stream_spmv<8, 0> : mode == 1 ? (const void *)k_diag_stream_spmv<8, 1> : (const void *)k_diag_stream_spmv<8, 2>;
+    fn = mode == 0 ? (const void *)k_diag_stream_spmv<8, 0> : mode == 1 ? (const void *)k_diag_stream_spmv<8, 1>
+       : mode == 2 ? (const void *)k_diag_stream_spmv<8, 2> : (const void *)k_diag_stream_spmv<8, 3>;
+    unsigned long long *d_trace = nullptr;
+    const size_t trace_words = (size_t)grid * kMainWarps * 8;
+    if (mode == 3) {
+        NUPGCM_CUDA(ctx, cudaMalloc(&d_trace, trace_words * sizeof(unsigned long long)));
+        NUPGCM_CUDA(ctx, cudaMemsetAsync(d_trace, 0, trace_words * sizeof(unsigned long long), ctx->stream));
+    }
+    args.trace = d_trace;
     NUPGCM_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, args.lay.total));
     const double *xi = ctx->d_ws;
     double *yd = y->d;
@@ -2184,6 +2240,12 @@ extern "C" int32_t nupgcm_diag_stream_spmv(nupgcm_csr *A, const nupgcm_vec *x, n
     ctx->launches += 2;
     NUPGCM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     NUPGCM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (d_trace) {
+        std::vector<unsigned long long> h(trace_words);
+        cudaMemcpy(h.data(), d_trace, trace_words * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+        cudaFree(d_trace);
+        for (size_t i = 0; i < trace_words; ++i) warp_cycles[i] = (double)h[i] / reps;
+    }
     if (ctx->h_scalars[7] != 0.0) return nupgcm_fail(ctx, NUPGCM_ERR_CUDA, "%s", "diag_stream_spmv: a shared-memory pipeline wait timed out");
     float ms = 0.f;
     NUPGCM_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->sev0, ctx->sev1));

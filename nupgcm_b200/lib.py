@@ -78,8 +78,8 @@ SIGNATURES = {
     "nupgcm_csr_inv_diag": [_P, _P],
     "nupgcm_rcm_order": [c_int64, _ip, _ip, c_int32, _ip],
     "nupgcm_shard_plan": [c_int64, _ip, _ip, c_int32, c_int32, c_int32, _ip, _ip, _ip, _ip],
-    "nupgcm_diag_stream_spmv_host": [c_int64, _ip, _ip, _dp, _dp, c_int32, c_int32, _dp, _ip, _ip],
-    "nupgcm_diag_stream_spmv": [_P, _P, _P, c_int32, c_int32, POINTER(c_float)],
+    "nupgcm_diag_stream_spmv_host": [c_int64, _ip, _ip, _dp, _dp, c_int32, c_int32, _dp, _ip, _ip, _ip, _ip],
+    "nupgcm_diag_stream_spmv": [_P, _P, _P, c_int32, c_int32, POINTER(c_float), _dp],
     "nupgcm_diag_tma_stream": [_P, c_int64, c_int32, c_int32, c_int32, c_int32, POINTER(c_float)],
     "nupgcm_spmv": [_P, _P, _P, c_double, c_double],
     "nupgcm_cg_solve": [_P, _P, c_double, _P, _P, c_double, c_double, c_int64, _dp, c_int64,
@@ -452,8 +452,10 @@ class CsrMatrix:
     def stream_spmv(self, x: Vector, y: Vector, reps=1, mode=0) -> float:
         """``y = A x`` by the persistent solvers' streaming SpMV engine alone; µs per product."""
         us = c_float()
-        _check(self.lib.nupgcm_diag_stream_spmv(self.h, x.h, y.h, int(reps), int(mode), C.byref(us)), self.ctx.h)
-        return float(us.value)
+        cyc = np.zeros((148, 11, 8)) if mode == 3 else None
+        _check(self.lib.nupgcm_diag_stream_spmv(self.h, x.h, y.h, int(reps), int(mode), C.byref(us),
+                                                _ptr(cyc) if cyc is not None else None), self.ctx.h)
+        return (float(us.value), cyc) if mode == 3 else float(us.value)
 
     def spmv(self, x: Vector, y: Vector, alpha=1.0, beta=0.0):
         _check(self.lib.nupgcm_spmv(self.h, x.h, y.h, float(alpha), float(beta)), self.ctx.h)
@@ -471,9 +473,10 @@ def rcm_order(mat):
     return out
 
 
-def stream_spmv_host(mat, x, grid: int = 148, fmax: int = 2560):
+def stream_spmv_host(mat, x, grid: int = 148, arena: int = 6656):
     """Host-only: ``y = mat @ x`` computed by walking the streaming-SpMV tables the persistent
-    kernels use (``nupgcm_diag_stream_spmv_host``).  Returns ``(y, n_tiles, n_stream_entries)``."""
+    kernels use (``nupgcm_diag_stream_spmv_host``).  Returns ``(y, info)`` with the number of tiles,
+    stream entries, slice positions and shared-memory wavefronts of the vector gathers."""
     import scipy.sparse as sp
     m = sp.csr_matrix(mat)
     m.sort_indices()
@@ -481,11 +484,13 @@ def stream_spmv_host(mat, x, grid: int = 148, fmax: int = 2560):
     col = np.ascontiguousarray(m.indices, dtype=np.int64)
     vals, xv = _f64(m.data), _f64(x)
     y = np.empty(m.shape[0])
-    nt, ne = np.zeros(1, dtype=np.int64), np.zeros(1, dtype=np.int64)
+    out = np.zeros(4, dtype=np.int64)
     _check(load().nupgcm_diag_stream_spmv_host(m.shape[0], _ptr(rowptr, _ip), _ptr(col, _ip), _ptr(vals),
-                                               _ptr(xv), int(grid), int(fmax), _ptr(y),
-                                               _ptr(nt, _ip), _ptr(ne, _ip)))
-    return y, int(nt[0]), int(ne[0])
+                                               _ptr(xv), int(grid), int(arena), _ptr(y),
+                                               _ptr(out[0:], _ip), _ptr(out[1:], _ip), _ptr(out[2:], _ip),
+                                               _ptr(out[3:], _ip)))
+    return y, {"tiles": int(out[0]), "entries": int(out[1]), "gather_wavefronts": int(out[2]),
+               "positions": int(out[3])}
 
 
 def shard_plan(mat, nranks: int, grid_per_rank: int = 148):

@@ -68,11 +68,11 @@ def test_streaming_cg_matches_oracle(ctx):
     assert rel(x.download(), xo) < 1e-6
 
 
-@pytest.mark.parametrize("orth,name", [(lib.ORTH_MGS, "mgs"), (lib.ORTH_CGS2_FUSED, "cgs2f")])
-@pytest.mark.parametrize("fmax", ["512", "1536"])
-def test_forced_streaming_many_tiles_per_cta(ctx, orth, name, fmax):
-    """h=0.1 3-D inversion matrix through the streaming form with a tiny footprint cap: several tiles
-    per CTA, both footprint buffers and every ring slot are recycled many times per SpMV."""
+@pytest.mark.parametrize("orth,name,grid", [(lib.ORTH_MGS, "mgs", "4"), (lib.ORTH_MGS, "mgs", "148"),
+                                            (lib.ORTH_CGS2_FUSED, "cgs2f", "24"), (lib.ORTH_CGS2_FUSED, "cgs2f", "148")])
+def test_forced_streaming_many_tiles_per_cta(ctx, orth, name, grid):
+    """h=0.1 3-D inversion matrix through the streaming form on few CTAs: a dozen tiles per CTA, so the
+    footprint arena is gone round several times and every ring slot is recycled many times per SpMV."""
     _, ops = workload("bowl_mixing")
     A = ops["A"]
     rng = np.random.default_rng(5)
@@ -81,7 +81,7 @@ def test_forced_streaming_many_tiles_per_cta(ctx, orth, name, fmax):
     M = np.full(y.size, ops["pscale"])
     xo, so = krylov.gmres(A, y, x0=x0, M=M, atol=0.0, rtol=1e-30, memory=20, itmax=45, orth=name)
     os.environ["NUPGCM_RESIDENT"] = "0"
-    os.environ["NUPGCM_STREAM_FMAX"] = fmax
+    os.environ["NUPGCM_GRID"] = grid
     try:
         dA = ctx.csr(A, drop_zeros=True)
         runs = []
@@ -92,7 +92,7 @@ def test_forced_streaming_many_tiles_per_cta(ctx, orth, name, fmax):
             runs.append((hist.copy(), x.download()))
     finally:
         os.environ.pop("NUPGCM_RESIDENT")
-        os.environ.pop("NUPGCM_STREAM_FMAX")
+        os.environ.pop("NUPGCM_GRID")
     assert st.niter == 45
     assert np.allclose(runs[0][0], so.residuals, rtol=1e-9)
     assert rel(runs[0][1], xo) < 1e-9
@@ -108,12 +108,10 @@ def test_forced_streaming_cg_small_rows(ctx):
     dinv = 1.0 / A.diagonal()
     xo, so = krylov.cg(A, b, x0=np.zeros(b.size), M=dinv, atol=1e-10, rtol=1e-10)
     os.environ["NUPGCM_RESIDENT"] = "0"
-    os.environ["NUPGCM_STREAM_FMAX"] = "256"
     try:
         x = ctx.vector(b.size)
         st, hist = lib.cg_solve(ctx.csr(A), ctx.vector(b), x, dinv=ctx.vector(dinv), atol=1e-10, rtol=1e-10, history=512)
     finally:
         os.environ.pop("NUPGCM_RESIDENT")
-        os.environ.pop("NUPGCM_STREAM_FMAX")
     assert st.solved and abs(st.niter - so.niter) <= 1
     assert rel(x.download(), xo) < 1e-9

@@ -190,7 +190,6 @@ def test_inversion_3d_sharded_streaming_form(ctx):
     b = np.random.default_rng(4).uniform(-1, 1, A.shape[0])
     ps = ops["pscale"]
     os.environ["NUPGCM_RESIDENT"] = "0"
-    os.environ["NUPGCM_STREAM_FMAX"] = "1024"
     try:
         for orth in (lib.ORTH_CGS2_FUSED, lib.ORTH_MGS):
             def solve(c, dA):
@@ -207,7 +206,6 @@ def test_inversion_3d_sharded_streaming_form(ctx):
                 assert rel(x, ref[2]) < 1e-6
     finally:
         os.environ.pop("NUPGCM_RESIDENT")
-        os.environ.pop("NUPGCM_STREAM_FMAX")
 
 
 def test_model_steps_sharded_match_single_rank(ctx):

@@ -3,7 +3,7 @@ does not fit in shared memory): stand-alone SpMV, GMRES(20) per-iteration time f
 orthogonalisations, and the in-kernel phase split (CTA 0's clock: SpMV / local vector work /
 reduction wait / scalar recurrences).
 
-    python tools/stream_bench.py [--level 1] [--iters 400] [--fmax 4096 ...]
+    python tools/stream_bench.py [--level 1] [--iters 400] 
 """
 import argparse
 import os
@@ -23,7 +23,6 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--level", type=int, default=1)
     ap.add_argument("--iters", type=int, default=400)
-    ap.add_argument("--fmax", type=int, nargs="*", default=[2560])
     ap.add_argument("--orth", nargs="*", default=["mgs", "cgs2f"])
     ap.add_argument("--no-spmv", action="store_true")
     args = ap.parse_args()
@@ -39,8 +38,7 @@ def main():
     n = A.shape[0]
     print(f"== h = {0.08 / 2 ** args.level:g}: N = {n}, nnz stored {A.nnz} (host set-up {time.time() - t0:.1f} s)", flush=True)
     names = {"mgs": lib.ORTH_MGS, "cgs2": lib.ORTH_CGS2, "cgs2f": lib.ORTH_CGS2_FUSED}
-    for fmax in args.fmax:
-        os.environ["NUPGCM_STREAM_FMAX"] = str(fmax)
+    for fmax in ["-"]:
         t0 = time.time()
         dA = ctx.csr(A, drop_zeros=True)
         nnz = dA.info()["nnz_stored"]
@@ -58,7 +56,7 @@ def main():
         dyv = ctx.vector(y)
         x = ctx.vector(n)
         lib.gmres_solve(dA, dyv, x, pscale=pscale, atol=0, rtol=1e-30, itmax=20, orth=lib.ORTH_MGS)
-        print(f"fmax {fmax}: nnz {nnz}, device tables + first solve {time.time() - t0:.1f} s", flush=True)
+        print(f"nnz {nnz}, device tables + first solve {time.time() - t0:.1f} s", flush=True)
         for name in args.orth:
             for prof in ("0", "1"):
                 os.environ["NUPGCM_PROFILE"] = prof
@@ -76,7 +74,6 @@ def main():
                           f"spmv alone = {spmv_bytes(n, nnz) / (pf[0] * 1e-6) / 1e9:.0f} GB/s", flush=True)
             os.environ.pop("NUPGCM_PROFILE")
         del dA
-    os.environ.pop("NUPGCM_STREAM_FMAX", None)
 
 
 if __name__ == "__main__":
