@@ -258,6 +258,11 @@ int32_t nupgcm_diag_stream_spmv(nupgcm_csr *A, const nupgcm_vec *x, nupgcm_vec *
 int32_t nupgcm_diag_tma_stream(nupgcm_ctx *ctx, int64_t total_bytes, int32_t piece, int32_t slots,
                                int32_t warps, int32_t reps, float *gb_per_s);
 
+/* diagnostics: SM cycles per dependent operation — out8 = {LDS.64 chase, DFMA chain, LDS.U16->LDS.64 pair,
+ * IMAD chain, DFMA with 8 independent chains (1 warp), same with 11 warps, one block of 8 streaming-SpMV
+ * slice positions (1 warp), same with 11 warps} */
+int32_t nupgcm_diag_latency(nupgcm_ctx *ctx, double *out8);
+
 /* diagnostics: average latency (µs) of the grid-wide reduction the persistent solvers use.
  * mode 0: flagged-slot exchange only; 1: + block reduction; 2: + release/acquire fences. */
 int32_t nupgcm_diag_reduce_latency(nupgcm_ctx *ctx, int32_t mode, int32_t reps, int32_t grid,

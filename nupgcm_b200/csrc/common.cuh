@@ -120,6 +120,7 @@ struct nupgcm_csr {
     int32_t *d_tile_ptr;           // [grid_per_rank+1]
     NupgcmWarpDesc *d_wdesc;       // [grid_per_rank][kMainWarps]
     NupgcmSlice *d_slices;         // slice tables of all warps
+    uint8_t *d_twcnt;              // [tiles][kMainWarps] slices of each warp in each tile
     int32_t *d_srow;               // row tables: internal row ids ...
     int32_t *d_slen;               //             ... and row lengths, in slice order
     int32_t *d_sfoot;              // footprints of all tiles (internal column ids, sorted per tile)
@@ -180,22 +181,27 @@ struct nupgcm_mesh {
 // rows in slice order, then position j+1, ...): consecutive lanes read consecutive addresses, no
 // padding, no cross-lane reduction, no divergence beyond the last few positions.  WHICH entry of a row
 // sits at which position is free, and chosen so that the 16 lanes of a half-warp hit 16 different
-// shared-memory banks when they gather the vector (round-2 profile: random placement cost 22 of 78 us
-// in bank conflicts).  Slice s of tile t belongs to warp (s + t) mod kMainWarps, so every warp owns ONE
+// shared-memory banks when they gather the vector.  Rows longer than kLongRow are kept out of the slices
+// (whole warp per row, entries contiguous).  The items of a tile — slices and long rows — are dealt to the
+// warps heaviest item to lightest warp (d_twcnt says how many each warp gets), so every warp owns ONE
 // contiguous entry stream per CTA — values and 16-bit offsets — which it pulls through a private
 // shared-memory ring with TMA bulk copies of kPieceEntries entries.
 static const int kMainWarps = 11;      // solver warps of the persistent kernels (krylov.cu)
 static const int kPieceEntries = 512;  // entries per TMA piece: 4 KB of values + 1 KB of offsets (sized from
                                        // profiles/tma_piece_size_r02.txt: >= 2 KB copies reach the HBM rate)
-static const int kRingPieces = 3;      // pieces per warp ring
+static const int kRingPieces = 2;      // pieces per warp ring: one being consumed, one in flight.  11 warps x 5 KB in flight
+                                       // saturate HBM (same profile); deeper rings only queue more bytes in front of the
+                                       // comm warps' footprint gathers (3 pieces: 3.7 us per L2 round trip under load)
 static const int kTileRows = 32 * kMainWarps;   // rows per tile (times a multiplier when a CTA would exceed kMaxTiles)
 static const int kMaxTiles = 64;       // tiles per CTA: one pair of mbarriers each
-static const int kArenaEntries = 6656; // staged footprint entries in flight (52 KB next to 165 KB of rings)
+static const int kArenaEntries = 13312; // staged footprint entries in flight (104 KB next to 110 KB of rings)
 
 struct NupgcmTileDesc { int32_t row0, nrows, foot_off, foot_len, xs_off, dep, pad0, pad1; };   // xs_off: arena offset (entries);
                                        // dep: tile of the same CTA that must be finished before this one is staged (-1: none)
 struct NupgcmWarpDesc { int32_t estart, elen, stab, rtab; };    // stream start (multiple of 8) / length, slice and row table offsets
-struct NupgcmSlice { int32_t eoff, roff, nrows, lmax; };        // entry offset in the warp's stream, rows (relative to rtab), longest row
+struct NupgcmSlice { int32_t eoff, roff, nrows, lmax; };        // entry offset in the warp's stream, rows (relative to rtab), longest row;
+                                       // nrows == 0: ONE row of lmax entries stored contiguously, processed by the whole warp
+static const int kLongRow = 96;        // rows longer than this are such whole-warp items (they would give a slice a long jagged end)
 
 static const int kPartialSlots = 24;   // >= memory+2 of GMRES
 static const int kMaxMemory = 20;

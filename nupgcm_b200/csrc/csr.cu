@@ -209,6 +209,7 @@ struct StreamTables {
     std::vector<NupgcmSlice> slices;
     std::vector<int32_t> srow, slen, foot, ssrc;
     std::vector<uint16_t> scols;
+    std::vector<uint8_t> twcnt;                    // [tiles][kMainWarps]: slices of each warp in each tile
     int max_foot = 0;
 };
 
@@ -258,10 +259,12 @@ static void assign_banks(int nl, const uint16_t *avail, const int (*size)[16], i
 // Tables of one CTA (rows [ra, rb)): tiles, footprints and the kMainWarps entry streams.
 struct CtaStream {
     std::vector<NupgcmTileDesc> tiles;             // foot_off relative to `foot`
+    std::vector<uint8_t> twcnt;                    // [tiles][kMainWarps]
     std::vector<int32_t> foot;
     std::vector<NupgcmSlice> wsl[kMainWarps];
     std::vector<int32_t> wrow[kMainWarps], wlen[kMainWarps], wsrc[kMainWarps];
     std::vector<uint16_t> wcols[kMainWarps];
+    long long wcost[kMainWarps] = {0};
     int max_foot = 0;
     bool ok = true;
 };
@@ -298,18 +301,56 @@ static void build_cta_stream(const int32_t *rowptr, const int32_t *col, int32_t 
                                           arena_pos, dep, 0, 0});
         arena_pos += flen;
         cs.foot.insert(cs.foot.end(), tile_cols.begin(), tile_cols.end());
-        // rows by decreasing length (ties by row id), cut into slices of 32; slice s -> warp (s + tile) mod W
+        // rows by decreasing length (ties by row id); rows longer than kLongRow become whole-warp items,
+        // the rest is cut into slices of 32.  Items go to the warps heaviest-first to the warp with the
+        // least work so far (work = slice positions), so that the warps of the CTA stay level
         order.resize(r_end - start);
         for (int32_t i = 0; i < r_end - start; ++i) order[i] = start + i;
         std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
             return rowptr[x + 1] - rowptr[x] > rowptr[y + 1] - rowptr[y];
         });
-        int sidx = 0;
-        for (size_t i = 0; i < order.size(); i += 32, ++sidx) {
-            const int nr = (int)std::min<size_t>(32, order.size() - i);
-            const int w = (sidx + tix) % W;
-            const int lmax = rowptr[order[i] + 1] - rowptr[order[i]];
-            cs.wsl[w].push_back(NupgcmSlice{(int32_t)cs.wcols[w].size(), (int32_t)cs.wrow[w].size(), nr, lmax});
+        size_t nlong = 0;
+        while (nlong < order.size() && rowptr[order[nlong] + 1] - rowptr[order[nlong]] > kLongRow) ++nlong;
+        struct Item { size_t first; int nrows; int cost; };
+        std::vector<Item> items;
+        for (size_t i = 0; i < nlong; ++i)
+            items.push_back(Item{i, 0, (rowptr[order[i] + 1] - rowptr[order[i]] + 31) / 32 + 4});
+        for (size_t i = nlong; i < order.size(); i += 32)
+            items.push_back(Item{i, (int)std::min<size_t>(32, order.size() - i), rowptr[order[i] + 1] - rowptr[order[i]] + 3});
+        std::stable_sort(items.begin(), items.end(), [](const Item &x, const Item &y) { return x.cost > y.cost; });
+        cs.twcnt.insert(cs.twcnt.end(), W, 0);
+        for (const Item &it : items) {
+            int w = 0;
+            for (int v = 1; v < W; ++v)
+                if (cs.wcost[v] < cs.wcost[w]) w = v;
+            cs.wcost[w] += it.cost;
+            cs.twcnt[(size_t)tix * W + w]++;
+            if (cs.twcnt[(size_t)tix * W + w] == 255) { cs.ok = false; return; }
+            const int lmax = rowptr[order[it.first] + 1] - rowptr[order[it.first]];
+            cs.wsl[w].push_back(NupgcmSlice{(int32_t)cs.wcols[w].size(), (int32_t)cs.wrow[w].size(), it.nrows, lmax});
+            if (it.nrows == 0) {
+                // a long row: entries contiguous, interleaved over the bank pairs so that 16 consecutive
+                // entries (one half-warp) mostly sit in 16 different banks
+                const int32_t row = order[it.first];
+                cs.wrow[w].push_back(row);
+                cs.wlen[w].push_back(lmax);
+                std::vector<int32_t> bucket[16];
+                for (int32_t k = rowptr[row]; k < rowptr[row + 1]; ++k) bucket[loc_of[col[k]] & 15].push_back(k);
+                for (size_t r = 0; ; ++r) {
+                    bool any = false;
+                    for (int bk = 0; bk < 16; ++bk)
+                        if (r < bucket[bk].size()) {
+                            const int32_t k = bucket[bk][r];
+                            cs.wcols[w].push_back((uint16_t)(8 * loc_of[col[k]]));
+                            cs.wsrc[w].push_back(k);
+                            any = true;
+                        }
+                    if (!any) break;
+                }
+                continue;
+            }
+            const int nr = it.nrows;
+            const size_t i = it.first;
             // per row: its entries bucketed by the bank pair (position in the staged footprint mod 16)
             std::vector<int32_t> bucket[32][16];
             int left[32], size[32][16];
@@ -377,6 +418,7 @@ static bool build_stream_tables(const int32_t *rowptr, const int32_t *col, int64
         while (st.foot.size() % 4) st.foot.push_back(0);
         const int32_t fbase = (int32_t)st.foot.size();
         for (NupgcmTileDesc td : cs.tiles) { td.foot_off += fbase; st.tiles.push_back(td); }
+        st.twcnt.insert(st.twcnt.end(), cs.twcnt.begin(), cs.twcnt.end());
         st.foot.insert(st.foot.end(), cs.foot.begin(), cs.foot.end());
         for (int w = 0; w < W; ++w) {
             while (st.scols.size() % 8) { st.scols.push_back(0); st.ssrc.push_back(-1); }   // 16-byte aligned streams
@@ -416,6 +458,7 @@ static void free_stream_tables(nupgcm_csr *A) {
     cudaFree(A->d_tile_ptr); A->d_tile_ptr = nullptr;
     cudaFree(A->d_wdesc); A->d_wdesc = nullptr;
     cudaFree(A->d_slices); A->d_slices = nullptr;
+    cudaFree(A->d_twcnt); A->d_twcnt = nullptr;
     cudaFree(A->d_srow); A->d_srow = nullptr;
     cudaFree(A->d_slen); A->d_slen = nullptr;
     cudaFree(A->d_sfoot); A->d_sfoot = nullptr;
@@ -576,6 +619,7 @@ int32_t nupgcm_csr_prepare(nupgcm_csr *A, int grid_per_rank) {
                 NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_tile_ptr, st.tile_ptr));
                 NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_wdesc, st.wdesc));
                 NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_slices, st.slices));
+                NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_twcnt, st.twcnt));
                 NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_srow, st.srow));
                 NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_slen, st.slen));
                 NUPGCM_CUDA(ctx, upload_vec((void **)&A->d_sfoot, st.foot));
@@ -722,18 +766,41 @@ extern "C" int32_t nupgcm_diag_stream_spmv_host(int64_t n, const int64_t *rowptr
                 owner[td.xs_off + i] = tix;
                 xs[td.xs_off + i] = x[st.foot[td.foot_off + i]];
             }
-            const int nsl = (td.nrows + 31) / 32;
             for (int w = 0; w < W; ++w) {
                 const NupgcmWarpDesc wd = st.wdesc[(size_t)b * W + w];
                 if (wd.estart % 8) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "misaligned stream");
-                const int first = ((w - tix) % W + W) % W;
-                for (int sidx = first; sidx < nsl; sidx += W) {
+                for (int k = 0; k < st.twcnt[(size_t)(st.tile_ptr[b] + tix) * W + w]; ++k) {
                     const NupgcmSlice sl = st.slices[(size_t)wd.stab + next_slice[w]++];
                     if (sl.eoff != walked[w]) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "slices do not tile the stream");
                     const int32_t *rows = st.srow.data() + wd.rtab + sl.roff, *lens = st.slen.data() + wd.rtab + sl.roff;
                     double acc[32] = {0};
                     int64_t off = sl.eoff;
-                    if (sl.nrows < 1 || sl.nrows > 32 || lens[0] != sl.lmax) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "bad slice header");
+                    if (sl.nrows < 0 || sl.nrows > 32 || lens[0] != sl.lmax) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "bad slice header");
+                    if (sl.nrows == 0) {                         // a long row: 32 consecutive entries per step
+                        if (sl.lmax <= kLongRow) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "short row stored as a long one");
+                        double sum = 0.0;
+                        for (int k0 = 0; k0 < sl.lmax; k0 += 32) {
+                            int load[2][16] = {{0}};
+                            for (int q = 0; q < 32 && k0 + q < sl.lmax; ++q) {
+                                const size_t e = (size_t)wd.estart + off + k0 + q;
+                                if (off + k0 + q >= wd.elen || st.scols[e] % 8 || st.scols[e] / 8 >= td.foot_len)
+                                    return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "entry outside its stream or footprint");
+                                sum += sv[e] * xs[td.xs_off + st.scols[e] / 8];
+                                load[q >> 4][(st.scols[e] / 8) & 15]++;
+                            }
+                            for (int hw = 0; hw < 2; ++hw) {
+                                int mx = 0;
+                                for (int bk = 0; bk < 16; ++bk) mx = std::max(mx, load[hw][bk]);
+                                waves += mx;
+                            }
+                            ++npos;
+                        }
+                        walked[w] = off + sl.lmax;
+                        if (rows[0] < td.row0 || rows[0] >= td.row0 + td.nrows) return nupgcm_fail(nullptr, NUPGCM_ERR_INVALID, "%s", "row outside its tile");
+                        y[rows[0]] = sum;
+                        written[rows[0]]++;
+                        continue;
+                    }
                     for (int j = 0; j < sl.lmax; ++j) {
                         int cnt = 0, load[2][16] = {{0}};
                         for (int q = 0; q < sl.nrows; ++q) {

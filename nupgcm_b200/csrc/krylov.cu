@@ -51,6 +51,7 @@ static const int kRingEntries = kPieceEntries * kRingPieces;
 static const uint32_t kPieceBytes = kPieceEntries * (sizeof(double) + sizeof(uint16_t));
 static_assert((kPieceEntries & (kPieceEntries - 1)) == 0, "piece size must be a power of two");
 static_assert(8 * 32 + kPieceEntries <= kRingEntries, "a block of 8 slice positions must fit in the ring next to one piece");
+static_assert(kRingPieces >= 2, "double buffering at least");
 
 struct KrylovArgs {
     const int32_t *rowptr;
@@ -68,6 +69,7 @@ struct KrylovArgs {
     const int32_t *tile_ptr;
     const NupgcmWarpDesc *wdesc;
     const NupgcmSlice *slices;
+    const uint8_t *twcnt;
     const int32_t *srow;
     const int32_t *slen;
     const int32_t *sfoot;
@@ -822,42 +824,52 @@ __device__ __forceinline__ bool stream_gather_service(const KrylovArgs &a, unsig
     const unsigned par = calls & 1u;
     bool ok = true;
     constexpr int U = kGatherU, RND = kGatherU * kCommThreads;
-    // round cursor: tile `t`, entries [base, base + RND) of its footprint
-    int t = t0, base = 0;
-    NupgcmTileDesc td = a.tiles[t0];
-    int32_t idx[U];
-    auto load_idx = [&](int32_t *dst, const NupgcmTileDesc &d, int b) {
-        const int32_t *foot = a.sfoot + d.foot_off;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = b + ct + u * kCommThreads;
-            dst[u] = i < d.foot_len ? __ldg(foot + i) : 0;
+    // A round = entries [base, base + RND) of the footprint of tile t.  Three rounds overlap: the column
+    // ids of round r+2 and the vector entries of round r+1 are in flight while round r is stored.
+    struct Cursor { int t, base; NupgcmTileDesc td; };
+    auto advance = [&](Cursor &c) {
+        c.base += RND;
+        if (c.base >= c.td.foot_len) {
+            c.base = 0;
+            if (++c.t < t1) c.td = a.tiles[c.t];
         }
     };
-    load_idx(idx, td, 0);
-    while (t < t1) {
-        if (base == 0 && td.dep >= 0) ok = mbar_wait(sh.xs_empty + td.dep, par, abort_word) && ok;
-        double xv[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) xv[u] = ld_cg(xin + idx[u]);
-        // cursor of the next round, and its column ids
-        const NupgcmTileDesc cur = td;
-        const int cbase = base;
-        int nt = t, nbase = base + RND;
-        if (nbase >= td.foot_len) { nt = t + 1; nbase = 0; }
-        if (nt < t1) {
-            if (nt != t) td = a.tiles[nt];
-            load_idx(idx, td, nbase);
-        }
-        double *dst = sh.xs + cur.xs_off;
+    auto load_idx = [&](int32_t *dst, const Cursor &c) {
+        const int32_t *foot = a.sfoot + c.td.foot_off;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int i = cbase + ct + u * kCommThreads;
-            if (i < cur.foot_len) dst[i] = xv[u];
+            const int i = c.base + ct + u * kCommThreads;
+            dst[u] = (c.t < t1 && i < c.td.foot_len) ? __ldg(foot + i) : 0;
         }
-        if (nt != t) mbar_arrive(sh.xs_full + (t - t0));         // the tile is complete (release: the stores above)
-        t = nt;
-        base = nbase;
+    };
+    auto load_x = [&](double *dst, const int32_t *idx) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) dst[u] = ld_cg(xin + idx[u]);
+    };
+    Cursor c0{t0, 0, a.tiles[t0]}, c1 = c0, c2;
+    int32_t idx[U];
+    double xa[U], xb[U];
+    load_idx(idx, c0);
+    load_x(xa, idx);                         // round 0
+    advance(c1);
+    load_idx(idx, c1);                       // ids of round 1
+    c2 = c1;
+    while (c0.t < t1) {
+        if (c1.t < t1) load_x(xb, idx);      // round r+1
+        advance(c2);
+        load_idx(idx, c2);                   // ids of round r+2
+        if (c0.base == 0 && c0.td.dep >= 0) ok = mbar_wait(sh.xs_empty + c0.td.dep, par, abort_word) && ok;
+        double *dst = sh.xs + c0.td.xs_off;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = c0.base + ct + u * kCommThreads;
+            if (i < c0.td.foot_len) dst[i] = xa[u];
+        }
+        if (c0.base + RND >= c0.td.foot_len) mbar_arrive(sh.xs_full + (c0.t - t0));   // tile complete (release: the stores above)
+        c0 = c1;
+        c1 = c2;
+#pragma unroll
+        for (int u = 0; u < U; ++u) xa[u] = xb[u];
     }
     ++calls;
     return ok;
@@ -963,7 +975,7 @@ struct SpmvEngine<T, false> {
             return;
         }
         if (t0 == t1) return;                                    // a CTA without rows posts nothing (both roles know)
-        long long tk[6] = {0, 0, 0, 0, 0, 0}, tlast = DBG == 3 ? clock64() : 0;   // DBG 3: cycles per activity
+        long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = DBG == 3 ? clock64() : 0;   // DBG 3: cycles per activity
         auto tick = [&](int k) { if (DBG == 3) { const long long now = clock64(); tk[k] += now - tlast; tlast = now; } };
         // ask the comm warps to stage the footprints of xin (no response: the tiles' mbarriers pace us)
         if (threadIdx.x == 0) { mb->count = kReqGather; mb->xin = xin; }
@@ -975,6 +987,7 @@ struct SpmvEngine<T, false> {
         int landed = 0;                                          // pieces of this call known to have arrived
         int issued = npieces < kRingPieces ? npieces : kRingPieces;
         auto ensure = [&](int need) {                            // entries [0, need) of the stream are in the ring
+            if (DBG == 4) return;                                // (timing experiment: no copies at all, stale ring)
             if (landed * kPieceEntries < need) {
                 tick(3);
                 do { wait_piece(abort_word); ++landed; } while (landed * kPieceEntries < need);
@@ -982,14 +995,18 @@ struct SpmvEngine<T, false> {
             }
         };
         auto release = [&](int cons) {                           // entries [0, cons) are consumed: refill freed slots
+            if (DBG == 4) return;
             const int lim = min(npieces, kRingPieces + cons / kPieceEntries);
             if (issued < lim) {
-                __syncwarp();                                    // every lane is done reading them
-                if (lane == 0) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                tick(3);
+                // Every lane's reads of the freed slot have returned (their values were consumed above):
+                // the copy engine may overwrite it.  No proxy fence: this is write-after-READ (the consumer
+                // release of any TMA pipeline); fence.proxy.async here cost ~1.9 k cycles per piece under load.
+                __syncwarp();
+                if (lane == 0)
                     for (int p = issued; p < lim; ++p) issue(p);
-                }
                 issued = lim;
+                if (DBG == 3) { __syncwarp(); tick(6); tk[7] += 1; }
             }
         };
         const unsigned char *xt = xs;                            // staged footprint of the current tile
@@ -999,44 +1016,104 @@ struct SpmvEngine<T, false> {
                                        : *reinterpret_cast<const double *>(xt + rc[idx]);
             return rv[idx] * xv;
         };
+        // 8 positions of 32 entries each that do not go round the end of the ring: every address is the
+        // lane's base plus a compile-time constant (no index arithmetic per position)
+        auto dense8 = [&](int base, double &s0, double &s1) {
+            const double *pv = rv + base + lane;
+            const uint16_t *pc = rc + base + lane;
+#pragma unroll
+            for (int p = 0; p < 8; p += 2) {
+                const double x0 = DBG == 2 ? *reinterpret_cast<const double *>(xt + 8 * lane)
+                                           : *reinterpret_cast<const double *>(xt + pc[32 * p]);
+                const double x1 = DBG == 2 ? *reinterpret_cast<const double *>(xt + 8 * lane)
+                                           : *reinterpret_cast<const double *>(xt + pc[32 * (p + 1)]);
+                s0 = fma(pv[32 * p], x0, s0);
+                s1 = fma(pv[32 * (p + 1)], x1, s1);
+            }
+        };
         // the first slice's tables are fetched before anything is waited for; then always one slice ahead
         int si = 0;                                              // next slice of this warp's list
         NupgcmSlice sl = slices[0];
         int mylen = 0, myrow = -1;
-        if (lane < sl.nrows) { mylen = __ldg(slen + sl.roff + lane); myrow = __ldg(srow + sl.roff + lane); }
+        if (lane < max(sl.nrows, 1)) { mylen = __ldg(slen + sl.roff + lane); myrow = __ldg(srow + sl.roff + lane); }
         NupgcmTileDesc td = a.tiles[t0];
+        int mine_next = __ldg(a.twcnt + (size_t)t0 * kMainWarps + wid);       // my items in the first tile
+        // results of whole-warp (long) rows are parked one per lane and handed to f together: f's global
+        // accesses then cost one round trip per 32 rows instead of one per row
+        int nparked = 0, prow = -1;
+        double pval = 0.0;
+        auto flush_parked = [&]() {
+            if (lane < nparked) f(prow, pval);
+            nparked = 0;
+        };
         for (int tix = 0; tix < t1 - t0; ++tix) {
-            const int nsl = (td.nrows + 31) >> 5;
             const int xs_off = td.xs_off;
-            if (tix + 1 < t1 - t0) td = a.tiles[t0 + tix + 1];   // next tile's descriptor: in flight during this one
-            int first = wid - tix % kMainWarps;
-            if (first < 0) first += kMainWarps;
+            const int mine = mine_next;                          // my items (slices, long rows) in this tile
+            if (tix + 1 < t1 - t0) {                             // next tile's tables: in flight during this one
+                td = a.tiles[t0 + tix + 1];
+                mine_next = __ldg(a.twcnt + (size_t)(t0 + tix + 1) * kMainWarps + wid);
+            }
             tick(2);
             if (!mbar_wait(xs_full + tix, par, abort_word)) failed = true;
             tick(0);
             xt = xs + (size_t)xs_off * 8;
-            for (int s = first; s < nsl; s += kMainWarps) {
+            for (int s = 0; s < mine; ++s) {
                 const NupgcmSlice cs = sl;
                 const int clen = mylen, crow = myrow;
                 ++si;
                 sl = slices[si];                                 // (the table ends with a null slice)
                 mylen = 0;
                 myrow = -1;
-                if (lane < sl.nrows) { mylen = __ldg(slen + sl.roff + lane); myrow = __ldg(srow + sl.roff + lane); }
+                if (lane < max(sl.nrows, 1)) { mylen = __ldg(slen + sl.roff + lane); myrow = __ldg(srow + sl.roff + lane); }
                 const int nr = cs.nrows;
+                int off = cs.eoff;
+                double acc0 = 0.0, acc1 = 0.0;
+                if (nr == 0) {
+                    // a long row: the whole warp strides over its (contiguous) entries, 8 x 32 at a time
+                    const int row = __shfl_sync(0xffffffffu, crow, 0);
+                    tick(2);
+                    for (int k0 = 0; k0 < cs.lmax; k0 += 256) {
+                        const int m = min(256, cs.lmax - k0);
+                        ensure(off + m);
+                        if (DBG != 1) {
+                            if (m == 256 && rpos + 256 <= kRingEntries) {
+                                dense8(rpos, acc0, acc1);
+                            } else {
+#pragma unroll
+                                for (int p = 0; p < 8; p += 2) {
+                                    if (32 * p + lane < m) acc0 += entry(rpos + 32 * p + lane);
+                                    if (32 * (p + 1) + lane < m) acc1 += entry(rpos + 32 * (p + 1) + lane);
+                                }
+                            }
+                        }
+                        off += m;
+                        rpos += m;
+                        if (rpos >= kRingEntries) rpos -= kRingEntries;
+                        release(off);
+                    }
+                    tick(4);
+                    acc0 = warp_sum(acc0 + acc1);
+                    if (lane == nparked) { prow = row; pval = acc0; }
+                    if (++nparked == 32) flush_parked();
+                    tick(5);
+                    continue;
+                }
                 const bool act = lane < nr;
                 const int lmin = __shfl_sync(0xffffffffu, clen, nr - 1);
                 tick(2);
-                int off = cs.eoff, j = 0;
-                double acc0 = 0.0, acc1 = 0.0;
+                int j = 0;
                 // positions every row of the slice has: nr entries each, lane q reads entry q
                 for (; j + 8 <= lmin; j += 8) {
                     ensure(off + 8 * nr);
-                    if (DBG != 1 && act) {
+                    if (DBG != 1) {
+                        if (nr == 32 && rpos + 256 <= kRingEntries) {
+                            dense8(rpos, acc0, acc1);
+                        } else if (act) {
 #pragma unroll
-                        for (int p = 0; p < 8; p += 2) {
-                            acc0 += entry(rpos + p * nr + lane);
-                            acc1 += entry(rpos + (p + 1) * nr + lane);
+                            for (int p = 0; p < 8; p += 2) {
+                                acc0 += entry(rpos + p * nr + lane);
+                                acc1 += entry(rpos + (p + 1) * nr + lane);
+                            }
                         }
                     }
                     off += 8 * nr;
@@ -1055,36 +1132,48 @@ struct SpmvEngine<T, false> {
                     j = lmin;
                 }
                 tick(3);
-                // the jagged end: rows are sorted by length, so position j is held by lanes 0 .. cnt-1
-                for (; j < cs.lmax; ++j) {
-                    const int cnt = __popc(__ballot_sync(0xffffffffu, clen > j));
-                    ensure(off + cnt);
-                    if (DBG != 1 && clen > j) acc0 += entry(rpos + lane);
-                    off += cnt;
-                    rpos += cnt;
+                // the jagged end, also 8 positions at a time: rows are sorted by length, so position j is
+                // held by lanes 0 .. cnt_j-1 and starts cnt_0 + .. + cnt_{j-1} entries further on
+                while (j < cs.lmax) {
+                    int start[9];
+                    start[0] = 0;
+#pragma unroll
+                    for (int p = 0; p < 8; ++p)
+                        start[p + 1] = start[p] + __popc(__ballot_sync(0xffffffffu, clen > j + p));
+                    ensure(off + start[8]);
+                    if (DBG != 1) {
+#pragma unroll
+                        for (int p = 0; p < 8; p += 2) {
+                            if (clen > j + p) acc0 += entry(rpos + start[p] + lane);
+                            if (clen > j + p + 1) acc1 += entry(rpos + start[p + 1] + lane);
+                        }
+                    }
+                    off += start[8];
+                    rpos += start[8];
                     if (rpos >= kRingEntries) rpos -= kRingEntries;
-                    release(off);                                // a long jagged end must keep the ring moving too
+                    j += 8;
+                    release(off);
                 }
                 release(off);
                 tick(4);
                 if (act) f(crow, acc0 + acc1);
                 tick(5);
             }
+            flush_parked();
             __syncwarp();
             if (lane == 0) mbar_arrive(xs_empty + tix);
         }
         ++calls;
         // this SpMV is done: start pulling the first pieces of the next one
         __syncwarp();
-        if (lane == 0 && npieces > 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (lane == 0 && DBG != 4)
             for (int p = 0; p < npieces && p < kRingPieces; ++p) issue(p);
-        }
         if (failed) mb->dead = 1;
         if (DBG == 3 && a.trace && lane == 0) {
             tick(2);
             unsigned long long *o = a.trace + ((size_t)blockIdx.x * kMainWarps + wid) * 8;
             for (int k = 0; k < 6; ++k) o[k] += (unsigned long long)tk[k];
+            o[7] += (unsigned long long)tk[6];                   // ring refills (inside the position rows' code)
         }
     }
 };
@@ -2043,6 +2132,7 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
     args.tile_ptr = A->d_tile_ptr;
     args.wdesc = A->d_wdesc;
     args.slices = A->d_slices;
+    args.twcnt = A->d_twcnt;
     args.srow = A->d_srow;
     args.slen = A->d_slen;
     args.sfoot = A->d_sfoot;
@@ -2199,7 +2289,7 @@ extern "C" int32_t nupgcm_diag_stream_spmv(nupgcm_csr *A, const nupgcm_vec *x, n
     nupgcm_ctx *ctx = A->ctx;
     NUPGCM_REQUIRE(ctx, A->n_rows == A->n_cols && x->n == A->n_rows && y->n == A->n_rows && x->d != y->d,
                    "diag_stream_spmv: square matrix and distinct vectors of its size");
-    NUPGCM_REQUIRE(ctx, reps >= 1 && mode >= 0 && mode <= 3 && !A->comm && (mode != 3 || warp_cycles), "diag_stream_spmv: bad argument");
+    NUPGCM_REQUIRE(ctx, reps >= 1 && mode >= 0 && mode <= 4 && !A->comm && (mode != 3 || warp_cycles), "diag_stream_spmv: bad argument");
     NUPGCM_CUDA(ctx, cudaSetDevice(ctx->device));
     const int grid = ctx->coop_grid;
     int32_t rc = nupgcm_csr_prepare(A, grid);
@@ -2212,7 +2302,7 @@ extern "C" int32_t nupgcm_diag_stream_spmv(nupgcm_csr *A, const nupgcm_vec *x, n
     if (rc) return rc;
     args.rowptr = A->d_prow; args.colidx = A->d_pcol; args.vals = A->d_pvals; args.perm = A->d_perm; args.part = A->d_part;
     args.svals = A->d_svals; args.scols = A->d_scols; args.tiles = A->d_tiles; args.tile_ptr = A->d_tile_ptr;
-    args.wdesc = A->d_wdesc; args.slices = A->d_slices; args.srow = A->d_srow; args.slen = A->d_slen; args.sfoot = A->d_sfoot;
+    args.wdesc = A->d_wdesc; args.slices = A->d_slices; args.twcnt = A->d_twcnt; args.srow = A->d_srow; args.slen = A->d_slen; args.sfoot = A->d_sfoot;
     args.n = (int)A->n_rows;
     args.nranks = 1;
     args.barrier = ctx->d_barrier;
@@ -2221,7 +2311,8 @@ extern "C" int32_t nupgcm_diag_stream_spmv(nupgcm_csr *A, const nupgcm_vec *x, n
     k_diag_permute_in<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->d_ws, x->d, A->d_perm, (int)A->n_rows);
     const void *fn;
     fn = mode == 0 ? (const void *)k_diag_stream_spmv<8, 0> : mode == 1 ? (const void *)k_diag_stream_spmv<8, 1>
-       : mode == 2 ? (const void *)k_diag_stream_spmv<8, 2> : (const void *)k_diag_stream_spmv<8, 3>;
+       : mode == 2 ? (const void *)k_diag_stream_spmv<8, 2> : mode == 3 ? (const void *)k_diag_stream_spmv<8, 3>
+       : (const void *)k_diag_stream_spmv<8, 4>;
     unsigned long long *d_trace = nullptr;
     const size_t trace_words = (size_t)grid * kMainWarps * 8;
     if (mode == 3) {

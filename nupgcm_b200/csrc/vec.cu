@@ -292,3 +292,118 @@ extern "C" int32_t nupgcm_vec_gather(nupgcm_vec *dst, const nupgcm_vec *src, con
     NUPGCM_CUDA(ctx, cudaGetLastError());
     return NUPGCM_OK;
 }
+
+
+// ---- diagnostics: latencies the kernels' cost models rest on (SM cycles per dependent operation) ----
+//   out[0] dependent LDS.64 (shared-memory pointer chase)     out[1] dependent DFMA chain
+//   out[2] dependent LDS.U16 -> address -> LDS.64 pair          out[3] dependent IMAD chain
+//   out[4] 8 independent DFMA chains, cycles per DFMA (one warp)
+//   out[5] same with 11 warps of the CTA running it together (cycles per DFMA per warp)
+__global__ void k_diag_latency(double *out, int n) {
+    __shared__ double sd[1024];
+    __shared__ unsigned short su[1024];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+        const int nxt = (i * 17 + 5) & 1023;
+        sd[i] = __longlong_as_double((long long)nxt);
+        su[i] = (unsigned short)(8 * nxt);
+    }
+    __syncthreads();
+    long long t0, t1;
+    if (wid == 0) {
+        int idx = lane;
+        t0 = clock64();
+        for (int i = 0; i < n; ++i) idx = (int)__double_as_longlong(sd[idx]) & 1023;
+        t1 = clock64();
+        if (lane == 0) out[0] = (double)(t1 - t0) / n + 1e-9 * idx;
+        double a = 1.0 + lane * 1e-3, b = 0.999999;
+        t0 = clock64();
+        for (int i = 0; i < n; ++i) a = fma(a, b, 1e-9);
+        t1 = clock64();
+        if (lane == 0) out[1] = (double)(t1 - t0) / n + 1e-30 * a;
+        unsigned off = 8 * lane;
+        double acc = 0.0;
+        t0 = clock64();
+        for (int i = 0; i < n; ++i) {
+            const unsigned short c = su[(off >> 3) & 1023];
+            const double v = *reinterpret_cast<const double *>(reinterpret_cast<const char *>(sd) + c);
+            off = (unsigned)__double_as_longlong(v) * 8;
+            acc += 0.0;
+        }
+        t1 = clock64();
+        if (lane == 0) out[2] = (double)(t1 - t0) / n + 1e-30 * off + acc;
+        int q = lane;
+        t0 = clock64();
+        for (int i = 0; i < n; ++i) q = q * 3 + i;
+        t1 = clock64();
+        if (lane == 0) out[3] = (double)(t1 - t0) / n + 1e-30 * q;
+    }
+    __syncthreads();
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 0 && wid != 0) continue;
+        double c[8];
+        for (int k = 0; k < 8; ++k) c[k] = 1.0 + 1e-3 * (lane + k);
+        const double b = 0.999999;
+        t0 = clock64();
+        for (int i = 0; i < n; ++i)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) c[k] = fma(c[k], b, 1e-9);
+        t1 = clock64();
+        double sum = 0.0;
+        for (int k = 0; k < 8; ++k) sum += c[k];
+        if (lane == 0 && wid == 0) out[4 + pass] = (double)(t1 - t0) / (8.0 * n) + 1e-30 * sum;
+    }
+}
+
+// out[6], out[7]: SM cycles per block of 8 slice positions (8 x {LDS.U16, LDS.64, gather LDS.64, DFMA} per
+// lane, two accumulators) for one warp alone and for 11 warps of a CTA together — the inner loop of the
+// streaming SpMV without any of its pipeline bookkeeping.
+__global__ void k_diag_block8(double *out, int nblocks) {
+    extern __shared__ __align__(128) unsigned char dsm[];
+    double *rv = reinterpret_cast<double *>(dsm);                       // [11][1024]
+    unsigned short *rc = reinterpret_cast<unsigned short *>(dsm + 11 * 1024 * 8);   // [11][1024]
+    const unsigned char *xt = dsm + 11 * 1024 * 10;                    // 4096 doubles
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 11 * 1024; i += blockDim.x) {
+        rv[i] = 1.0 + 1e-6 * i;
+        rc[i] = (unsigned short)(8 * ((i * 2654435761u >> 7) & 4095));
+    }
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) reinterpret_cast<double *>(dsm + 11 * 1024 * 10)[i] = 1e-3 * i;
+    __syncthreads();
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 0 && wid != 0) continue;
+        if (pass == 1) __syncthreads();
+        double s0 = 0.0, s1 = 0.0;
+        const long long t0 = clock64();
+        for (int b = 0; b < nblocks; ++b) {
+            const int base = (b & 3) * 256;
+            const double *pv = rv + wid * 1024 + base + lane;
+            const unsigned short *pc = rc + wid * 1024 + base + lane;
+#pragma unroll
+            for (int p = 0; p < 8; p += 2) {
+                const double x0 = *reinterpret_cast<const double *>(xt + pc[32 * p]);
+                const double x1 = *reinterpret_cast<const double *>(xt + pc[32 * (p + 1)]);
+                s0 = fma(pv[32 * p], x0, s0);
+                s1 = fma(pv[32 * (p + 1)], x1, s1);
+            }
+            asm volatile("" ::: "memory");
+        }
+        const long long t1 = clock64();
+        if (wid == 0 && lane == 0) out[6 + pass] = (double)(t1 - t0) / nblocks + 1e-300 * (s0 + s1);
+        if (lane == 1 && s0 + s1 == 12345.678) out[8] = s0;
+    }
+}
+
+extern "C" int32_t nupgcm_diag_latency(nupgcm_ctx *ctx, double *out6) {
+    NUPGCM_REQUIRE(nullptr, ctx && out6, "diag_latency: NULL argument");
+    NUPGCM_CUDA(ctx, cudaSetDevice(ctx->device));
+    k_diag_latency<<<1, 352, 0, ctx->stream>>>(ctx->d_scalars, 4096);
+    NUPGCM_CUDA(ctx, cudaFuncSetAttribute((const void *)k_diag_block8, cudaFuncAttributeMaxDynamicSharedMemorySize, 11 * 1024 * 10 + 4096 * 8));
+    k_diag_block8<<<1, 352, 11 * 1024 * 10 + 4096 * 8, ctx->stream>>>(ctx->d_scalars, 2048);
+    ctx->launches += 2;
+    NUPGCM_CUDA(ctx, cudaGetLastError());
+    NUPGCM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NUPGCM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 8; ++i) out6[i] = ctx->h_scalars[i];
+    return NUPGCM_OK;
+}

@@ -81,6 +81,7 @@ SIGNATURES = {
     "nupgcm_diag_stream_spmv_host": [c_int64, _ip, _ip, _dp, _dp, c_int32, c_int32, _dp, _ip, _ip, _ip, _ip],
     "nupgcm_diag_stream_spmv": [_P, _P, _P, c_int32, c_int32, POINTER(c_float), _dp],
     "nupgcm_diag_tma_stream": [_P, c_int64, c_int32, c_int32, c_int32, c_int32, POINTER(c_float)],
+    "nupgcm_diag_latency": [_P, _dp],
     "nupgcm_spmv": [_P, _P, _P, c_double, c_double],
     "nupgcm_cg_solve": [_P, _P, c_double, _P, _P, c_double, c_double, c_int64, _dp, c_int64,
                         POINTER(SolveStats)],
@@ -219,6 +220,12 @@ class Context:
         _check(self.lib.nupgcm_diag_tma_stream(self.h, int(total_bytes), int(piece), int(slots), int(warps),
                                                int(reps), C.byref(out)), self.h)
         return float(out.value)
+
+    def latencies(self):
+        out = np.zeros(8)
+        _check(self.lib.nupgcm_diag_latency(self.h, _ptr(out)), self.h)
+        return dict(zip(["lds64", "dfma", "lds16_lds64", "imad", "dfma_ilp8_1warp", "dfma_ilp8_11warps",
+                         "block8_1warp", "block8_11warps"], out))
 
     def launch_count(self) -> int:
         n = c_int64()

@@ -43,17 +43,18 @@ def main():
         if 3 in args.modes:
             us, cyc = dA.stream_spmv(dx, dy, reps=args.reps, mode=3)
             names = ["wait footprint", "wait ring", "tables+misc", "full positions", "jagged ends", "callback", "closing barrier"]
-            tot = cyc[:, :, :7].sum(axis=2)
+            tot = cyc[:, :, :8].sum(axis=2)
             print(f"mode 3: {us:.1f} us per product; per-warp SM cycles per product (mean over all warps | slowest warp of CTA 0):")
             w = np.unravel_index(np.argmax(cyc[0, :, :6].sum(axis=1)), (11,))[0]
             for k, nm in enumerate(names):
                 print(f"    {nm:16s} {cyc[:, :, k].mean():9.0f} | {cyc[0, w, k]:9.0f}")
+            print(f"    {'ring refills':16s} {cyc[:, :, 7].mean():9.0f} | {cyc[0, w, 7]:9.0f}")
             print(f"    {'total':16s} {tot.mean():9.0f} | {tot[0, w]:9.0f}   busy (no closing barrier): min {cyc[:, :, :6].sum(axis=2).min():.0f} max {cyc[:, :, :6].sum(axis=2).max():.0f}", flush=True)
         for mode in [m for m in args.modes if m != 3]:
             dA.stream_spmv(dx, dy, reps=3, mode=mode)
             us = dA.stream_spmv(dx, dy, reps=args.reps, mode=mode)
             gbs = spmv_bytes(n, nnz) / (us * 1e-6) / 1e9
-            what = {0: "product", 1: "copy pipeline only", 2: "no footprint gather"}[mode]
+            what = {0: "product", 1: "copy pipeline only", 2: "no footprint gather", 4: "compute only, no copy"}[mode]
             print(f"mode {mode} ({what:19s}): {us:8.1f} us  {gbs:7.1f} GB/s  ({gbs / peak:.3f} of measured HBM peak)"
                   + (f"  rel err vs SciPy {err:.1e}" if mode == 0 else ""), flush=True)
         del dA
