@@ -36,7 +36,7 @@ typedef enum {
     NUPGCM_ERR_INVALID = -1,   /* bad argument (null handle, size mismatch, bad enum ...) */
     NUPGCM_ERR_CUDA = -2,      /* a CUDA runtime call failed */
     NUPGCM_ERR_NO_DEVICE = -3, /* no CUDA device / not an sm_100 device */
-    NUPGCM_ERR_NCCL = -4,      /* NCCL unavailable or a NCCL call failed */
+    NUPGCM_ERR_COMM = -4,      /* a sharded (multi-GPU) solve aborted: a peer did not answer within the watchdog */
     NUPGCM_ERR_ALLOC = -5      /* host or device allocation failed */
 } nupgcm_status;
 
@@ -193,6 +193,11 @@ typedef struct {
     float   sm_mhz;        /* GMRES: SM clock the kernel actually ran at (clock64 / globaltimer) */
     float   reserved2;
 } nupgcm_solve_stats;
+
+/* sizeof(nupgcm_solve_stats) as this library was built: a host binding asserts it against its own
+ * mirror of the struct at load time (a shorter mirror would be overrun: the library writes the whole
+ * struct).  nupgcm_version() / 100 is the ABI major version. */
+int64_t nupgcm_solve_stats_size(void);
 
 /* CG with Jacobi/scalar left preconditioner (CgWorkspace, src/evolution.jl:118-126) */
 int32_t nupgcm_cg_solve(const nupgcm_csr *A, const nupgcm_vec *dinv, double pscale,

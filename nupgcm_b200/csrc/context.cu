@@ -6,6 +6,8 @@ char g_nupgcm_err[512] = "";
 
 extern "C" int32_t nupgcm_version(void) { return NUPGCM_B200_VERSION; }
 
+extern "C" int64_t nupgcm_solve_stats_size(void) { return (int64_t)sizeof(nupgcm_solve_stats); }
+
 extern "C" const char *nupgcm_last_error(const nupgcm_ctx *ctx) {
     return ctx ? ctx->err : g_nupgcm_err;
 }

@@ -2219,7 +2219,7 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
         cudaFree(d_trace);
     }
     if (res[7] != 0.0)
-        return nupgcm_fail(ctx, NUPGCM_ERR_CUDA, "%s",
+        return nupgcm_fail(ctx, comm ? NUPGCM_ERR_COMM : NUPGCM_ERR_CUDA, "%s",
                            "persistent solver kernel aborted: cross-CTA wait watchdog expired");
     const int64_t hist_len = (int64_t)res[6];
     if (hist_cap > 0 && hist_len > 0)
@@ -2619,7 +2619,7 @@ extern "C" int32_t nupgcm_diag_xreduce(nupgcm_comm *comm, int32_t count, int32_t
     if (es != cudaSuccess) { comm->broken = 1; NUPGCM_CUDA(ctx, es); }
     if (ctx->h_scalars[7] != 0.0) {
         comm->broken = 1;
-        return nupgcm_fail(ctx, NUPGCM_ERR_CUDA, "%s", "diag kernel aborted: cross-rank wait watchdog expired");
+        return nupgcm_fail(ctx, NUPGCM_ERR_COMM, "%s", "diag kernel aborted: cross-rank wait watchdog expired");
     }
     comm->xgen += (unsigned)ctx->h_scalars[13];
     *us_per_reduction = (float)(ctx->h_scalars[1] * 1e-3 / reps);

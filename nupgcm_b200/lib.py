@@ -109,7 +109,7 @@ SIGNATURES = {
     "nupgcm_rhs_adv": [_P, c_int32, c_double, c_double, _P, _P, _P, _P, _P],
     "nupgcm_rhs_combine": [_P, _P, c_double, c_double, _P, _P, _P, _P, _P],
 }
-OTHER_SYMBOLS = ["nupgcm_version", "nupgcm_last_error"]
+OTHER_SYMBOLS = ["nupgcm_version", "nupgcm_last_error", "nupgcm_solve_stats_size"]
 
 _lib = None
 
@@ -132,6 +132,11 @@ def load():
     lib.nupgcm_version.argtypes = []
     lib.nupgcm_last_error.restype = c_char_p
     lib.nupgcm_last_error.argtypes = [_P]
+    lib.nupgcm_solve_stats_size.restype = c_int64
+    lib.nupgcm_solve_stats_size.argtypes = []
+    if lib.nupgcm_solve_stats_size() != C.sizeof(SolveStats):
+        raise NupgcmError(f"ABI mismatch: nupgcm_solve_stats is {lib.nupgcm_solve_stats_size()} bytes in the "
+                          f"library, {C.sizeof(SolveStats)} in this binding")
     _lib = lib
     return lib
 
