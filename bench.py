@@ -1,33 +1,34 @@
 #!/usr/bin/env python
 """Benchmark of nuPGCM's per-timestep solve path on B200 (BASELINE.json metric: timesteps/sec,
-bowl3D, FP64).
+bowl3D, FP64, at 1/2/4/8 B200).
 
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
-Workload at every N: BASELINE.json configs[1] — bowl3D h=0.08 mesh, examples/bowl_mixing.jl set-up
-(ε=0.2, α=½, μϱ=1, BDF2 Δt=1e-3, b(0)=0.1 exp(−(z+H)/(0.1α)), initial inversion), synthetic
-forcing, random-free deterministic data.  A "step" is one model timestep: element RHS assembly +
-RHS combine + CG solve (evolve!) and SpMV + restarted GMRES(20) solve (invert!) with the
-reference's default tolerances (atol = rtol = 1e-6), plus the blow-up check.
+Workload at every N (north_star: "timesteps/sec reported at 1/2/4/8 B200 on a refined bowl3D mesh"):
+the once-refined bowl3D mesh (h = 0.04: the shipped h = 0.08 mesh of examples/bowl_mixing.jl refined
+once, N = 263 159 velocity + pressure DOFs, 14.8 M non-zeros — the mesh of BASELINE configs[2]) with
+the examples/bowl_mixing.jl set-up (ε=0.2, α=½, μϱ=1, BDF2 Δt=1e-3, b(0)=0.1 exp(−(z+H)/(0.1α)), initial
+inversion).  A "step" is one model timestep: element RHS assembly + RHS combine + CG solve (evolve!) and
+SpMV + restarted GMRES(20) solve (invert!) with the reference's default tolerances (atol = rtol = 1e-6),
+plus the blow-up check.  It fits one GPU; for N > 1 (torchrun, one rank per GPU) the SAME simulation is
+stepped with both Krylov solves row-block sharded over the N GPUs ("strong" scaling).
 
-Lines printed (rank 0, one JSON line):
-  value     timesteps/s with the state resident in HBM (device time, CUDA events per step)
-  e2e       same metric through the public Python API with the state on the HOST: every step
-            uploads (u, p, b) from host memory and downloads the new (u, p, b), as the reference's
-            host-resident state does (src/model.jl:275,282,312)
-  roofline  the dominant kernel (persistent GMRES): algorithmic bytes of its iterations / its
-            CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline  the CPU oracle (reference's CPU algorithm: LU factor once, direct solves per
-            step + NumPy element RHS) timed on a bounded sample of the same workload
-`--impl reference` times that CPU path alone with the same metric/config.
-
-For N > 1 (launched by torchrun, one rank per GPU) the SAME workload is stepped once, with both
-Krylov solves row-block sharded over the N GPUs (halo rows and dot-product words travel through
-peer memory over NVLink inside the persistent kernels; element RHS and the small vector kernels
-are replicated), so scaling is "strong".  The h=0.08 system (N=31 395) fits in the shared memory of
-ONE B200 and is bound by reduction latency, so it cannot speed up across GPUs; the `refined` object
-of the same JSON line therefore also times BASELINE configs[2] — the inversion-only GMRES(20)
-solve on the refined h=0.04 mesh (N=263 159) — at the same N, which is where sharding pays.
+One JSON line (rank 0):
+  value      timesteps/s, state resident in HBM (CUDA events per step), with orth = mgs: modified
+             Gram-Schmidt, what Krylov.jl does and the API default — the parity configuration
+  e2e        same through the public Python API with the state on the HOST: every step uploads (u, p, b)
+             from pinned host memory and downloads the new (u, p, b) (src/model.jl:275,282,312)
+  cgs2f      the same two numbers with the two-reduction CGS2 orthogonalisation (orth = cgs2f)
+  secondary  BASELINE configs[1] (shipped h = 0.08 mesh, N = 31 395), both orthogonalisations
+             and `tight`: timesteps/s there when the solves are driven to a relative residual of 1e-10
+             (north_star's parity tolerance) instead of the reference's 1e-6
+  parity     true relative residual of the last inversion, mgs-vs-cgs2f and sharded-vs-single-GPU
+             relative differences of the fields after the timed steps
+  roofline   the dominant kernel (persistent GMRES): algorithmic bytes of its iterations / its
+             CUDA-event duration against MEASURED_PEAKS.json hbm_gbs (mgs; `roofline_cgs2f` for the other)
+  cpu_baseline  the CPU port of the same algorithm (oracle/: Krylov.jl restatement + NumPy element RHS)
+             on a bounded sample, see cpu_krylov_sample
+`--impl reference` prints that CPU measurement alone with the same metric/config.
 """
 from __future__ import annotations
 
@@ -46,13 +47,20 @@ sys.path.insert(0, ROOT)
 
 METRIC = "timesteps/sec (bowl3D, FP64)"
 UNIT = "timesteps/s"
+# GMRES / CG iterations of one timestep of the workload, recorded from this benchmark's own GPU run
+# (profiles/bench_r02_n1.json, orth = mgs); the CPU legs time a bounded number of iterations and scale
+# to these counts (the CPU oracle and the GPU kernels run the same recurrences: counts agree to the
+# spread documented in BASELINE.md §5)
+RECORDED_ITERS = os.path.join(ROOT, "profiles", "iterations_h0.04_r02.json")
 
 
-def workload_config(h):
-    return {"workload": f"bowl3D h={h:g} mesh, examples/bowl_mixing.jl set-up (BASELINE configs[1]): "
-                        "evolve! (element RHS + CG) + invert! (GMRES(20), P=I/h^3), atol=rtol=1e-6",
-            "mesh_h": h, "l2": "flushed between timed steps (256 MiB fill); the 29 MB matrix is "
-                              "re-read thousands of times inside one step regardless"}
+def workload_config(level):
+    h = 0.08 / 2 ** level
+    return {"workload": f"bowl3D h={h:g} mesh" + (" (shipped h=0.08 mesh refined once)" if level == 1 else "")
+                        + ", examples/bowl_mixing.jl set-up: evolve! (element RHS + CG) + invert! "
+                          "(GMRES(20), P=I/h^3), atol=rtol=1e-6",
+            "mesh_h": h, "l2": "flushed between timed steps (256 MiB fill); the 148 MB matrix does not fit "
+                               "in the 126 MB L2 and is streamed from HBM every iteration"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -64,9 +72,9 @@ def peaks():
 
 
 def measured_traffic(kernel="k_gmres"):
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/ncu_traffic_r01.json, written from tools/profile_round.sh output); None if absent."""
-    p = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture
+    (profiles/ncu_traffic_r02.json, written from tools/profile_round.sh output); None if absent."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")
     try:
         return float(json.load(open(p))[kernel]["dram_bytes_per_launch"])
     except Exception:
@@ -149,18 +157,81 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_run(w, ops, steps, warmup):
-    """The reference's CPU algorithm on this box's host cores: LU factorisations at set-up
-    (src/inversion.jl:58, src/evolution.jl:152,170), then per step NumPy element RHS + two
-    triangular-solve pairs.  Returns (timesteps/s, seconds per step list)."""
-    from oracle.stepping import cpu_model_for
-    m = cpu_model_for(w, ops, solver="direct")
-    m.invert()                                   # examples/bowl_mixing.jl:194 (also factorises)
-    m.run(n_steps=warmup)
-    t0 = time.perf_counter()
-    m.run(n_steps=steps)
-    dt = time.perf_counter() - t0
-    return steps / dt, dt
+class ThreadedCSR:
+    """`A @ x` with the rows of a SciPy CSR matrix split over `threads` threads (SciPy's csr_matvec
+    releases the GIL): the CPU baseline's SpMV on all host cores."""
+
+    def __init__(self, A, threads):
+        from concurrent.futures import ThreadPoolExecutor
+        self.shape = A.shape
+        cuts = np.linspace(0, A.shape[0], threads + 1).astype(int)
+        self.blocks = [A[cuts[i]:cuts[i + 1]] for i in range(threads)]
+        self.cuts = cuts
+        self.pool = ThreadPoolExecutor(threads)
+
+    def __matmul__(self, x):
+        out = np.empty(self.shape[0])
+
+        def work(i):
+            out[self.cuts[i]:self.cuts[i + 1]] = self.blocks[i] @ x
+        list(self.pool.map(work, range(len(self.blocks))))
+        return out
+
+
+def recorded_iterations():
+    try:
+        return json.load(open(RECORDED_ITERS))
+    except Exception:
+        return {"gmres_per_step": 900.0, "cg_per_step": 8.0, "source": "fallback guess (no recorded run)"}
+
+
+def cpu_krylov_sample(w, ops, steps, warmup, threads, gmres_sample=40):
+    """The CPU port of the path on this box's host cores.  One "step" of the sample = the element RHS
+    assembly + RHS combine (complete), the evolution CG solve (complete) and `gmres_sample` iterations of
+    the inversion's GMRES(20) from the benchmark's initial state; the GMRES time is scaled to the
+    iteration count one timestep of this workload needs (recorded_iterations).  The reference's own CPU
+    path would LU-factorise the 263 159-row saddle-point matrix first (src/inversion.jl:58; SuperLU needs
+    more than 10 minutes and 5 GB for it on this host) — not a bounded sample; the Krylov port is the
+    reference's GPU algorithm (src/iterative_solvers.jl:58) on the CPU.
+    Returns (timesteps/s, description)."""
+    from oracle import krylov
+    from oracle.element_rhs import rhs_adv, rhs_combine
+    rec = recorded_iterations()
+    A = ThreadedCSR(ops["A"].tocsr(), threads) if threads > 1 else ops["A"].tocsr()
+    p = w.params
+    dt = w.timestepper_kwargs["Δt"]
+    θ = 2.0 / 3.0 * dt * p.α ** 2 * p.ε ** 2 / p.μϱ
+    Ae = (ops["M"] + θ * (ops["Kh"] + ops["Kv"])).tocsr()
+    dinv = 1.0 / Ae.diagonal()
+    nu = ops["nu"]
+    xb = ops["b_init"].copy()
+    xu = np.zeros(ops["A"].shape[0])
+    M = np.full(xu.size, ops["pscale"])
+    t_rhs = t_cg = t_gm = 0.0
+    n_cg = 0
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        adv = rhs_adv(ops["tables"], 2, dt, p.N2, xb, xb, xu[:nu], xu[:nu])
+        y = rhs_combine(adv, θ, dt, ops["rhs_diff"], ops["rhs_flux"], ops["rhs_m"], ops["rhs_h"], ops["rhs_v"])
+        t1 = time.perf_counter()
+        xb_new, st = krylov.cg(Ae, y, x0=xb, M=dinv, atol=1e-6, rtol=1e-6, history=False)
+        t2 = time.perf_counter()
+        yi = ops["B"] @ xb_new + ops["b0"]
+        xu_new, sg = krylov.gmres(A, yi, x0=xu, M=M, atol=1e-6, rtol=1e-6, itmax=gmres_sample, memory=20, history=False)
+        t3 = time.perf_counter()
+        if s >= warmup:
+            t_rhs += t1 - t0
+            t_cg += t2 - t1
+            t_gm += (t3 - t2) / max(sg.niter, 1)
+            n_cg += st.niter
+        # (the sample always restarts from the benchmark's initial state: it times iterations, not a trajectory)
+    per_step = t_rhs / steps + t_cg / steps + t_gm / steps * rec["gmres_per_step"]
+    desc = (f"{steps} sample steps after {warmup} warm-up: element RHS + combine ({1e3 * t_rhs / steps:.0f} ms) and the "
+            f"evolution CG solve ({n_cg / steps:.0f} iterations, {1e3 * t_cg / steps:.0f} ms) complete, "
+            f"{gmres_sample} GMRES(20) iterations of the inversion ({1e3 * t_gm / steps:.1f} ms each) scaled to the "
+            f"{rec['gmres_per_step']:.0f} iterations a timestep needs ({rec.get('source', RECORDED_ITERS)}); "
+            f"NumPy/SciPy port of Krylov.jl CG/GMRES (oracle/), SpMV on {threads} thread(s)")
+    return 1.0 / per_step, desc
 
 
 def reference_arm(args):
@@ -168,81 +239,56 @@ def reference_arm(args):
     if rank != 0:
         return
     from nupgcm_b200 import workloads as W
-    w = W.bowl_example(h=args.h)
+    w = W.bowl_example(mesh=W.refined_bowl(args.level)) if args.level > 0 else W.bowl_example()
     ops = W.host_operands(w)
-    steps = max(1, args.steps)
-    val, secs = cpu_reference_run(w, ops, steps, min(args.warmup, 2))
-    sample = (f"{steps} timesteps of the same workload after LU factorisation (SciPy SuperLU "
-              "stands in for UMFPACK); single-threaded triangular solves + NumPy element RHS")
+    cores = os.cpu_count() or 1
+    steps = max(1, min(args.steps, 5))           # each sample step is ~5-10 s of CPU work
+    t0 = time.perf_counter()
+    val, sample = cpu_krylov_sample(w, ops, steps, args.warmup, cores)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 / val,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / val,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(args.h),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "data": "synthetic", "config": workload_config(args.level),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample + f"; {steps} of the {args.steps} requested steps were sampled "
+                                            f"({time.perf_counter() - t0:.0f} s of CPU time)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def refined_leg(args, arch, ctx, orth, world, barrier, dist):
-    """BASELINE configs[2]: inversion-only GMRES(20) solve on the refined bowl3D mesh (h=0.04, one
-    refinement of the shipped h=0.08 mesh, N=263 159), cold start, bounded to --refined-iters
-    iterations; sharded over the ranks when world > 1."""
-    import nupgcm_b200 as npg
-    from nupgcm_b200 import lib
-    from nupgcm_b200 import workloads as W
-    w = W.bowl_example(mesh=W.refined_bowl(1))
-    fe = w.fe_data()
-    from nupgcm_b200.inversion import permuted_inversion_system
-    A, B, b0, pscale = permuted_inversion_system(fe, w.params, w.forcings)
-    b_init = fe.spaces.B.interpolate(w.b0)[0][fe.dofs.p_b]
-    inv = npg.InversionToolkit(arch, A, pscale, B, b0, orth=orth, drop_zeros=True,
-                               itmax=args.refined_iters, history=False)
-    xb = ctx.vector(b_init)
-    n = A.shape[0]
-    nnz = inv.solver.A.info()["nnz_stored"]
-    ms, its = [], []
-    for rep in range(3):                       # first pass warms up (set-up of the sharded tables)
-        inv.solver.x.fill(0.0)
-        barrier()
-        npg.inversion.invert_(inv, xb)
-        ms.append(inv.solver.stats.timer * 1e3)
-        its.append(inv.solver.stats.niter)
-    t_ms, it = float(np.min(ms[1:])), int(its[-1])
-    if dist is not None:
-        import torch
-        t = torch.tensor([t_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_ms = float(t[0])
-    peak, _ = peaks()
-    gbs = gmres_bytes(n, nnz, it) / (t_ms * 1e-3) / 1e9
-    info = inv.solver.A.shard_info(0) if world > 1 else None
-    return {"workload": "bowl3D h=0.04 (h=0.08 mesh refined once), inversion-only GMRES(20) solve, cold start, "
-                        f"bounded to {args.refined_iters} iterations (BASELINE configs[2])",
-            "N": n, "nnz": nnz, "n_gpus": world, "iterations": it, "ms": t_ms,
-            "us_per_iter": 1e3 * t_ms / max(it, 1), "solves_per_s": 1e3 / t_ms,
-            "rnorm_over_rnorm0": float(inv.solver.stats.rnorm / max(inv.solver.stats.rnorm0, 1e-300)),
-            "algorithmic_gbs": gbs, "frac_of_hbm_peak_all_gpus": gbs / (peak * world),
-            "rank0_rows": None if info is None else [info["row_begin"], info["row_end"]],
-            "rank0_halo_rows": None if info is None else info["halo_rows"]}
-
-
 # ---------------------------------------------------------------------------------------------
+def true_residual(ctx, inv):
+    """‖A x − y‖ / ‖y‖ of the inversion system as it stands (device SpMV + norms)."""
+    s = inv.solver
+    r = ctx.vector(len(s.y))
+    s.A.spmv(s.x, r)
+    r.axpby(1.0, s.y, -1.0)
+    return r.norm2() / max(s.y.norm2(), 1e-300)
+
+
+def step_model(npg, ctx, m, steps, flush):
+    ms = []
+    for _ in range(steps):
+        flush.fill(0.0)
+        ctx.timer_start()
+        npg.run_(m, n_steps=1, resume=True)      # one continuous run, timed step by step
+        ms.append(ctx.timer_stop())
+    return ms
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--h", type=float, default=0.08)
-    ap.add_argument("--orth", default="cgs2f", choices=["mgs", "cgs2", "cgs2f"],
-                    help="Arnoldi orthogonalisation: cgs2f (CGS2 with 2 grid reductions per iteration, "
-                         "default), cgs2 (3 reductions) or mgs (Krylov.jl order, k+1 reductions)")
+    ap.add_argument("--level", type=int, default=1, help="refinements of the shipped h=0.08 mesh (1: h=0.04, the headline)")
     ap.add_argument("--keep-zeros", action="store_true", help="store Gridap's explicit zeros too")
-    ap.add_argument("--cpu-sample-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-refined", action="store_true", help="skip the h=0.04 inversion-only leg")
-    ap.add_argument("--refined-iters", type=int, default=2000)
+    ap.add_argument("--no-secondary", action="store_true", help="skip the h=0.08 (BASELINE configs[1]) leg")
+    ap.add_argument("--no-tight", action="store_true", help="skip the rtol=1e-10 leg")
+    ap.add_argument("--tight-steps", type=int, default=3)
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -262,31 +308,17 @@ def main():
     from nupgcm_b200 import lib
     from nupgcm_b200 import workloads as W
 
-    w = W.bowl_example(h=args.h)
+    t_setup = time.perf_counter()
+    w = W.bowl_example(mesh=W.refined_bowl(args.level)) if args.level > 0 else W.bowl_example()
     ops = W.host_operands(w)
-    comm = None
+    t_setup = time.perf_counter() - t_setup
     if world > 1:
         from nupgcm_b200.sharding import torch_comm
-        arch, comm = torch_comm(max_n=300000)        # largest system solved below: h=0.04, N=263 159
+        arch, comm = torch_comm(max_n=ops["A"].shape[0] + 16)
     else:
         arch = npg.GPU(local)
     ctx = arch.ctx
-    orth = {"mgs": lib.ORTH_MGS, "cgs2": lib.ORTH_CGS2, "cgs2f": lib.ORTH_CGS2_FUSED}[args.orth]
-
-    def make_model():
-        inv = npg.InversionToolkit(arch, ops["A"], ops["pscale"], ops["B"], ops["b0"], orth=orth,
-                                   drop_zeros=not args.keep_zeros)
-        ts = w.timestepper()
-        ts.t_stop = float("inf")
-        evo = npg.EvolutionToolkit(arch, ops, w.params, w.forcings, ts)
-        m = npg.Model(arch, w.params, w.forcings, w.fe_data(), inv, evo, ts, tables=ops["tables"])
-        m.xb.upload(ops["b_init"])
-        if dist is not None:
-            dist.barrier()                       # ranks enter the first collective solve together
-        npg.invert_(m)                           # examples/bowl_mixing.jl:194
-        return m
-
-    flush = ctx.vector(32 * 1024 * 1024)         # 256 MiB > 126 MB L2
+    ORTH = {"mgs": lib.ORTH_MGS, "cgs2f": lib.ORTH_CGS2_FUSED}
 
     def barrier():
         ctx.synchronize()
@@ -294,106 +326,195 @@ def main():
             dist.barrier()
         ctx.synchronize()
 
-    # ---------------- device-resident run -------------------------------------------------
-    m = make_model()
-    init_gmres = m.inversion.solver.stats.niter
-    npg.run_(m, n_steps=args.warmup)
-    barrier()
-    launches0 = ctx.launch_count()
-    step_ms = []
-    with ClockSampler(local) as clocks:
-        t_wall0 = time.perf_counter()
-        for _ in range(args.steps):
-            flush.fill(0.0)
-            ctx.timer_start()
-            npg.run_(m, n_steps=1, resume=True)     # one 100-step-style run, timed step by step
-            step_ms.append(ctx.timer_stop())
-        barrier()
-        t_wall = time.perf_counter() - t_wall0
-    launches = ctx.launch_count() - launches0 - args.steps        # minus the L2-flush fills
-    total_ms = float(np.sum(step_ms))
-    log = m.step_log[-args.steps:]
+    def make_model(wl, o, orth, a=None, **tol):
+        a = arch if a is None else a
+        inv = npg.InversionToolkit(a, o["A"], o["pscale"], o["B"], o["b0"], orth=ORTH[orth],
+                                   drop_zeros=not args.keep_zeros, **tol)
+        ts = wl.timestepper()
+        ts.t_stop = float("inf")
+        evo = npg.EvolutionToolkit(a, o, wl.params, wl.forcings, ts, **tol)
+        m = npg.Model(a, wl.params, wl.forcings, wl.fe_data(), inv, evo, ts, tables=o["tables"])
+        m.xb.upload(o["b_init"])
+        if dist is not None and a is arch:
+            dist.barrier()                       # ranks enter the first collective solve together
+        npg.invert_(m)                           # examples/bowl_mixing.jl:194
+        return m
 
-    # ---------------- end-to-end run: host-resident state ----------------------------------
-    m2 = make_model()
+    flush = ctx.vector(32 * 1024 * 1024)         # 256 MiB > 126 MB L2
     d = w.fe_data().dofs
-    x0 = m2.inversion.solver.x.download()[d.inv_p_inversion]
-    host = {"u": x0[:d.nu].copy(), "p": x0[d.nu:].copy(), "b": m2.xb.download()[d.inv_p_b]}
-    npg.run_(m2, n_steps=args.warmup, sync_state=True, host_state=host)
-    barrier()
-    t0 = time.perf_counter()
-    npg.run_(m2, n_steps=args.steps, sync_state=True, host_state=host, resume=True)
-    barrier()
-    e2e_s = time.perf_counter() - t0
     state_bytes = 8 * (d.nu + d.np + d.nb)
-
-    # ---------------- max over ranks ---------------------------------------------------------
-    if dist is not None:
-        import torch
-        t = torch.tensor([total_ms, e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s = float(t[0]), float(t[1])
-    value = args.steps / (total_ms * 1e-3)          # one simulation, sharded over `world` GPUs
-    e2e = args.steps / e2e_s
-
-    # ---------------- roofline of the dominant kernel (persistent GMRES) ---------------------
-    infoA = m.inversion.solver.A.info()
-    n, nnz = infoA["n_rows"], infoA["nnz_stored"]
-    g_iters = np.array([r["gmres_iters"] for r in log], dtype=float)
-    g_ms = np.array([r["gmres_ms"] for r in log], dtype=float)
-    c_iters = np.array([r["cg_iters"] for r in log], dtype=float)
-    c_ms = np.array([r["cg_ms"] for r in log], dtype=float)
     peak, peak_src = peaks()
-    g_bytes = float(np.mean([gmres_bytes(n, nnz, k) for k in g_iters]))
-    achieved = g_bytes / (float(np.mean(g_ms)) * 1e-3) / 1e9 if g_ms.mean() > 0 else 0.0
-    peak_src += "" if world == 1 else f" x {world} GPUs"
-    peak *= world
-    roofline = {"bound": "hbm", "kernel": "k_gmres (persistent GMRES(20), one launch per invert!"
-                                          + (f", sharded over {world} GPUs)" if world > 1 else ")"),
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": measured_traffic() if world == 1 else None, "peak_source": peak_src,
-                "traffic_note": "DRAM read+write bytes of one k_gmres launch (ncu --set full, "
-                                "profiles/ncu_gmres_r01.txt): the matrix is read from HBM once per solve and "
-                                "then served from shared memory, so traffic << algorithmic bytes",
-                "algorithmic_bytes_per_launch": g_bytes, "ms_per_launch": float(g_ms.mean()),
-                "nnz_counted": nnz, "share_of_step": float(g_ms.sum() / total_ms)}
+
+    def run_variant(orth, clocks=None):
+        """Device-resident timed steps, then the same simulation continued with a host-resident state."""
+        m = make_model(w, ops, orth)
+        init_gmres = m.inversion.solver.stats.niter
+        npg.run_(m, n_steps=args.warmup)
+        barrier()
+        launches0 = ctx.launch_count()
+        t_wall0 = time.perf_counter()
+        if clocks is not None:
+            with clocks:
+                ms = step_model(npg, ctx, m, args.steps, flush)
+                barrier()
+        else:
+            ms = step_model(npg, ctx, m, args.steps, flush)
+            barrier()
+        t_wall = time.perf_counter() - t_wall0
+        launches = ctx.launch_count() - launches0 - args.steps      # minus the L2-flush fills
+        log = m.step_log[-args.steps:]
+        fields = (m.inversion.solver.x.download(), m.xb.download())
+        resid = true_residual(ctx, m.inversion)
+        # end to end: host-resident state (Gridap order), pinned buffers, copies inside the timed region
+        x0 = fields[0][d.inv_p_inversion]
+        host = {"u": x0[:d.nu].copy(), "p": x0[d.nu:].copy(), "b": fields[1][d.inv_p_b]}
+        npg.run_(m, n_steps=1, sync_state=True, host_state=host, resume=True)      # builds the staging buffers
+        barrier()
+        t0 = time.perf_counter()
+        npg.run_(m, n_steps=args.steps, sync_state=True, host_state=host, resume=True)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        e2e_iters = float(np.mean([r["gmres_iters"] for r in m.step_log[-args.steps:]]))
+        total_ms = float(np.sum(ms))
+        if dist is not None:
+            import torch
+            t = torch.tensor([total_ms, e2e_s], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms, e2e_s = float(t[0]), float(t[1])
+        infoA = m.inversion.solver.A.info()
+        n, nnz = infoA["n_rows"], infoA["nnz_stored"]
+        g_iters = np.array([r["gmres_iters"] for r in log], dtype=float)
+        g_ms = np.array([r["gmres_ms"] for r in log], dtype=float)
+        c_iters = np.array([r["cg_iters"] for r in log], dtype=float)
+        c_ms = np.array([r["cg_ms"] for r in log], dtype=float)
+        g_bytes = float(np.mean([gmres_bytes(n, nnz, k) for k in g_iters]))
+        achieved = g_bytes / (float(np.mean(g_ms)) * 1e-3) / 1e9 if g_ms.mean() > 0 else 0.0
+        res = {
+            "orth": orth, "value": args.steps / (total_ms * 1e-3), "ms_per_step": total_ms / args.steps,
+            "e2e": args.steps / e2e_s, "e2e_gmres_per_step": e2e_iters, "gpu_launches": int(launches), "wall_ms_per_step": 1e3 * t_wall / args.steps,
+            "iterations": {"gmres_per_step_mean": float(g_iters.mean()), "gmres_per_step_min": float(g_iters.min()),
+                           "gmres_per_step_max": float(g_iters.max()), "cg_per_step_mean": float(c_iters.mean()),
+                           "gmres_us_per_iter": float(1e3 * g_ms.sum() / max(g_iters.sum(), 1)),
+                           "cg_us_per_iter": float(1e3 * c_ms.sum() / max(c_iters.sum(), 1)),
+                           "initial_inversion_gmres_iters": int(init_gmres),
+                           "all_solved": bool(all(r["gmres_solved"] and r["cg_solved"] for r in log))},
+            "roofline": {"bound": "hbm", "kernel": f"k_gmres (persistent GMRES(20), orth={orth}, one launch per invert!"
+                                                   + (f", sharded over {world} GPUs)" if world > 1 else ")"),
+                         "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
+                         "traffic": measured_traffic(f"k_gmres_{orth}") if world == 1 else None,
+                         "peak_source": peak_src + ("" if world == 1 else f" x {world} GPUs"),
+                         "algorithmic_bytes_per_launch": g_bytes, "ms_per_launch": float(g_ms.mean()),
+                         "nnz_counted": nnz, "share_of_step": float(g_ms.sum() / total_ms)},
+            "true_rel_residual_last_inversion": float(resid), "N": n, "nnz": nnz,
+        }
+        return res, fields, m
+
+    clocks = ClockSampler(local)
+    mgs, f_mgs, m_mgs = run_variant("mgs", clocks)
+    del m_mgs
+    cgs, f_cgs, m_cgs = run_variant("cgs2f")
+    del m_cgs
+    rel = lambda a, b: float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))      # noqa: E731
+    parity = {"true_rel_residual_last_inversion": {"mgs": mgs["true_rel_residual_last_inversion"],
+                                                   "cgs2f": cgs["true_rel_residual_last_inversion"]},
+              "mgs_vs_cgs2f_rel_diff": {"u_p": rel(f_cgs[0], f_mgs[0]), "b": rel(f_cgs[1], f_mgs[1])},
+              "note": "fields after warmup+steps timesteps at the reference's atol=rtol=1e-6: two correct solvers "
+                      "agree to the solver tolerance, not to 1e-8 (that is the `tight` leg and the tests)",
+              "sharded_vs_single_rel_diff": None}
+    if world > 1 and rank == 0:
+        # the same simulation on this rank's GPU alone (not collective): sharding must not change the answer
+        single = make_model(w, ops, "mgs", a=npg.GPU(local))
+        npg.run_(single, n_steps=args.warmup)
+        npg.run_(single, n_steps=args.steps, resume=True)
+        parity["sharded_vs_single_rel_diff"] = {"u_p": rel(f_mgs[0], single.inversion.solver.x.download()),
+                                                "b": rel(f_mgs[1], single.xb.download()),
+                                                "gmres_iters_per_step_single": float(np.mean(
+                                                    [r["gmres_iters"] for r in single.step_log[-args.steps:]]))}
+        del single
+    barrier()
 
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "metric": METRIC, "value": mgs["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": mgs["ms_per_step"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": dict(workload_config(args.h), N=n, nnz=nnz, nb=d.nb, orth=args.orth,
-                       drop_zeros=not args.keep_zeros,
+        "config": dict(workload_config(args.level), N=mgs["N"], nnz=mgs["nnz"], nb=d.nb, orth="mgs",
+                       drop_zeros=not args.keep_zeros, host_setup_s=t_setup,
                        parallelism="single GPU" if world == 1 else
                        f"CG and GMRES row-block sharded over {world} GPUs (peer-memory halo pushes and "
                        "reductions inside the persistent kernels); element RHS and vector kernels replicated"),
-        "iterations": {"gmres_per_step_mean": float(g_iters.mean()), "gmres_per_step_min": float(g_iters.min()),
-                       "gmres_per_step_max": float(g_iters.max()), "cg_per_step_mean": float(c_iters.mean()),
-                       "gmres_us_per_iter": float(1e3 * g_ms.sum() / max(g_iters.sum(), 1)),
-                       "cg_us_per_iter": float(1e3 * c_ms.sum() / max(c_iters.sum(), 1)),
-                       "initial_inversion_gmres_iters": int(init_gmres),
-                       "all_solved": bool(all(r["gmres_solved"] and r["cg_solved"] for r in log))},
-        "scaling_note": ("the h=0.08 system (N=31 395) lives in the shared memory of one GPU and is bound by "
-                         "reduction latency, so `value` stays flat under sharding by construction; the `refined` "
-                         "object times BASELINE configs[2] (h=0.04 inversion-only solve), the configuration quoted "
-                         "at 1/2/4/8 GPUs, in the same run"),
+        "iterations": mgs["iterations"],
         "clocks": clocks.summary(),
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": state_bytes,
-                "d2h_bytes_per_step": state_bytes},
-        "gpu_launches": int(launches),
-        "wall_ms_per_step": 1e3 * t_wall / args.steps,
-        "roofline": roofline,
+        "e2e": {"value": mgs["e2e"], "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes,
+                "gmres_per_step_mean": mgs["e2e_gmres_per_step"],
+                "note": "the steps that follow the device-timed ones in the same simulation (no L2 flush between them)"},
+        "gpu_launches": mgs["gpu_launches"], "wall_ms_per_step": mgs["wall_ms_per_step"],
+        "roofline": mgs["roofline"],
+        "cgs2f": {"value": cgs["value"], "ms_per_step": cgs["ms_per_step"], "e2e": cgs["e2e"],
+                  "e2e_gmres_per_step": cgs["e2e_gmres_per_step"],
+                  "iterations": cgs["iterations"], "gpu_launches": cgs["gpu_launches"]},
+        "roofline_cgs2f": cgs["roofline"],
+        "parity": parity,
     }
+
+    if not args.no_secondary:
+        w2 = W.bowl_example()
+        ops2 = W.host_operands(w2)
+        sec = {"workload": "bowl3D h=0.08 shipped mesh, examples/bowl_mixing.jl 100-step set-up (BASELINE configs[1]); "
+                           "N = 31 395 lives in the shared memory of one GPU and is bound by reduction latency"}
+        for orth in ("mgs", "cgs2f"):
+            m2 = make_model(w2, ops2, orth)
+            npg.run_(m2, n_steps=args.warmup)
+            barrier()
+            ms = step_model(npg, ctx, m2, args.steps, flush)
+            barrier()
+            tot = float(np.sum(ms))
+            if dist is not None:
+                import torch
+                t = torch.tensor([tot], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                tot = float(t[0])
+            lg = m2.step_log[-args.steps:]
+            gi = float(np.sum([r["gmres_iters"] for r in lg]))
+            sec[orth] = {"value": args.steps / (tot * 1e-3), "unit": UNIT,
+                         "gmres_per_step_mean": gi / args.steps,
+                         "gmres_us_per_iter": float(1e3 * np.sum([r["gmres_ms"] for r in lg]) / max(gi, 1))}
+            del m2
+        if not args.no_tight:
+            # north_star's parity tolerance: relative residual <= 1e-10 (the reference's GPU default is 1e-6); on this
+            # mesh, because GMRES(20) with the scalar preconditioner needs ~500 000 iterations per timestep for it at h = 0.04
+            mt = make_model(w2, ops2, "mgs", atol=0.0, rtol=1e-10)
+            npg.run_(mt, n_steps=1)
+            barrier()
+            ms = step_model(npg, ctx, mt, args.tight_steps, flush)
+            barrier()
+            tot = float(np.sum(ms))
+            if dist is not None:
+                import torch
+                t = torch.tensor([tot], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                tot = float(t[0])
+            lg = mt.step_log[-args.tight_steps:]
+            sec["tight"] = {"atol": 0.0, "rtol": 1e-10, "orth": "mgs", "steps": args.tight_steps,
+                            "value": args.tight_steps / (tot * 1e-3), "unit": UNIT,
+                            "gmres_per_step_mean": float(np.mean([r["gmres_iters"] for r in lg])),
+                            "cg_per_step_mean": float(np.mean([r["cg_iters"] for r in lg])),
+                            "true_rel_residual_last_inversion": float(true_residual(ctx, mt.inversion))}
+            del mt
+        out["secondary"] = sec
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, secs = cpu_reference_run(w, ops, args.cpu_sample_steps, 1)
-        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                               "sample": f"{args.cpu_sample_steps} timesteps of the same workload "
-                                         f"({secs:.1f} s) after LU factorisation; SciPy SuperLU direct "
-                                         "solves + NumPy element RHS, single-threaded"}
-    if not args.no_refined:
-        del m, m2
-        out["refined"] = refined_leg(args, arch, ctx, orth, world, barrier, dist)
+        cores = os.cpu_count() or 1
+        v1, s1 = cpu_krylov_sample(w, ops, 1, 1, 1)
+        vN, sN = cpu_krylov_sample(w, ops, 2, 1, cores)
+        out["cpu_baseline"] = {"value": vN, "unit": UNIT, "cores": cores, "kind": "port", "sample": sN,
+                               "value_1_core": v1}
     if rank == 0:
+        if world == 1:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            json.dump({"gmres_per_step": mgs["iterations"]["gmres_per_step_mean"],
+                       "cg_per_step": mgs["iterations"]["cg_per_step_mean"],
+                       "source": f"bench.py GPU run, orth=mgs, steps {args.warmup + 1}..{args.warmup + args.steps}"},
+                      open(os.path.join(ROOT, "gpurun_out", "iterations_h0.04_measured.json"), "w"))
         print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()

@@ -1673,8 +1673,71 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
             main_sync();
             pc.mark(0);
             double hsq = 0.0;                            // ‖q‖² after orthogonalisation
+            bool normalised = false;                     // V[k] already holds q / H
             if (a.orth == NUPGCM_ORTH_MGS) {
                 // h_i = v_i·q ; q −= h_i v_i, sequentially (one grid reduction per i)
+                constexpr int RMAX = MR ? 4 : 7;
+                if (r1 - r0 <= RMAX * nthr) {
+                    // Register-resident form (up to RMAX rows per thread): the thread keeps its rows of q and of
+                    // the current basis vector in registers and fetches its rows of v_{i+1} while the
+                    // reduction of h_i is in flight, so that between two reductions there is only register
+                    // arithmetic (one fma per row, then the next partial dot) — k+1 reductions in a row are what
+                    // modified Gram-Schmidt costs, nothing should be added to them.  Same operations on the
+                    // same rows in the same order as the streaming form below: bit-identical results.
+                    double qr[RMAX], vc[RMAX], vn[RMAX];
+                    const double *v0p = V.at(0);
+#pragma unroll
+                    for (int j = 0; j < RMAX; ++j) {
+                        const int row = r0 + tid + j * nthr;
+                        qr[j] = row < r1 ? q[row] : 0.0;
+                        vc[j] = row < r1 ? v0p[row] : 0.0;
+                    }
+                    for (int i = 0; i < k; ++i) {
+                        double part = 0.0;
+#pragma unroll
+                        for (int j = 0; j < RMAX; ++j) part = fma(vc[j], qr[j], part);
+                        if (i + 1 < k) {
+                            const double *vnp = V.at(i + 1);
+#pragma unroll
+                            for (int j = 0; j < RMAX; ++j) {
+                                const int row = r0 + tid + j * nthr;
+                                vn[j] = row < r1 ? vnp[row] : 0.0;
+                            }
+                        }
+                        pc.mark(1);
+                        const double h = gr.sum_threads<false>(part);
+                        pc.mark(2);
+                        if (tid == 0) sR[nr + i] = h;
+#pragma unroll
+                        for (int j = 0; j < RMAX; ++j) {
+                            qr[j] = fma(-h, vc[j], qr[j]);
+                            vc[j] = vn[j];
+                        }
+                    }
+                    double part = 0.0;
+                    halo_arm(hp, a, gr.gen);
+#pragma unroll
+                    for (int j = 0; j < RMAX; ++j) {
+                        const int row = r0 + tid + j * nthr;
+                        if (row < r1) {
+                            dst[row] = qr[j];
+                            halo_put(hp, dst + row, row, qr[j]);
+                            part = fma(qr[j], qr[j], part);
+                        }
+                    }
+                    pc.mark(1);
+                    hsq = gr.sum_threads<true>(part);     // publishes dst for the next gather
+                    pc.mark(2);
+                    // v_{k+1} = q / H straight from the registers (H is known to every thread now): saves the
+                    // store of the raw q and the normalisation sweep over it further down
+                    const double ih = 1.0 / sqrt(hsq);
+#pragma unroll
+                    for (int j = 0; j < RMAX; ++j) {
+                        const int row = r0 + tid + j * nthr;
+                        if (row < r1) q[row] = qr[j] * ih;
+                    }
+                    normalised = true;
+                } else {
                 double hprev = 0.0;
                 for (int i = 0; i < k; ++i) {
                     const double *vi = V.at(i);
@@ -1703,6 +1766,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
                 pc.mark(1);
                 hsq = gr.sum_threads<true>(part);     // publishes dst for the next gather
                 pc.mark(2);
+                }
             } else if (a.orth == NUPGCM_ORTH_CGS2_FUSED) {
                 // CGS2 with two grid reductions per iteration instead of three:
                 //   1. h₁ = Vᵀq ;            q₁ = q − V h₁ — q₁ is what the other CTAs will gather
@@ -1864,7 +1928,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
             if (!(solved || inner_tired || breakdown)) {
                 // v_{k+1} = q / Hbis on own rows (q already sits in V[k]); raw q was published in dst
                 inv_h = 1.0 / Hbis;
-                if (!fused)
+                if (!fused && !normalised)
                     for (int row = r0 + tid; row < r1; row += nthr) q[row] *= inv_h;
                 cur ^= 1;
             }
