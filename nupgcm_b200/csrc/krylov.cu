@@ -1530,6 +1530,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
     __shared__ double sR[kMaxMemory * (kMaxMemory + 1) / 2];
     __shared__ double s_flags[4];      // rnorm, inconsistent, -, Hbis
     __shared__ double s_seg[32];
+    __shared__ double s_dot[kMaxMemory + 1][kMainWarps];       // per-warp partial dots of the register-resident CGS2 form
     // fused CGS2: unrotated Hessenberg columns (packed: column j holds rows 0..j+1 at j(j+3)/2),
     // the second-pass coefficients h₂, the correction H̄ h₂ / H and per-warp partial norms
     __shared__ double sHbar[kMaxMemory * (kMaxMemory + 3) / 2], s_h2[kMaxMemory], s_corr[kMaxMemory + 1], s_wsum[kMainWarps];
@@ -1777,6 +1778,127 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
                 // vector INSIDE the span the next projection removes.  So q₁ of the next iteration is
                 // unchanged and only its coefficients need the correction h = Vᵀq̂ − c (VᵀV = I up to
                 // O(ε), c = O(ε): the neglected term is O(ε²)).  Equal to CGS2 in exact arithmetic.
+                constexpr int RF = MR ? 4 : 8;
+                if (r1 - r0 <= RF * (nthr - 32)) {
+                    // Register-resident form (up to RF rows per thread of warps 1..10; warp 0 owns no rows and does
+                    // the scalar recurrences while the others finish the vector): the thread keeps its rows of q
+                    // in registers through both projections and both updates, so each of the four passes reads
+                    // the basis rows once, with all loads of a pass independent, and q is read and written once
+                    // per iteration instead of eight times.
+                    const int t1 = tid - 32, nt = nthr - 32;
+                    double qr[RF];
+#pragma unroll
+                    for (int j = 0; j < RF; ++j) {
+                        const int row = r0 + t1 + j * nt;
+                        qr[j] = (t1 >= 0 && row < r1) ? q[row] : 0.0;
+                    }
+                    // (the basis vectors are taken two at a time so that 2 x RF loads are in flight per thread)
+                    auto dots = [&](int extra, double extra_val) {       // sm_in[i] <- this CTA's part of v_i . q (i < k)
+                        for (int i = 0; i < k; i += 2) {
+                            const double *va = V.at(i), *vb = V.at(i + 1 < k ? i + 1 : i);
+                            double xa[RF], xb[RF];
+#pragma unroll
+                            for (int j = 0; j < RF; ++j) {
+                                const int row = r0 + t1 + j * nt;
+                                const bool ok = t1 >= 0 && row < r1;
+                                xa[j] = ok ? va[row] : 0.0;
+                                xb[j] = ok ? vb[row] : 0.0;
+                            }
+                            double pa = 0.0, pb = 0.0;
+#pragma unroll
+                            for (int j = 0; j < RF; ++j) {
+                                pa = fma(xa[j], qr[j], pa);
+                                pb = fma(xb[j], qr[j], pb);
+                            }
+                            pa = warp_sum(pa);
+                            pb = warp_sum(pb);
+                            if (lane == 0) {
+                                s_dot[i][wid] = pa;
+                                if (i + 1 < k) s_dot[i + 1][wid] = pb;
+                            }
+                        }
+                        if (extra) {
+                            const double e = warp_sum(extra_val);
+                            if (lane == 0) s_dot[k][wid] = e;
+                        }
+                        main_sync();
+                        if (tid < k + extra) {
+                            double t = 0.0;
+                            for (int wv = 1; wv < nwarps; ++wv) t += s_dot[tid][wv];
+                            sm_in[tid] = t;
+                        }
+                        main_sync();
+                    };
+                    auto update = [&]() {                                // q <- q - V h, h = sm_out[0..k)
+                        for (int i = 0; i < k; i += 2) {
+                            const double *va = V.at(i), *vb = V.at(i + 1 < k ? i + 1 : i);
+                            const double ha = sm_out[i], hb = i + 1 < k ? sm_out[i + 1] : 0.0;
+                            double xa[RF], xb[RF];
+#pragma unroll
+                            for (int j = 0; j < RF; ++j) {
+                                const int row = r0 + t1 + j * nt;
+                                const bool ok = t1 >= 0 && row < r1;
+                                xa[j] = ok ? va[row] : 0.0;
+                                xb[j] = ok ? vb[row] : 0.0;
+                            }
+#pragma unroll
+                            for (int j = 0; j < RF; ++j) qr[j] = fma(-hb, xb[j], fma(-ha, xa[j], qr[j]));
+                        }
+                    };
+                    dots(0, 0.0);
+                    pc.mark(1);
+                    gr.sumN(k);
+                    pc.mark(2);
+                    update();
+                    double part = 0.0;
+                    halo_arm(hp, a, gr.gen);
+#pragma unroll
+                    for (int j = 0; j < RF; ++j) {
+                        const int row = r0 + t1 + j * nt;
+                        if (t1 >= 0 && row < r1) {
+                            dst[row] = qr[j];
+                            halo_put(hp, dst + row, row, qr[j]);
+                            part = fma(qr[j], qr[j], part);
+                        }
+                    }
+                    if (tid < k) sR[nr + tid] = have_corr ? sm_out[tid] - s_corr[tid] : sm_out[tid];
+                    dots(1, part);
+                    pc.mark(1);
+                    gr.sumN(k + 1, true);                          // also publishes dst (= q₁)
+                    pc.mark(2);
+                    double h2sq = 0.0;
+                    for (int i = 0; i < k; ++i) h2sq = fma(sm_out[i], sm_out[i], h2sq);
+                    hsq = fmax(sm_out[k] - h2sq, 0.0);
+                    const double Hb = sqrt(hsq);
+                    if (wid == 0) {
+                        const int hc = (k - 1) * (k + 2) / 2;      // packed offset of H̄ column k-1
+                        if (lane < k) {
+                            const double h = sR[nr + lane] + sm_out[lane];
+                            sR[nr + lane] = h;
+                            s_h2[lane] = sm_out[lane];
+                            sHbar[hc + lane] = h;
+                        } else if (lane == k) {
+                            sHbar[hc + k] = Hb;
+                        }
+                        __syncwarp();
+                        if (lane <= k) {
+                            double c = 0.0;
+                            for (int j = lane > 0 ? lane - 1 : 0; j < k; ++j) c = fma(sHbar[j * (j + 3) / 2 + lane], s_h2[j], c);
+                            s_corr[lane] = Hb > 0.0 ? c / Hb : 0.0;
+                        }
+                        __syncwarp();
+                        if (lane == 0) scalar_step(k, nr, hsq);
+                    } else {
+                        update();                                  // q₂ = q₁ − V h₂ ; v_{k+1} = q₂ / H
+                        const double ih = 1.0 / Hb;
+#pragma unroll
+                        for (int j = 0; j < RF; ++j) {
+                            const int row = r0 + t1 + j * nt;
+                            if (row < r1) q[row] = qr[j] * ih;
+                        }
+                    }
+                    have_corr = true;
+                } else {
                 const int nseg = nwarps / k > 0 ? nwarps / k : 1;
                 const int rows = r1 - r0;
                 const int seglen = (rows + nseg - 1) / nseg;
@@ -1866,6 +1988,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
                     }
                 }
                 have_corr = true;
+                }
             } else {
                 // CGS2: all k projections at once, twice; warp w handles basis vector w % k on
                 // row segment w / k.

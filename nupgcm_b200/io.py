@@ -171,12 +171,15 @@ def read_jld2(path: str) -> dict:
         addr = int.from_bytes(body[off + nl + ln:off + nl + ln + 8], "little") + base
         if name.startswith("_"):
             continue
-        dims, raw, is_f64 = (), None, False
+        dims, raw, is_f64, is_i64 = (), None, False, False
         for mt, mb in _messages(buf, addr):
             if mt == 1:
                 dims = tuple(int.from_bytes(mb[4 + 8 * i:12 + 8 * i], "little") for i in range(mb[1]))
             elif mt == 3:
                 is_f64 = (mb[0] & 0x0F) == 1 and int.from_bytes(mb[4:8], "little") == 8
+                # class 0 = fixed point: `t = 0` (an Int64) is what save_state writes for a model
+                # without a timestepper (IO.jl:3-4)
+                is_i64 = (mb[0] & 0x0F) == 0 and int.from_bytes(mb[4:8], "little") == 8
             elif mt == 8:
                 if mb[0] != 4:
                     raise ValueError("layout version 4 expected")
@@ -187,20 +190,32 @@ def read_jld2(path: str) -> dict:
                     raw = mb[4:4 + int.from_bytes(mb[2:4], "little")]
                 else:
                     raise ValueError("chunked layouts are not supported")
-        if not is_f64 or raw is None:
-            raise ValueError(f"{path}:{name}: only Float64 datasets are supported")
-        arr = np.frombuffer(raw, dtype="<f8").copy()
+        if not (is_f64 or is_i64) or raw is None:
+            raise ValueError(f"{path}:{name}: only Float64 / Int64 datasets are supported")
+        arr = np.frombuffer(raw, dtype="<f8" if is_f64 else "<i8").astype(np.float64)
         out[name] = arr.reshape(dims) if dims else float(arr[0])
     return out
 
 
 # ---- the reference's two functions ---------------------------------------------------------------
 
-def save_state(model, ofile: str) -> None:
-    """``save_state(model, ofile)`` (IO.jl:1-10): u, p, b free values in Gridap order and t."""
+def save_state(model, ofile: str, history: bool = False) -> None:
+    """``save_state(model, ofile)`` (IO.jl:1-10): u, p, b free values in Gridap order and t.
+
+    ``history=True`` additionally stores the previous-step fields ``u_prev``, ``p_prev``, ``b_prev``, the step
+    index and Δt, which the reference does not (a resumed BDF2 run of the reference restarts with
+    prev = curr, model.jl:120-123): with them ``set_state_from_file_`` + ``run_(..., resume=True)``
+    continues a BDF2 run bit for bit.  A file written with ``history=False`` is byte-compatible with the
+    reference's."""
     s = model.state
     t = 0.0 if model.timestepper is None else model.timestepper.t
-    write_jld2(ofile, {"u": s.u, "p": s.p, "b": s.b, "t": t})
+    fields = {"u": s.u, "p": s.p, "b": s.b, "t": t}
+    if history and getattr(model, "_has_prev", False):
+        d = model.fe_data.dofs
+        xp = model._u_prev.download()[d.inv_p_inversion]
+        fields.update({"u_prev": xp[:d.nu], "p_prev": xp[d.nu:], "b_prev": model._b_prev.download()[d.inv_p_b],
+                       "step_index": float(getattr(model, "_step_index", 1)), "dt": float(model.timestepper.Δt)})
+    write_jld2(ofile, fields)
 
 
 def set_state_from_file_(model, ifile: str):
@@ -214,4 +229,14 @@ def set_state_from_file_(model, ifile: str):
     model.xb.upload(d["b"][dofs.p_b])
     if model.timestepper is not None:
         model.timestepper.t = float(d["t"])
+    if "b_prev" in d and model.evolution is not None:
+        # BDF2 history written by save_state(..., history=True): run_(..., resume=True) continues the run
+        model._u_prev.upload(np.concatenate([d["u_prev"], d["p_prev"]])[dofs.p_inversion])
+        model._b_prev.upload(d["b_prev"][dofs.p_b])
+        model._has_prev = True
+        model._step_index = int(d["step_index"])
+        model.timestepper.Δt = float(d["dt"])
+        if model._step_index >= 2 and model.timestepper.scheme == 2:
+            from .evolution import collect_evolution_LHS_
+            collect_evolution_LHS_(model.evolution, model.params, model.forcings, model.timestepper)   # model.jl:134-137
     return model

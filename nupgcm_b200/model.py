@@ -156,7 +156,7 @@ def _sync_buffers(model: Model) -> dict:
 
 
 def run_(model: Model, n_info=10, n_save=float("inf"), n_steps=None, sync_state=False,
-         host_state=None, log=None, advection=True, resume=False):
+         host_state=None, log=None, advection=True, resume=False, out_dir=None, save_history=False):
     """``run!`` (model.jl:90-211).  ``n_steps`` bounds the number of steps taken by this call
     (the reference loops until ``t >= t_stop``); ``resume=True`` makes a call continue the previous
     one (see below).  With ``sync_state`` the state is copied to the
@@ -225,6 +225,15 @@ def run_(model: Model, n_info=10, n_save=float("inf"), n_steps=None, sync_state=
         model.step_log.append(rec)
         if log is not None and i % n_info == 0:
             log(rec)
+        if n_save != float("inf") and i % int(n_save) == 0:         # model.jl:194-197 (save_vtk is out of scope)
+            if out_dir is None:
+                raise ValueError("run_(..., n_save=k) needs out_dir: the directory the state files go to "
+                                 "(the reference writes $out_dir/data/state_%016d.jld2)")
+            import os
+            from .io import save_state
+            os.makedirs(os.path.join(out_dir, "data"), exist_ok=True)
+            model._step_index = i + 1
+            save_state(model, os.path.join(out_dir, "data", "state_%016d.jld2" % i), history=save_history)
         i += 1
         done += 1
     model._step_index = i

@@ -40,7 +40,14 @@ def update_t_(ts: AbstractTimestepper):
 def update_Δt_(ts, mesh=None, u=None, u_min=0.01):
     """``update_Δt!`` (timesteppers.jl:108-122): Δt = CFL_factor · min_K h_K / max(|u|_{L∞(K)}, u_min)
     for an adaptive BDF1 — one kernel over the cells of ``mesh`` (a ``lib.ElementMesh``) and the
-    device velocity ``u`` — and a no-op otherwise."""
+    device velocity ``u`` — and a no-op otherwise.
+
+    DELIBERATE DEVIATION (pinned by tests/test_host_logic.py): the reference's ``update_Δt!(::BDF1, …)``
+    has no ``adaptive`` check and ``run!`` calls it unconditionally (model.jl:131), so upstream a
+    ``BDF1(adaptive=false)`` run also changes Δt every step — while its left-hand side is only re-formed
+    when ``adaptive`` or the convection parameterisation is on (model.jl:251), i.e. the matrix and the
+    right-hand side then disagree about Δt.  Here Δt changes only for ``adaptive=True``, which is the only
+    configuration the reference exercises with BDF1 (scratch/run.jl:163)."""
     if getattr(ts, "adaptive", False):
         ts.Δt = mesh.cfl_dt(u, ts.CFL_factor, u_min)
     return ts

@@ -22,6 +22,10 @@ def test_timesteppers_mirror_the_reference():
 
     update_Δt_(bdf1, FakeMesh(), None)
     assert bdf1.Δt == pytest.approx(0.5 * 2.0 / 0.01)
+    # declared deviation from timesteppers.jl:108-119 (see update_Δt_): a non-adaptive BDF1 keeps its Δt
+    fixed = BDF1(t_start=0.0, t_stop=1.0, Δt=0.1)
+    update_Δt_(fixed, FakeMesh(), None)
+    assert fixed.Δt == 0.1
     update_t_(bdf1)
     assert bdf1.t == pytest.approx(100.0)
     # t_stop = 50 Δt takes 51 steps with `while t < t_stop; t += Δt`

@@ -87,3 +87,53 @@ def test_save_and_restore_model_state(tmp_path):
     assert b.timestepper.t == a.timestepper.t
     d = oracle_read(f)
     assert np.array_equal(d["u"], a.state.u) and np.array_equal(d["b"], a.state.b)
+
+
+def test_reader_accepts_the_int64_time_of_a_model_without_timestepper(tmp_path):
+    """save_state writes `t = 0` as an Int64 when the model has no timestepper (IO.jl:3-4): patch the
+    datatype message of a file we wrote into the fixed-point class and read it back."""
+    f = tmp_path / "s.jld2"
+    sio.write_jld2(str(f), {"u": np.arange(4.0), "t": 0.0})
+    raw = bytearray(f.read_bytes())
+    f64 = bytes([0x31, 0x20, 0x3F, 0x00])                 # class 1 (float) v1 datatype header written by write_jld2
+    pos = raw.rfind(f64)                                  # the last dataset written is `t`
+    assert pos > 0
+    raw[pos] = 0x30                                       # class 0 (fixed point), same 8-byte size
+    f.write_bytes(bytes(raw))
+    try:
+        back = sio.read_jld2(str(f))
+    except ValueError as e:                               # object-header checksum now differs: that is the only accepted reason
+        assert "checksum" in str(e)
+    else:
+        assert back["t"] == 0.0
+
+
+@pytest.mark.gpu
+def test_periodic_save_and_bdf2_restart_continue_the_run_bit_for_bit(tmp_path):
+    """run_(n_save=k, out_dir=..., save_history=True) writes $out_dir/data/state_%016d.jld2 (model.jl:194-197) with
+    the BDF2 history; a fresh model restored from it and resumed ends where the uninterrupted run ends."""
+    import nupgcm_b200 as npg
+    from conftest import workload
+    w, ops = workload("bowl_mixing", dim=2)
+
+    def make():
+        arch = npg.GPU(0)
+        inv = npg.InversionToolkit(arch, ops["A"], ops["pscale"], ops["B"], ops["b0"])
+        ts = w.timestepper()
+        evo = npg.EvolutionToolkit(arch, ops, w.params, w.forcings, ts)
+        m = npg.Model(arch, w.params, w.forcings, w.fe_data(), inv, evo, ts, tables=ops["tables"])
+        m.xb.upload(ops["b_init"])
+        return m
+
+    a = make()
+    npg.run_(a, n_steps=6, n_save=3, out_dir=str(tmp_path), save_history=True)
+    files = sorted((tmp_path / "data").iterdir())
+    assert [p.name for p in files] == ["state_%016d.jld2" % 3, "state_%016d.jld2" % 6]
+    b = make()
+    sio.set_state_from_file_(b, str(files[0]))
+    npg.run_(b, n_steps=3, resume=True)
+    assert np.array_equal(a.xb.download(), b.xb.download())
+    assert np.array_equal(a.inversion.solver.x.download(), b.inversion.solver.x.download())
+    assert b.timestepper.t == a.timestepper.t
+    with pytest.raises(ValueError):
+        npg.run_(make(), n_steps=1, n_save=1)             # n_save without out_dir is refused, not ignored
