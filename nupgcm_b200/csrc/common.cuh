@@ -200,7 +200,8 @@ struct NupgcmTileDesc { int32_t row0, nrows, foot_off, foot_len, xs_off, dep, pa
                                        // dep: tile of the same CTA that must be finished before this one is staged (-1: none)
 struct NupgcmWarpDesc { int32_t estart, elen, stab, rtab; };    // stream start (multiple of 8) / length, slice and row table offsets
 struct NupgcmSlice { int32_t eoff, roff, nrows, lmax; };        // entry offset in the warp's stream, rows (relative to rtab), longest row;
-                                       // nrows == 0: ONE row of lmax entries stored contiguously, processed by the whole warp
+                                       // nrows == 0: ONE row of lmax entries stored contiguously, processed by the whole warp;
+                                       // nrows = 32 | nblk << 8: the first nblk blocks of 8 positions are stored "blocked" (csr.cu)
 static const int kLongRow = 96;        // rows longer than this are such whole-warp items (they would give a slice a long jagged end)
 
 static const int kPartialSlots = 24;   // >= memory+2 of GMRES

@@ -1032,10 +1032,13 @@ struct SpmvEngine<T, false> {
             }
         };
         // the first slice's tables are fetched before anything is waited for; then always one slice ahead
+        int cur = 0;                                             // stream entries consumed so far (slices may be preceded by alignment padding)
         int si = 0;                                              // next slice of this warp's list
-        NupgcmSlice sl = slices[0];
+        // (two-stage: the header of item i+2 is requested while item i is processed, so that the row table of
+        // item i+1 — whose address needs that item's header — can be requested without waiting for a header)
+        NupgcmSlice sl = slices[0], sl2 = slices[1];
         int mylen = 0, myrow = -1;
-        if (lane < max(sl.nrows, 1)) { mylen = __ldg(slen + sl.roff + lane); myrow = __ldg(srow + sl.roff + lane); }
+        if (lane < max(sl.nrows & 0xff, 1)) { mylen = __ldg(slen + sl.roff + lane); myrow = __ldg(srow + sl.roff + lane); }
         NupgcmTileDesc td = a.tiles[t0];
         int mine_next = __ldg(a.twcnt + (size_t)t0 * kMainWarps + wid);       // my items in the first tile
         // results of whole-warp (long) rows are parked one per lane and handed to f together: f's global
@@ -1061,12 +1064,15 @@ struct SpmvEngine<T, false> {
                 const NupgcmSlice cs = sl;
                 const int clen = mylen, crow = myrow;
                 ++si;
-                sl = slices[si];                                 // (the table ends with a null slice)
+                sl = sl2;                                        // header of the next item: requested one item ago
+                sl2 = slices[si + 1];                            // (the table ends with two null slices)
                 mylen = 0;
                 myrow = -1;
-                if (lane < max(sl.nrows, 1)) { mylen = __ldg(slen + sl.roff + lane); myrow = __ldg(srow + sl.roff + lane); }
-                const int nr = cs.nrows;
+                if (lane < max(sl.nrows & 0xff, 1)) { mylen = __ldg(slen + sl.roff + lane); myrow = __ldg(srow + sl.roff + lane); }
+                const int nr = cs.nrows & 0xff, nblk = cs.nrows >> 8;
                 int off = cs.eoff;
+                rpos += off - cur;                               // skip the alignment padding in front of a blocked slice
+                if (rpos >= kRingEntries) rpos -= kRingEntries;
                 double acc0 = 0.0, acc1 = 0.0;
                 if (nr == 0) {
                     // a long row: the whole warp strides over its (contiguous) entries, 8 x 32 at a time
@@ -1095,13 +1101,38 @@ struct SpmvEngine<T, false> {
                     acc0 = warp_sum(acc0 + acc1);
                     if (lane == nparked) { prow = row; pval = acc0; }
                     if (++nparked == 32) flush_parked();
+                    cur = off;
                     tick(5);
                     continue;
                 }
                 const bool act = lane < nr;
                 const int lmin = __shfl_sync(0xffffffffu, clen, nr - 1);
                 tick(2);
-                int j = 0;
+                int j = 8 * nblk;
+                // blocked part of a full slice: the lane's 8 offsets in one 16-byte load, its values in pairs
+                for (int bq = 0; bq < nblk; ++bq) {
+                    ensure(off + 256);
+                    if (DBG != 1) {
+                        int ic = rpos + lane * 8;
+                        if (ic >= kRingEntries) ic -= kRingEntries;
+                        const uint4 cv = *reinterpret_cast<const uint4 *>(rc + ic);
+                        const unsigned cw[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+                        for (int pp = 0; pp < 4; ++pp) {
+                            int iv = rpos + pp * 64 + lane * 2;
+                            if (iv >= kRingEntries) iv -= kRingEntries;
+                            const double2 vv = *reinterpret_cast<const double2 *>(rv + iv);
+                            const double x0 = *reinterpret_cast<const double *>(xt + (DBG == 2 ? 8u * lane : (cw[pp] & 0xffffu)));
+                            const double x1 = *reinterpret_cast<const double *>(xt + (DBG == 2 ? 8u * lane : (cw[pp] >> 16)));
+                            acc0 = fma(vv.x, x0, acc0);
+                            acc1 = fma(vv.y, x1, acc1);
+                        }
+                    }
+                    off += 256;
+                    rpos += 256;
+                    if (rpos >= kRingEntries) rpos -= kRingEntries;
+                    release(off);
+                }
                 // positions every row of the slice has: nr entries each, lane q reads entry q
                 for (; j + 8 <= lmin; j += 8) {
                     ensure(off + 8 * nr);
@@ -1155,6 +1186,7 @@ struct SpmvEngine<T, false> {
                     release(off);
                 }
                 release(off);
+                cur = off;
                 tick(4);
                 if (act) f(crow, acc0 + acc1);
                 tick(5);

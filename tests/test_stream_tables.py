@@ -17,7 +17,8 @@ def _check(A, grid, arena=6656, seed=0):
     ref = A @ x
     scale = np.abs(A) @ np.abs(x) + 1e-300
     assert np.max(np.abs(y - ref) / scale) < 1e-14
-    assert info["entries"] >= A.nnz and info["entries"] < A.nnz + 8 * 11 * grid + 600   # alignment + one tail piece
+    # padding: stream alignment (<= 7 per warp and CTA), <= 7 in front of every blocked slice, one tail piece
+    assert info["entries"] >= A.nnz and info["entries"] < 1.005 * A.nnz + 8 * 11 * grid + 600
     return info
 
 
