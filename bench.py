@@ -33,6 +33,7 @@ One JSON line (rank 0):
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -267,13 +268,15 @@ def true_residual(ctx, inv):
     return r.norm2() / max(s.y.norm2(), 1e-300)
 
 
-def step_model(npg, ctx, m, steps, flush):
+def step_model(npg, ctx, m, steps, flush, tag=""):
     ms = []
+    gc.collect()                                 # finalisers of earlier models (cudaFree) stay out of the timed steps
     for _ in range(steps):
         flush.fill(0.0)
         ctx.timer_start()
         npg.run_(m, n_steps=1, resume=True)      # one continuous run, timed step by step
         ms.append(ctx.timer_stop())
+    print(f"[bench] {tag} ms per step: " + " ".join(f"{v:.2f}" for v in ms), file=sys.stderr, flush=True)
     return ms
 
 
@@ -355,10 +358,10 @@ def main():
         t_wall0 = time.perf_counter()
         if clocks is not None:
             with clocks:
-                ms = step_model(npg, ctx, m, args.steps, flush)
+                ms = step_model(npg, ctx, m, args.steps, flush, f"h=0.04 {orth}")
                 barrier()
         else:
-            ms = step_model(npg, ctx, m, args.steps, flush)
+            ms = step_model(npg, ctx, m, args.steps, flush, f"h=0.04 {orth}")
             barrier()
         t_wall = time.perf_counter() - t_wall0
         launches = ctx.launch_count() - launches0 - args.steps      # minus the L2-flush fills
@@ -465,7 +468,7 @@ def main():
             m2 = make_model(w2, ops2, orth)
             npg.run_(m2, n_steps=args.warmup)
             barrier()
-            ms = step_model(npg, ctx, m2, args.steps, flush)
+            ms = step_model(npg, ctx, m2, args.steps, flush, f"h=0.08 {orth}")
             barrier()
             tot = float(np.sum(ms))
             if dist is not None:
@@ -477,7 +480,10 @@ def main():
             gi = float(np.sum([r["gmres_iters"] for r in lg]))
             sec[orth] = {"value": args.steps / (tot * 1e-3), "unit": UNIT,
                          "gmres_per_step_mean": gi / args.steps,
-                         "gmres_us_per_iter": float(1e3 * np.sum([r["gmres_ms"] for r in lg]) / max(gi, 1))}
+                         "gmres_us_per_iter": float(1e3 * np.sum([r["gmres_ms"] for r in lg]) / max(gi, 1)),
+                         "ms_per_step": tot / args.steps,
+                         "gmres_ms_per_step": float(np.mean([r["gmres_ms"] for r in lg])),
+                         "cg_ms_per_step": float(np.mean([r["cg_ms"] for r in lg]))}
             del m2
         if not args.no_tight:
             # north_star's parity tolerance: relative residual <= 1e-10 (the reference's GPU default is 1e-6); on this
@@ -485,7 +491,7 @@ def main():
             mt = make_model(w2, ops2, "mgs", atol=0.0, rtol=1e-10)
             npg.run_(mt, n_steps=1)
             barrier()
-            ms = step_model(npg, ctx, mt, args.tight_steps, flush)
+            ms = step_model(npg, ctx, mt, args.tight_steps, flush, "h=0.08 tight mgs")
             barrier()
             tot = float(np.sum(ms))
             if dist is not None:

@@ -302,6 +302,15 @@ int32_t nupgcm_mesh_create(nupgcm_ctx *ctx, int64_t n_cells, int32_t n_loc,
                            const double *vol, int32_t nq, const double *bary, const double *w,
                            int64_t nb, const double *b_dirichlet, int64_t nbd, int64_t nu,
                            const double *u_dirichlet, int64_t nud, nupgcm_mesh **out);
+/* Same with first-order buoyancy (reference src/spaces.jl:31-39 `Spaces(...; b_order=1)`, the production
+ * set-up of scratch/run.jl:152): the velocity stays P2 (n_loc = 10 / 6 nodes in cell_u) while cell_b holds
+ * n_loc_b buoyancy DOFs per cell — n_loc (P2) or the vertex count 4 / 3 (P1: cell_b[c*n_loc_b + i]).
+ * All kernels of this handle (rhs_adv, rebuild_kv, rebuild_friction) follow the buoyancy order. */
+int32_t nupgcm_mesh_create_orders(nupgcm_ctx *ctx, int64_t n_cells, int32_t n_loc, int32_t n_loc_b,
+                                  const int32_t *cell_b, const int32_t *cell_u, const double *grad,
+                                  const double *vol, int32_t nq, const double *bary, const double *w,
+                                  int64_t nb, const double *b_dirichlet, int64_t nbd, int64_t nu,
+                                  const double *u_dirichlet, int64_t nud, nupgcm_mesh **out);
 int32_t nupgcm_mesh_destroy(nupgcm_mesh *m);
 /* scheme 1: ∫(b − Δt(u·∇b + w N²)) d   (src/model.jl:292-295)
  * scheme 2: ∫(4/3 b − 1/3 b⁻ − 2/3 Δt((2u−u⁻)·∇(2b−b⁻) + (2w−w⁻) N²)) d   (:297-300)

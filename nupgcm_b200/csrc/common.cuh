@@ -142,14 +142,15 @@ int32_t nupgcm_reserve_solver_workspace(nupgcm_ctx *ctx, int64_t max_n);
 struct nupgcm_mesh {
     nupgcm_ctx *ctx;
     int64_t n_cells;
-    int n_loc, n_vert, nq;
+    int n_loc, n_vert, nq;         // n_loc: local velocity nodes (P2)
+    int n_loc_b;                   // local buoyancy DOFs: n_loc (P2) or n_vert (P1)
     int64_t nb, nbd, nu, nud;
-    int32_t *d_cell_b;             // [n_loc][n_cells]   (transposed: coalesced over cells)
+    int32_t *d_cell_b;             // [n_loc_b][n_cells] (transposed: coalesced over cells)
     int32_t *d_cell_u;             // [n_loc*3][n_cells]
     double *d_grad;                // [n_vert*3][n_cells]
     double *d_vol;                 // [n_cells]
     double *d_bdir, *d_udir;       // Dirichlet values
-    double *d_elem;                // [n_loc][n_cells] elemental vectors
+    double *d_elem;                // [n_loc_b][n_cells] elemental vectors
     int32_t *d_gptr;               // [nb+1] gather lists: per free DOF, the elemental slots
     int32_t *d_gidx;               //        sorted by cell id (deterministic summation order)
     double *d_phi;                 // [nq][n_loc] basis values
@@ -160,7 +161,7 @@ struct nupgcm_mesh {
     // Kᵥ rebuild (convection parameterisation): per stored matrix entry, its element-matrix slots
     int32_t *d_kptr, *d_kidx;
     double *d_kvq;                 // [n_cells][nq] base κᵥ at the quadrature points
-    double *d_emat, *d_evec;       // [n_loc*n_loc][n_cells], 2 x [n_loc][n_cells]
+    double *d_emat, *d_evec;       // [n_loc_b*n_loc_b][n_cells], 2 x [n_loc_b][n_cells]
     int64_t kv_nnz;
     // friction-block rebuild (eddy parameterisation)
     int32_t *d_nptr, *d_nidx;

@@ -1638,6 +1638,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
     int npass = 0;
 
     const bool fused = a.orth == NUPGCM_ORTH_CGS2_FUSED;
+    constexpr int QCAP = RES ? 0 : kArenaEntries;      // rows of the new vector the idle footprint arena can hold
     // Givens / least-squares update of one Arnoldi column (Krylov.jl order), by ONE thread
     auto scalar_step = [&](int k, int nr, double hsq) {
         const double Hbis = sqrt(hsq);
@@ -1771,15 +1772,32 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
                     }
                     normalised = true;
                 } else {
+                // Streaming form (more rows per thread than registers hold).  In the streamed-matrix kernels the
+                // footprint arena is idle between two SpMVs: the CTA's first `qcap` rows of the new vector live
+                // there through the k+1 steps (read and written once per step where the global form does two
+                // accesses each), and v_{k+1} = q / H is written to the basis straight from it.
+                double *qs = QCAP ? reinterpret_cast<double *>(dyn_smem + a.lay.st_xs) : nullptr;
+                const int qcap = QCAP && a.lay.streaming ? QCAP : 0;
                 double hprev = 0.0;
                 for (int i = 0; i < k; ++i) {
                     const double *vi = V.at(i);
                     const double *vp = V.at(i > 0 ? i - 1 : 0);
                     double part = 0.0;
+#pragma unroll 8
                     for (int row = r0 + tid; row < r1; row += nthr) {
-                        double qv = q[row];
-                        if (i > 0) { qv = fma(-hprev, vp[row], qv); q[row] = qv; }
+                        const bool in_s = row - r0 < qcap;
+                        double qv = (i > 0 && in_s) ? qs[row - r0] : q[row];
+                        if (i > 0) qv = fma(-hprev, vp[row], qv);
+                        if (in_s) qs[row - r0] = qv;
+                        else if (i > 0) q[row] = qv;
                         part = fma(vi[row], qv, part);
+                    }
+                    // the next step reads v_{i+1} (and v_i again): have the former on its way into L2 while the
+                    // reduction is in flight — the basis does not fit in L2 at the sizes that take this form
+                    if (i + 1 < k && (lane & 15) == 0) {
+                        const double *vn = V.at(i + 1);
+                        for (int row = r0 + tid; row < r1; row += nthr)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(vn + row));
                     }
                     pc.mark(1);
                     hprev = gr.sum_threads<false>(part);
@@ -1790,8 +1808,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
                 double part = 0.0;
                 halo_arm(hp, a, gr.gen);
                 for (int row = r0 + tid; row < r1; row += nthr) {
-                    const double qv = fma(-hprev, vp[row], q[row]);
-                    q[row] = qv;
+                    const bool in_s = row - r0 < qcap;
+                    const double qv = fma(-hprev, vp[row], in_s ? qs[row - r0] : q[row]);
+                    if (in_s) qs[row - r0] = qv;
+                    else q[row] = qv;
                     dst[row] = qv;
                     halo_put(hp, dst + row, row, qv);
                     part = fma(qv, qv, part);
@@ -1799,6 +1819,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
                 pc.mark(1);
                 hsq = gr.sum_threads<true>(part);     // publishes dst for the next gather
                 pc.mark(2);
+                if (qcap > 0) {
+                    const double ih = 1.0 / sqrt(hsq);
+                    for (int row = r0 + tid; row < r1; row += nthr) q[row] = (row - r0 < qcap ? qs[row - r0] : q[row]) * ih;
+                    normalised = true;
+                }
                 }
             } else if (a.orth == NUPGCM_ORTH_CGS2_FUSED) {
                 // CGS2 with two grid reductions per iteration instead of three:

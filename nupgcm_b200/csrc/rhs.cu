@@ -23,7 +23,9 @@ struct P2 {
 __device__ __constant__ int c_edge_a[6] = {0, 0, 1, 0, 1, 2};
 __device__ __constant__ int c_edge_b[6] = {1, 2, 2, 3, 3, 3};
 
-template <int NV>
+// NLB: local buoyancy DOFs per cell — P2<NV>::NLOC (reference default b_order = 2) or NV (b_order = 1,
+// the production set-up of scratch/run.jl:152: φ_i = λ_i, ∇φ_i = ∇λ_i).  The velocity is always P2.
+template <int NV, int NLB>
 __global__ void __launch_bounds__(128)
 k_elem(const int32_t *__restrict__ cell_b, const int32_t *__restrict__ cell_u,
        const double *__restrict__ grad, const double *__restrict__ vol,
@@ -34,6 +36,8 @@ k_elem(const int32_t *__restrict__ cell_b, const int32_t *__restrict__ cell_u,
        double *__restrict__ elem) {
     constexpr int NLOC = P2<NV>::NLOC;
     constexpr int NE = P2<NV>::NE;
+    constexpr bool BP1 = NLB == NV;
+    static_assert(BP1 || NLB == NLOC, "buoyancy is P1 or P2");
     extern __shared__ double s_q[];               // bary[nq][NV], w[nq]
     for (int i = threadIdx.x; i < nq * NV; i += blockDim.x) s_q[i] = bary[i];
     for (int i = threadIdx.x; i < nq; i += blockDim.x) s_q[nq * NV + i] = w[i];
@@ -42,9 +46,9 @@ k_elem(const int32_t *__restrict__ cell_b, const int32_t *__restrict__ cell_u,
     if (c >= n_cells) return;
 
     // gather the cell's fields: b* (advected), lin (time-derivative part), u* (advecting)
-    double bs[NLOC], lin[NLOC], us[NLOC][3];
+    double bs[NLB], lin[NLB], us[NLOC][3];
 #pragma unroll
-    for (int i = 0; i < NLOC; ++i) {
+    for (int i = 0; i < NLB; ++i) {
         const int32_t ib = cell_b[i * n_cells + c];
         const double b0 = ib < nb ? b[ib] : bdir[ib - nb];
         const double b1 = ib < nb ? bp[ib] : bdir[ib - nb];
@@ -55,6 +59,9 @@ k_elem(const int32_t *__restrict__ cell_b, const int32_t *__restrict__ cell_u,
             bs[i] = b0;
             lin[i] = b0;
         }
+    }
+#pragma unroll
+    for (int i = 0; i < NLOC; ++i) {
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
             const int32_t iu = cell_u[(i * 3 + d) * n_cells + c];
@@ -71,9 +78,9 @@ k_elem(const int32_t *__restrict__ cell_b, const int32_t *__restrict__ cell_u,
     const double fac = scheme == 2 ? (2.0 / 3.0) * dt : dt;
     const double vc = vol[c];
 
-    double out[NLOC];
+    double out[NLB];
 #pragma unroll
-    for (int i = 0; i < NLOC; ++i) out[i] = 0.0;
+    for (int i = 0; i < NLB; ++i) out[i] = 0.0;
 
     for (int q = 0; q < nq; ++q) {
         double lam[NV];
@@ -85,7 +92,7 @@ k_elem(const int32_t *__restrict__ cell_b, const int32_t *__restrict__ cell_u,
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             phi[i] = lam[i] * (2.0 * lam[i] - 1.0);
-            const double dl = 4.0 * lam[i] - 1.0;
+            const double dl = BP1 ? 1.0 : 4.0 * lam[i] - 1.0;
 #pragma unroll
             for (int d = 0; d < 3; ++d) gb[d] = fma(bs[i] * dl, gl[i][d], gb[d]);
         }
@@ -93,23 +100,26 @@ k_elem(const int32_t *__restrict__ cell_b, const int32_t *__restrict__ cell_u,
         for (int e = 0; e < NE; ++e) {
             const int ia = c_edge_a[e], ib = c_edge_b[e];
             phi[NV + e] = 4.0 * lam[ia] * lam[ib];
+            if constexpr (!BP1) {
 #pragma unroll
-            for (int d = 0; d < 3; ++d)
-                gb[d] = fma(4.0 * bs[NV + e], fma(lam[ia], gl[ib][d], lam[ib] * gl[ia][d]), gb[d]);
+                for (int d = 0; d < 3; ++d)
+                    gb[d] = fma(4.0 * bs[NV + e], fma(lam[ia], gl[ib][d], lam[ib] * gl[ia][d]), gb[d]);
+            }
         }
 #pragma unroll
         for (int i = 0; i < NLOC; ++i) {
-            lq = fma(phi[i], lin[i], lq);
 #pragma unroll
             for (int d = 0; d < 3; ++d) uq[d] = fma(phi[i], us[i][d], uq[d]);
         }
+#pragma unroll
+        for (int i = 0; i < NLB; ++i) lq = fma(BP1 ? lam[i] : phi[i], lin[i], lq);
         const double adv = uq[0] * gb[0] + uq[1] * gb[1] + uq[2] * gb[2] + uq[2] * N2;
         const double val = (lq - fac * adv) * (s_q[nq * NV + q] * vc);
 #pragma unroll
-        for (int i = 0; i < NLOC; ++i) out[i] = fma(val, phi[i], out[i]);
+        for (int i = 0; i < NLB; ++i) out[i] = fma(val, BP1 ? lam[i] : phi[i], out[i]);
     }
 #pragma unroll
-    for (int i = 0; i < NLOC; ++i) elem[i * n_cells + c] = out[i];
+    for (int i = 0; i < NLB; ++i) elem[i * n_cells + c] = out[i];
 }
 
 // Adaptive timestep (reference src/timesteppers.jl:108-119): Δt = c · min_K h_K / max(|u|_{L∞(K)}, u_min),
@@ -177,14 +187,15 @@ k_cfl(const int32_t *__restrict__ cell_u, const double *__restrict__ bary, int n
 // uploads the results; here one thread per cell writes the cell's 10x10 element matrix and two
 // element vectors to [slot][cell] arrays, and gather kernels add each matrix entry's / DOF's
 // slots in a fixed order (sorted by cell): no atomics, bitwise reproducible.
-template <int NV>
+template <int NV, int NLOC>   // NLOC: local buoyancy DOFs (P2: NV + edges, P1: NV)
 __global__ void __launch_bounds__(128)
 k_kv_elem(const int32_t *__restrict__ cell_b, const double *__restrict__ grad, const double *__restrict__ vol,
           const double *__restrict__ bary, const double *__restrict__ w, int nq, int64_t n_cells,
           const double *__restrict__ b, const double *__restrict__ bdir, int64_t nb,
           const double *__restrict__ kv_q, double alpha, double N2, double kappa_c, double N2min,
           double *__restrict__ emat, double *__restrict__ evec_v, double *__restrict__ evec_d) {
-    constexpr int NLOC = P2<NV>::NLOC;
+    constexpr bool BP1 = NLOC == NV;
+    static_assert(BP1 || NLOC == P2<NV>::NLOC, "buoyancy is P1 or P2");
     constexpr int MAXQ = 16;
     extern __shared__ double s_q[];               // bary[nq][NV], w[nq]
     for (int i = threadIdx.x; i < nq * NV; i += blockDim.x) s_q[i] = bary[i];
@@ -204,6 +215,7 @@ k_kv_elem(const int32_t *__restrict__ cell_b, const double *__restrict__ grad, c
     const double vc = vol[c];
     // ∂z φ_i at quadrature point q
     auto dz = [&](int q, int i) -> double {
+        if (BP1) return gz[i];
         const double *lam = s_q + q * NV;
         if (i < NV) return (4.0 * lam[i] - 1.0) * gz[i];
         const int ia = c_edge_a[i - NV], ib = c_edge_b[i - NV];
@@ -248,7 +260,7 @@ k_kv_elem(const int32_t *__restrict__ cell_b, const double *__restrict__ grad, c
 // it.  Here the constant part (pressure gradient, divergence, Coriolis) stays on the device and one
 // thread per cell writes the 3x3 blocks of the cell's 10x10 (6x6) node pairs:
 //   block(i,j)[a][b] = α²ε² Σ_q w_q |K| ν_q (δ_ab ∇φ_i·∇φ_j + ∂_a φ_j ∂_b φ_i).
-template <int NV>
+template <int NV, int NLB>   // NLB: local buoyancy DOFs (only ∂z b enters); the velocity blocks are P2
 __global__ void __launch_bounds__(64)
 k_nu_elem(const int32_t *__restrict__ cell_b, const double *__restrict__ grad, const double *__restrict__ vol,
           const double *__restrict__ bary, const double *__restrict__ w, int nq, int64_t n_cells,
@@ -256,6 +268,8 @@ k_nu_elem(const int32_t *__restrict__ cell_b, const double *__restrict__ grad, c
           const double *__restrict__ f_q, double a2e2, double alpha, double N2, double N2min, double smoothing,
           double nu_min, double *__restrict__ emat) {
     constexpr int NLOC = P2<NV>::NLOC;
+    constexpr bool BP1 = NLB == NV;
+    static_assert(BP1 || NLB == NLOC, "buoyancy is P1 or P2");
     constexpr int MAXQ = 16;
     extern __shared__ double s_q[];               // bary[nq][NV], w[nq]
     for (int i = threadIdx.x; i < nq * NV; i += blockDim.x) s_q[i] = bary[i];
@@ -282,9 +296,9 @@ k_nu_elem(const int32_t *__restrict__ cell_b, const double *__restrict__ grad, c
     };
     double cq[MAXQ];                                  // α²ε² w_q |K| ν(x_q)
     {
-        double bv[NLOC];
+        double bv[NLB];
 #pragma unroll
-        for (int i = 0; i < NLOC; ++i) {
+        for (int i = 0; i < NLB; ++i) {
             const int32_t ib = cell_b[i * n_cells + c];
             bv[i] = ib < nb ? b[ib] : bdir[ib - nb];
         }
@@ -292,10 +306,14 @@ k_nu_elem(const int32_t *__restrict__ cell_b, const double *__restrict__ grad, c
         for (int q = 0; q < nq; ++q) {
             double dzb = 0.0;
 #pragma unroll
-            for (int i = 0; i < NLOC; ++i) {
-                double g[3];
-                gphi(q, i, g);
-                dzb = fma(bv[i], g[2], dzb);
+            for (int i = 0; i < NLB; ++i) {
+                if constexpr (BP1) {
+                    dzb = fma(bv[i], gl[i][2], dzb);
+                } else {
+                    double g[3];
+                    gphi(q, i, g);
+                    dzb = fma(bv[i], g[2], dzb);
+                }
             }
             const double abz = alpha * (N2 + dzb);
             const double f = f_q[c * (int64_t)nq + q];
@@ -380,31 +398,54 @@ static cudaError_t upload(Tp **dst, const std::vector<Tp> &src) {
     return e;
 }
 
+// Launch `KERNEL<NV, NLB>` for the mesh's cell type and buoyancy order.
+#define NUPGCM_MESH_DISPATCH(m, KERNEL, GRID, BLOCK, SMEM, STREAM, ...)                                    \
+    do {                                                                                                   \
+        if ((m)->n_vert == 4 && (m)->n_loc_b == 10) KERNEL<4, 10><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__); \
+        else if ((m)->n_vert == 4) KERNEL<4, 4><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__);                \
+        else if ((m)->n_loc_b == 6) KERNEL<3, 6><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__);               \
+        else KERNEL<3, 3><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__);                                      \
+    } while (0)
+
 extern "C" int32_t nupgcm_mesh_create(nupgcm_ctx *ctx, int64_t n_cells, int32_t n_loc,
                                       const int32_t *cell_b, const int32_t *cell_u,
                                       const double *grad, const double *vol, int32_t nq,
                                       const double *bary, const double *w, int64_t nb,
                                       const double *b_dirichlet, int64_t nbd, int64_t nu,
                                       const double *u_dirichlet, int64_t nud, nupgcm_mesh **out) {
+    return nupgcm_mesh_create_orders(ctx, n_cells, n_loc, n_loc, cell_b, cell_u, grad, vol, nq, bary, w, nb,
+                                     b_dirichlet, nbd, nu, u_dirichlet, nud, out);
+}
+
+extern "C" int32_t nupgcm_mesh_create_orders(nupgcm_ctx *ctx, int64_t n_cells, int32_t n_loc, int32_t n_loc_b,
+                                             const int32_t *cell_b, const int32_t *cell_u,
+                                             const double *grad, const double *vol, int32_t nq,
+                                             const double *bary, const double *w, int64_t nb,
+                                             const double *b_dirichlet, int64_t nbd, int64_t nu,
+                                             const double *u_dirichlet, int64_t nud, nupgcm_mesh **out) {
     NUPGCM_REQUIRE(nullptr, ctx, "ctx is NULL");
     NUPGCM_REQUIRE(ctx, out && cell_b && cell_u && grad && vol && bary && w, "mesh_create: NULL argument");
     NUPGCM_REQUIRE(ctx, n_loc == 10 || n_loc == 6, "mesh_create: n_loc must be 10 (tets) or 6 (triangles)");
+    NUPGCM_REQUIRE(ctx, n_loc_b == n_loc || n_loc_b == (n_loc == 10 ? 4 : 3),
+                   "mesh_create: n_loc_b must be n_loc (P2 buoyancy) or the vertex count (P1 buoyancy)");
     NUPGCM_REQUIRE(ctx, n_cells > 0 && nq > 0 && nq <= 64, "mesh_create: bad n_cells or nq");
     NUPGCM_REQUIRE(ctx, nb >= 0 && nbd >= 0 && nu >= 0 && nud >= 0, "mesh_create: negative size");
     NUPGCM_REQUIRE(ctx, (nbd == 0 || b_dirichlet) && (nud == 0 || u_dirichlet), "mesh_create: NULL Dirichlet values");
     NUPGCM_REQUIRE(ctx, n_cells * n_loc * 3 < INT32_MAX, "mesh_create: mesh too large for int32 slots");
     const int nv = n_loc == 10 ? 4 : 3;
     // transpose tables to [local][cell]; validate indices; build the per-DOF gather lists
-    std::vector<int32_t> tb((size_t)n_cells * n_loc), tu((size_t)n_cells * n_loc * 3);
+    std::vector<int32_t> tb((size_t)n_cells * n_loc_b), tu((size_t)n_cells * n_loc * 3);
     std::vector<double> tg((size_t)n_cells * nv * 3);
     std::vector<int32_t> gptr(nb + 1, 0);
     for (int64_t c = 0; c < n_cells; ++c) {
-        for (int i = 0; i < n_loc; ++i) {
-            const int32_t ib = cell_b[c * n_loc + i];
+        for (int i = 0; i < n_loc_b; ++i) {
+            const int32_t ib = cell_b[c * n_loc_b + i];
             if (ib < 0 || ib >= nb + nbd)
                 return nupgcm_fail(ctx, NUPGCM_ERR_INVALID, "invalid argument: %s", "mesh_create: cell_b index out of range");
             tb[(size_t)i * n_cells + c] = ib;
             if (ib < nb) gptr[ib + 1]++;
+        }
+        for (int i = 0; i < n_loc; ++i) {
             for (int d = 0; d < 3; ++d) {
                 const int32_t iu = cell_u[(c * n_loc + i) * 3 + d];
                 if (iu < 0 || iu >= nu + nud)
@@ -418,8 +459,8 @@ extern "C" int32_t nupgcm_mesh_create(nupgcm_ctx *ctx, int64_t n_cells, int32_t 
     for (int64_t i = 0; i < nb; ++i) gptr[i + 1] += gptr[i];
     std::vector<int32_t> gidx(gptr[nb]), fill(gptr.begin(), gptr.end() - 1);
     for (int64_t c = 0; c < n_cells; ++c)          // cells in order -> lists sorted by cell id
-        for (int i = 0; i < n_loc; ++i) {
-            const int32_t ib = cell_b[c * n_loc + i];
+        for (int i = 0; i < n_loc_b; ++i) {
+            const int32_t ib = cell_b[c * n_loc_b + i];
             if (ib < nb) gidx[fill[ib]++] = (int32_t)((int64_t)i * n_cells + c);
         }
     nupgcm_mesh *m = (nupgcm_mesh *)calloc(1, sizeof(nupgcm_mesh));
@@ -427,6 +468,7 @@ extern "C" int32_t nupgcm_mesh_create(nupgcm_ctx *ctx, int64_t n_cells, int32_t 
     m->ctx = ctx;
     m->n_cells = n_cells;
     m->n_loc = n_loc;
+    m->n_loc_b = n_loc_b;
     m->n_vert = nv;
     m->nq = nq;
     m->nb = nb;
@@ -444,7 +486,7 @@ extern "C" int32_t nupgcm_mesh_create(nupgcm_ctx *ctx, int64_t n_cells, int32_t 
     NUPGCM_CUDA(ctx, upload(&m->d_gidx, gidx));
     NUPGCM_CUDA(ctx, upload(&m->d_phi, std::vector<double>(bary, bary + (size_t)nq * nv)));   // bary
     NUPGCM_CUDA(ctx, upload(&m->d_w, std::vector<double>(w, w + nq)));
-    NUPGCM_CUDA(ctx, cudaMalloc(&m->d_elem, (size_t)n_cells * n_loc * sizeof(double)));
+    NUPGCM_CUDA(ctx, cudaMalloc(&m->d_elem, (size_t)n_cells * n_loc_b * sizeof(double)));
     NUPGCM_CUDA(ctx, cudaDeviceSynchronize());   // set-up copies ran on the default stream
     *out = m;
     return NUPGCM_OK;
@@ -492,10 +534,9 @@ extern "C" int32_t nupgcm_rhs_adv(nupgcm_mesh *m, int32_t scheme, double dt, dou
     const int block = 128;
     const int grid = (int)((m->n_cells + block - 1) / block);
     const size_t smem = (size_t)m->nq * (m->n_vert + 1) * sizeof(double);
-    if (m->n_vert == 4)
-        k_elem<4><<<grid, block, smem, ctx->stream>>>(m->d_cell_b, m->d_cell_u, m->d_grad, m->d_vol, m->d_phi, m->d_w, m->nq, m->n_cells, b->d, b_prev->d, m->d_bdir, m->nb, u->d, u_prev->d, m->d_udir, m->nu, scheme, dt, N2, m->d_elem);
-    else
-        k_elem<3><<<grid, block, smem, ctx->stream>>>(m->d_cell_b, m->d_cell_u, m->d_grad, m->d_vol, m->d_phi, m->d_w, m->nq, m->n_cells, b->d, b_prev->d, m->d_bdir, m->nb, u->d, u_prev->d, m->d_udir, m->nu, scheme, dt, N2, m->d_elem);
+    NUPGCM_MESH_DISPATCH(m, k_elem, grid, block, smem, ctx->stream, m->d_cell_b, m->d_cell_u, m->d_grad, m->d_vol, m->d_phi,
+                         m->d_w, m->nq, m->n_cells, b->d, b_prev->d, m->d_bdir, m->nb, u->d, u_prev->d, m->d_udir, m->nu,
+                         scheme, dt, N2, m->d_elem);
     NUPGCM_CUDA(ctx, cudaGetLastError());
     if (m->nb > 0) {
         int g2 = (int)((m->nb + 255) / 256);
@@ -556,7 +597,7 @@ extern "C" int32_t nupgcm_mesh_enable_kv_rebuild(nupgcm_mesh *m, const nupgcm_cs
                    "mesh_enable_kv_rebuild: pattern must be the nb x nb evolution pattern created with drop_zeros=0");
     NUPGCM_REQUIRE(ctx, m->nq <= 16, "mesh_enable_kv_rebuild: at most 16 quadrature points");
     const int64_t nc = m->n_cells, nnz = pattern->nnz;
-    const int nl = m->n_loc;
+    const int nl = m->n_loc_b;
     NUPGCM_REQUIRE(ctx, (int64_t)nl * nl * nc < INT32_MAX, "mesh_enable_kv_rebuild: mesh too large for int32 slots");
     // host copy of the transposed cell_b table
     std::vector<int32_t> tb((size_t)nc * nl);
@@ -611,11 +652,9 @@ extern "C" int32_t nupgcm_rebuild_kv(nupgcm_mesh *m, double alpha, double N2, do
     const int block = 128;
     const int grid = (int)((m->n_cells + block - 1) / block);
     const size_t smem = (size_t)m->nq * (m->n_vert + 1) * sizeof(double);
-    double *ev = m->d_evec, *ed = m->d_evec + (size_t)m->n_cells * m->n_loc;
-    if (m->n_vert == 4)
-        k_kv_elem<4><<<grid, block, smem, ctx->stream>>>(m->d_cell_b, m->d_grad, m->d_vol, m->d_phi, m->d_w, m->nq, m->n_cells, b->d, m->d_bdir, m->nb, m->d_kvq, alpha, N2, kappa_c, N2min, m->d_emat, ev, ed);
-    else
-        k_kv_elem<3><<<grid, block, smem, ctx->stream>>>(m->d_cell_b, m->d_grad, m->d_vol, m->d_phi, m->d_w, m->nq, m->n_cells, b->d, m->d_bdir, m->nb, m->d_kvq, alpha, N2, kappa_c, N2min, m->d_emat, ev, ed);
+    double *ev = m->d_evec, *ed = m->d_evec + (size_t)m->n_cells * m->n_loc_b;
+    NUPGCM_MESH_DISPATCH(m, k_kv_elem, grid, block, smem, ctx->stream, m->d_cell_b, m->d_grad, m->d_vol, m->d_phi, m->d_w,
+                         m->nq, m->n_cells, b->d, m->d_bdir, m->nb, m->d_kvq, alpha, N2, kappa_c, N2min, m->d_emat, ev, ed);
     NUPGCM_CUDA(ctx, cudaGetLastError());
     int g = (int)std::min<int64_t>((m->kv_nnz + 255) / 256, (int64_t)ctx->sm_count * 8);
     if (g < 1) g = 1;
@@ -699,10 +738,8 @@ extern "C" int32_t nupgcm_rebuild_friction(nupgcm_mesh *m, double a2e2, double a
     const int block = 64;
     const int grid = (int)((m->n_cells + block - 1) / block);
     const size_t smem = (size_t)m->nq * (m->n_vert + 1) * sizeof(double);
-    if (m->n_vert == 4)
-        k_nu_elem<4><<<grid, block, smem, ctx->stream>>>(m->d_cell_b, m->d_grad, m->d_vol, m->d_phi, m->d_w, m->nq, m->n_cells, b->d, m->d_bdir, m->nb, m->d_fq, a2e2, alpha, N2, N2min, smoothing, nu_min, m->d_nmat);
-    else
-        k_nu_elem<3><<<grid, block, smem, ctx->stream>>>(m->d_cell_b, m->d_grad, m->d_vol, m->d_phi, m->d_w, m->nq, m->n_cells, b->d, m->d_bdir, m->nb, m->d_fq, a2e2, alpha, N2, N2min, smoothing, nu_min, m->d_nmat);
+    NUPGCM_MESH_DISPATCH(m, k_nu_elem, grid, block, smem, ctx->stream, m->d_cell_b, m->d_grad, m->d_vol, m->d_phi, m->d_w,
+                         m->nq, m->n_cells, b->d, m->d_bdir, m->nb, m->d_fq, a2e2, alpha, N2, N2min, smoothing, nu_min, m->d_nmat);
     NUPGCM_CUDA(ctx, cudaGetLastError());
     int g = (int)std::min<int64_t>((m->nu_nnz + 255) / 256, (int64_t)ctx->sm_count * 8);
     if (g < 1) g = 1;

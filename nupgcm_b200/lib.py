@@ -99,6 +99,8 @@ SIGNATURES = {
     "nupgcm_diag_xreduce": [_P, c_int32, c_int32, c_int32, POINTER(c_float)],
     "nupgcm_mesh_create": [_P, c_int64, c_int32, _i32p, _i32p, _dp, _dp, c_int32, _dp, _dp, c_int64,
                            _dp, c_int64, c_int64, _dp, c_int64, POINTER(_P)],
+    "nupgcm_mesh_create_orders": [_P, c_int64, c_int32, c_int32, _i32p, _i32p, _dp, _dp, c_int32, _dp, _dp, c_int64,
+                                  _dp, c_int64, c_int64, _dp, c_int64, POINTER(_P)],
     "nupgcm_mesh_destroy": [_P],
     "nupgcm_mesh_set_cell_sizes": [_P, _dp, c_int64],
     "nupgcm_cfl_dt": [_P, _P, c_double, c_double, _dp],
@@ -585,7 +587,8 @@ def gmres_solve_prec(A: CsrMatrix, M: BlockPrec, y: Vector, x: Vector, atol=1e-6
 
 
 class ElementMesh:
-    """Device-side element tables of the advection RHS (``nupgcm_mesh_create``)."""
+    """Device-side element tables of the advection RHS (``nupgcm_mesh_create_orders``: P2 velocity,
+    P2 or P1 buoyancy — told apart by the number of local DOFs in ``cell_b``)."""
 
     def __init__(self, ctx: Context, tables: dict):
         self.ctx = ctx
@@ -599,8 +602,8 @@ class ElementMesh:
         bd = _f64(tables["b_dirichlet"])
         ud = _f64(tables["u_dirichlet"])
         h = _P()
-        _check(self.lib.nupgcm_mesh_create(
-            ctx.h, cb.shape[0], cb.shape[1], _ptr(cb, _i32p), _ptr(cu, _i32p), _ptr(grad),
+        _check(self.lib.nupgcm_mesh_create_orders(
+            ctx.h, cb.shape[0], cu.shape[1], cb.shape[1], _ptr(cb, _i32p), _ptr(cu, _i32p), _ptr(grad),
             _ptr(vol), w.size, _ptr(bary), _ptr(w), int(tables["nb"]), _ptr(bd), bd.size,
             int(tables["nu"]), _ptr(ud), ud.size, byref(h)), ctx.h)
         self.h = h

@@ -163,6 +163,15 @@ def channel_basin_box(n=(6, 12, 4), α: float = 0.125) -> Workload:
                     lambda x: 0.1 * x[:, 2] / α)
 
 
+def with_b_order(w: Workload, b_order: int) -> Workload:
+    """The same set-up with buoyancy of order ``b_order`` (``Spaces(...; b_order=1)`` is what the
+    production runs use, ``scratch/run.jl:152``)."""
+    w.spaces_kwargs = dict(w.spaces_kwargs, b_order=b_order)
+    w.name = f"{w.name}_bP{b_order}"
+    w._fe = None
+    return w
+
+
 def host_operands(w: Workload) -> dict:
     """Every host-side operand of the solve path, in solver (permuted) order — what a Julia host
     would hand over the C ABI.  Also the input of the CPU oracle."""

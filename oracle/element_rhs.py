@@ -29,6 +29,18 @@ def _p2(bary):
     return val, der
 
 
+def _p1(bary):
+    nq, nv = bary.shape
+    return bary.copy(), np.broadcast_to(np.eye(nv), (nq, nv, nv)).copy()
+
+
+def _b_basis(tables):
+    """Buoyancy basis: P2 (reference default) or P1 (``Spaces(...; b_order=1)``, scratch/run.jl:152),
+    told apart by the number of local DOFs in ``cell_b``."""
+    bary = tables["bary"]
+    return _p1(bary) if tables["cell_b"].shape[1] == bary.shape[1] else _p2(bary)
+
+
 def rhs_adv(tables, scheme, dt, N2, b, b_prev, u, u_prev):
     """Advection RHS in solver (permuted) row order.
 
@@ -39,7 +51,8 @@ def rhs_adv(tables, scheme, dt, N2, b, b_prev, u, u_prev):
     free values in permuted order.
     """
     cb, cu = tables["cell_b"], tables["cell_u"]
-    phi, dphi = _p2(tables["bary"])
+    phi, _ = _p2(tables["bary"])                                          # velocity: always P2
+    phib, dphib = _b_basis(tables)
     grad = tables["grad"]
     wq = tables["w"][None, :] * tables["vol"][:, None]                    # (nc, nq)
     bx = np.concatenate([b, tables["b_dirichlet"]])
@@ -55,12 +68,12 @@ def rhs_adv(tables, scheme, dt, N2, b, b_prev, u, u_prev):
         bs, us, lin, fac = bx[cb], ux[cu], bx[cb], dt
     else:
         raise ValueError("scheme must be 1 (BDF1) or 2 (BDF2)")
-    gphi = np.einsum("qik,ckd->cqid", dphi, grad)                         # ∇φᵢ at q
+    gphi = np.einsum("qik,ckd->cqid", dphib, grad)                        # ∇φᵢ at q
     gb = np.einsum("cqid,ci->cqd", gphi, bs)                              # ∇b*
     uq = np.einsum("qi,cid->cqd", phi, us)                                # u*
-    lq = np.einsum("qi,ci->cq", phi, lin)
+    lq = np.einsum("qi,ci->cq", phib, lin)
     val = lq - fac * (np.einsum("cqd,cqd->cq", uq, gb) + uq[:, :, 2] * N2)
-    fe = np.einsum("cq,cq,qi->ci", wq, val, phi)
+    fe = np.einsum("cq,cq,qi->ci", wq, val, phib)
     out = np.zeros(tables["nb"] + tables["b_dirichlet"].size)
     np.add.at(out, cb.ravel(), fe.ravel())
     return out[:tables["nb"]]
@@ -88,7 +101,7 @@ def kv_rebuild(tables, kv_q, α, N2, κc, N2min, b, pattern):
     import scipy.sparse as sp
     cb = tables["cell_b"]
     nb = tables["nb"]
-    _, dphi = _p2(tables["bary"])
+    _, dphi = _b_basis(tables)
     gz = tables["grad"][:, :, 2]                                          # (nc, d+1)
     dz = np.einsum("qik,ck->cqi", dphi, gz)                               # ∂z φ_i at q
     bx = np.concatenate([b, tables["b_dirichlet"]])
@@ -125,16 +138,15 @@ def nu_friction(tables, f_q, a2e2, α, N2, N2min, b, N, smoothing=10.0, ν_min=1
     cb, cu = tables["cell_b"], tables["cell_u"]
     nb, nu = tables["nb"], tables["nu"]
     _, dphi = _p2(tables["bary"])
-    g = np.einsum("qik,ckd->cqid", dphi, tables["grad"])                  # ∇φ_i at q
+    g = np.einsum("qik,ckd->cqid", dphi, tables["grad"])                  # ∇φ_i at q (velocity, P2)
     bx = np.concatenate([b, tables["b_dirichlet"]])
-    dzb = np.einsum("cqi,ci->cq", g[:, :, :, 2], bx[cb])
+    dzb = np.einsum("qik,ck,ci->cq", _b_basis(tables)[1], tables["grad"][:, :, 2], bx[cb])
     αbz = α * (N2 + dzb)
     ν = f_q * (f_q / np.sqrt(N2min ** 2 + αbz * αbz))
     ν = np.logaddexp(smoothing * ν_min, smoothing * ν) / smoothing
     wq = a2e2 * tables["w"][None, :] * tables["vol"][:, None] * ν
     S = np.einsum("cq,cqid,cqjd->cij", wq, g, g)
     T = np.einsum("cq,cqja,cqib->ciajb", wq, g, g)                        # ∂_a φ_j ∂_b φ_i
-    nloc = cb.shape[1]
     blk = T + np.einsum("cij,ab->ciajb", S, np.eye(3))
     rows = np.broadcast_to(cu[:, :, :, None, None], blk.shape).ravel()
     cols = np.broadcast_to(cu[:, None, None, :, :], blk.shape).ravel()

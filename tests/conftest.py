@@ -23,11 +23,15 @@ _CACHE = {}
 
 
 def workload(name, **kw):
-    """Cached (workload, host operands)."""
+    """Cached (workload, host operands).  ``b_order=1``: the same set-up with P1 buoyancy."""
     from nupgcm_b200 import workloads as W
     key = (name, tuple(sorted(kw.items())))
     if key not in _CACHE:
+        kw = dict(kw)
+        b_order = kw.pop("b_order", None)
         w = getattr(W, name)(**kw)
+        if b_order is not None:
+            w = W.with_b_order(w, b_order)
         _CACHE[key] = (w, W.host_operands(w))
     return _CACHE[key]
 

@@ -131,11 +131,14 @@ def test_combine_and_inv_diag(ctx):
         assert rel(B.spmv(ctx.vector(xx), ctx.vector(xx.size)).download(), 2.0 * (ops["A"] @ xx)) < 1e-13
 
 
+@pytest.mark.parametrize("b_order", [2, 1])
 @pytest.mark.parametrize("name", ["bowl_mixing", "bowl_dirichlet", "bowl_surface_flux"])
 @pytest.mark.parametrize("scheme", [1, 2])
-def test_element_rhs_matches_oracle(ctx, name, scheme):
+def test_element_rhs_matches_oracle(ctx, name, scheme, b_order):
+    """b_order = 1: first-order buoyancy with P2 velocity (Spaces(...; b_order=1), scratch/run.jl:152)."""
     kw = {"dim": 2} if name == "bowl_mixing" and scheme == 1 else {}
-    _, ops = workload(name, **kw)
+    _, ops = workload(name, b_order=b_order, **kw)
+    assert ops["tables"]["cell_b"].shape[1] == {2: ops["tables"]["cell_u"].shape[1], 1: ops["tables"]["bary"].shape[1]}[b_order]
     tb = ops["tables"]
     rng = np.random.default_rng(7)
     nb, nu = ops["nb"], ops["nu"]

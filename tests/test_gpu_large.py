@@ -115,3 +115,24 @@ def test_forced_streaming_cg_small_rows(ctx):
         os.environ.pop("NUPGCM_RESIDENT")
     assert st.solved and abs(st.niter - so.niter) <= 1
     assert rel(x.download(), xo) < 1e-9
+
+
+@pytest.mark.parametrize("orth,name", [(lib.ORTH_MGS, "mgs"), (lib.ORTH_CGS2_FUSED, "cgs2f")])
+def test_streaming_vector_forms_with_many_rows_per_cta(ctx, orth, name):
+    """5 300 rows per CTA (24 CTAs): more rows per thread than the register-resident Arnoldi forms hold, so
+    the streaming forms run — with the first rows of the new vector parked in the idle footprint arena."""
+    ops = refined_ops()
+    A = ops["A"]
+    y = ops["B"] @ ops["b_init"] + ops["b0"]
+    M = np.full(y.size, ops["pscale"])
+    xo, so = krylov.gmres(A, y, x0=np.zeros(y.size), M=M, atol=0.0, rtol=1e-30, memory=20, itmax=45, orth=name)
+    os.environ["NUPGCM_GRID"] = "24"
+    try:
+        x = ctx.vector(y.size)
+        st, hist = lib.gmres_solve(ctx.csr(A, drop_zeros=True), ctx.vector(y), x, pscale=ops["pscale"],
+                                   atol=0.0, rtol=1e-30, itmax=45, memory=20, orth=orth, history=64)
+    finally:
+        os.environ.pop("NUPGCM_GRID")
+    assert st.niter == 45
+    assert np.allclose(hist, so.residuals, rtol=1e-9)
+    assert rel(x.download(), xo) < 1e-9

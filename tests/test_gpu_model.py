@@ -130,7 +130,8 @@ def test_adaptive_bdf1_steps_match_oracle():
     assert ts.t == pytest.approx(cpu.t, rel=1e-12)
 
 
-@pytest.mark.parametrize("name,kw", [("bowl_mixing", {"dim": 2}), ("bowl_dirichlet", {})])
+@pytest.mark.parametrize("name,kw", [("bowl_mixing", {"dim": 2}), ("bowl_dirichlet", {}),
+                                     ("bowl_mixing", {"dim": 2, "b_order": 1}), ("bowl_dirichlet", {"b_order": 1})])
 def test_kv_rebuild_matches_oracle(ctx, name, kw):
     """nupgcm_rebuild_kv (convection parameterisation, model.jl:229-246) against the NumPy
     restatement: matrix values, Dirichlet lift and rhs_diff; bitwise reproducible."""
@@ -192,7 +193,7 @@ def test_convection_steps_match_oracle():
     assert rel(plain.xb, cpu.xb) > 1e-6
 
 
-@pytest.mark.parametrize("kw", [{"dim": 2}, {}])
+@pytest.mark.parametrize("kw", [{"dim": 2}, {}, {"dim": 2, "b_order": 1}, {"b_order": 1}])
 def test_friction_rebuild_matches_oracle(ctx, kw):
     """nupgcm_rebuild_friction (eddy parameterisation, model.jl:160-170) against the NumPy
     restatement, probed through SpMV; bitwise reproducible."""
@@ -278,12 +279,14 @@ def test_resume_makes_stepwise_calls_equal_one_call():
     assert not np.array_equal(a.xb.download(), c.xb.download())
 
 
-def test_channel_basin_production_configuration_matches_oracle():
+@pytest.mark.parametrize("b_order", [2, 1])
+def test_channel_basin_production_configuration_matches_oracle(b_order):
     """BASELINE config 4 (declared substitute mesh): wind + surface buoyancy flux, adaptive BDF1, the
     convection parameterisation every step and the eddy-viscosity rebuild after step 10 — every
-    "next" row of the scope table in one run — against the oracle's direct-solve path."""
+    "next" row of the scope table in one run — against the oracle's direct-solve path.  b_order = 1 is
+    the production choice (scratch/run.jl:152: P1 buoyancy under the P2-P1 flow)."""
     from nupgcm_b200 import workloads as W
-    w = W.channel_basin_box()
+    w = W.with_b_order(W.channel_basin_box(), b_order)
     ops = W.host_operands(w)
     n = 12
     cpu = cpu_model_for(w, ops, solver="direct")

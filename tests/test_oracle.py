@@ -69,10 +69,11 @@ def test_sym_givens():
         assert abs(c * a + s * b - rho) < 1e-15 and abs(s * a - c * b) < 1e-15
 
 
-def test_element_rhs_reduces_to_mass_matrix():
+@pytest.mark.parametrize("b_order", [2, 1])
+def test_element_rhs_reduces_to_mass_matrix(b_order):
     """With u = 0 the BDF1 form is ∫ b d = M_full b: checks the oracle's element loop against the
-    assembled mass matrix (free rows, free + Dirichlet columns)."""
-    w, ops = workload("bowl_dirichlet")
+    assembled mass matrix (free rows, free + Dirichlet columns), for P2 and P1 buoyancy."""
+    w, ops = workload("bowl_dirichlet", b_order=b_order)
     tb = ops["tables"]
     rng = np.random.default_rng(2)
     b = rng.uniform(-1, 1, ops["nb"])
@@ -114,7 +115,7 @@ def test_oracle_cfl_and_parameterisation_rebuilds_match_host_assembly():
     * cfl_dt with u = 0 is CFL · min h / u_min and decreases once the flow is fast."""
     from nupgcm_b200._forms import build_A_inversion
     from oracle.element_rhs import cfl_dt, kv_rebuild, nu_friction
-    for name, kw in (("bowl_mixing", {"dim": 2}), ("bowl_dirichlet", {})):
+    for name, kw in (("bowl_mixing", {"dim": 2}), ("bowl_dirichlet", {}), ("bowl_dirichlet", {"b_order": 1})):
         w, ops = workload(name, **kw)
         fe = w.fe_data()
         t = ops["tables"]
