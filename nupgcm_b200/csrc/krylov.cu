@@ -1836,7 +1836,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
                 // unchanged and only its coefficients need the correction h = Vᵀq̂ − c (VᵀV = I up to
                 // O(ε), c = O(ε): the neglected term is O(ε²)).  Equal to CGS2 in exact arithmetic.
                 constexpr int RF = MR ? 4 : 8;
-                if (r1 - r0 <= RF * (nthr - 32)) {
+                // (streamed-matrix kernels only: with the basis in shared memory the segment form below is faster —
+                // 18.7 against 21.6 us per iteration at h = 0.08 — because its k projections run on different warps
+                // while this form walks them in sequence, two warp reductions per pair of basis vectors)
+                if (!RES && r1 - r0 <= RF * (nthr - 32)) {
                     // Register-resident form (up to RF rows per thread of warps 1..10; warp 0 owns no rows and does
                     // the scalar recurrences while the others finish the vector): the thread keeps its rows of q
                     // in registers through both projections and both updates, so each of the four passes reads

@@ -53,6 +53,7 @@ class DiscreteModel:
         self.nv = self.nodes.shape[0]
         self._number_edges()
         self._tag_boundary(raw)
+        self._identify_periodic(getattr(raw, "periodic", None))
 
     # edges by first appearance (cell-major, local-edge-minor)
     def _number_edges(self):
@@ -103,6 +104,31 @@ class DiscreteModel:
         self.vertex_tags = vtag
         self.edge_tags = etag
         self._bit = bit
+
+    def _identify_periodic(self, master):
+        """Owner-level identification of a periodic mesh: ``vertex_master`` / ``edge_master`` give, for every
+        vertex / edge, the vertex / edge whose DOFs it shares (itself when it is not a slave).  An edge is a
+        slave when both of its end points are; its master is the edge between their masters, which a
+        periodic surface mesh always has."""
+        self.vertex_master = np.arange(self.nv, dtype=np.int64)
+        self.edge_master = np.arange(self.ne, dtype=np.int64)
+        self.periodic = master is not None
+        if master is None:
+            return
+        master = np.asarray(master, dtype=np.int64)
+        if master.shape != (self.nv,) or not np.array_equal(master[master], master):
+            raise ValueError("periodic: need one master per node, masters being their own masters")
+        self.vertex_master = master
+        a, b = self.edges[:, 0], self.edges[:, 1]
+        slave = (master[a] != a) & (master[b] != b)
+        em = self.edge_ids(master[a[slave]], master[b[slave]])
+        if (em < 0).any():
+            raise ValueError("periodic: a slave edge has no master edge (surface meshes do not match)")
+        self.edge_master[slave] = em
+        tags_differ = (self.vertex_tags != self.vertex_tags[self.vertex_master]).any() or \
+            (self.edge_tags != self.edge_tags[self.edge_master]).any()
+        if tags_differ:
+            raise ValueError("periodic: slave and master carry different boundary tags")
 
     def tag_mask(self, tags) -> np.uint32:
         m = np.uint32(0)
@@ -192,10 +218,12 @@ class LagrangeSpace:
             self.n_owners = nv
             self.cell_owners = model.cells
             owner_tags = model.vertex_tags
+            owner_master = model.vertex_master
         elif order == 2:
             self.n_owners = nv + ne
             self.cell_owners = np.concatenate([model.cells, nv + model.cell_edges], axis=1)
             owner_tags = np.concatenate([model.vertex_tags, model.edge_tags])
+            owner_master = np.concatenate([model.vertex_master, nv + model.edge_master])
         else:
             raise ValueError("order must be 1 or 2")
         diri = np.zeros((self.n_owners, ncomp), dtype=bool)
@@ -208,14 +236,20 @@ class LagrangeSpace:
                 if mask[c]:
                     diri[on, c] = True
         if fix_last_owner:           # constraint=:zeromean fixes the last DOF (spaces.jl:45)
-            diri[-1, :] = True
+            diri[owner_master[-1], :] = True
+        # periodic meshes: a slave owner has no DOFs of its own, it carries its master's ids
+        own = owner_master == np.arange(self.n_owners)
+        self.owner_is_master = own
         flat = diri.ravel()
-        ids = np.empty(flat.size, dtype=np.int64)
-        ids[~flat] = np.arange((~flat).sum())
-        ids[flat] = -(np.arange(flat.sum()) + 1)
-        self.owner_dofs = ids.reshape(self.n_owners, ncomp)
-        self.nfree = int((~flat).sum())
-        self.ndiri = int(flat.sum())
+        numbered = np.repeat(own, ncomp)
+        ids = np.zeros(flat.size, dtype=np.int64)
+        free_sel, diri_sel = numbered & ~flat, numbered & flat
+        ids[free_sel] = np.arange(free_sel.sum())
+        ids[diri_sel] = -(np.arange(diri_sel.sum()) + 1)
+        ids = ids.reshape(self.n_owners, ncomp)
+        self.owner_dofs = ids[owner_master]
+        self.nfree = int(free_sel.sum())
+        self.ndiri = int(diri_sel.sum())
         self.dirichlet_values = np.zeros(self.ndiri)
 
     def owner_coordinates(self):
@@ -434,5 +468,8 @@ def restrict_vector(vec_owner_comp, test: LagrangeSpace):
     v = np.asarray(vec_owner_comp).reshape(test.n_owners, test.ncomp)
     out = np.zeros(test.nfree)
     ids = test.owner_dofs
-    out[ids[ids >= 0]] = v[ids >= 0]
+    if test.owner_is_master.all():
+        out[ids[ids >= 0]] = v[ids >= 0]
+    else:                            # periodic: the slave owners' integrals belong to their masters' DOFs
+        np.add.at(out, ids[ids >= 0], v[ids >= 0])
     return out

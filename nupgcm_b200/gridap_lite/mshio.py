@@ -28,6 +28,10 @@ class RawMesh:
     elements: dict = field(default_factory=dict)
     element_names: dict = field(default_factory=dict)
     physical_names: dict = field(default_factory=dict)  # (dim, tag) -> name
+    # periodic meshes (gmsh.model.mesh.setPeriodic, reference meshes/channel_basin_flat.jl:114-121): master node of
+    # every node (itself when it is not a slave); None = not periodic.  Geometry keeps all nodes, the FE
+    # spaces give a slave node (and a slave edge) the DOFs of its master.
+    periodic: np.ndarray | None = None
 
     @property
     def dim(self) -> int:

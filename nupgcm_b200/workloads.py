@@ -141,9 +141,11 @@ def bowl_example(h: float = 0.08, mesh=None, n_steps: int | None = None) -> Work
                     lambda x: 0.1 * np.exp(-(x[:, 2] + H(x)) / (0.1 * α)), invert_first=True)
 
 
-def channel_basin_box(n=(6, 12, 4), α: float = 0.125) -> Workload:
+def channel_basin_box(n=(6, 12, 4), α: float = 0.125, periodic: bool = False) -> Workload:
     """Config 4 substitute: flat channel-basin box x∈[0,1], y∈[−1,1], z∈[−α,0] (n cells per
-    direction), wind + surface flux forcing, adaptive BDF1, convection + eddy parameterisations."""
+    direction), wind + surface flux forcing, adaptive BDF1, convection + eddy parameterisations.
+    ``periodic``: the channel part y <= −1/2 is periodic in x, as in ``meshes/channel_basin_flat.jl:5-10,114-121``
+    (the basin part keeps its walls)."""
     from .gridap_lite import box_mesh
     from .inputs import ConvectionParameterization, EddyParameterization
     ε, μϱ = np.sqrt(1e-1), 1.0
@@ -155,8 +157,8 @@ def channel_basin_box(n=(6, 12, 4), α: float = 0.125) -> Workload:
                         SurfaceFluxBC(lambda x: 1e-3 * np.sin(np.pi * x[:, 0])),
                         conv_param=ConvectionParameterization(κᶜ=1.0, N2min=1e-3),
                         eddy_param=EddyParameterization(f=f, N2min=np.sqrt(1e-3)))
-    mesh = box_mesh(*n, z=(-α, 0.0))
-    return Workload("channel_basin_box", params, forcings, mesh, dict(_U_DIRI),
+    mesh = box_mesh(*n, z=(-α, 0.0), periodic_x_below=-0.5 if periodic else None)
+    return Workload("channel_basin_box" + ("_periodic" if periodic else ""), params, forcings, mesh, dict(_U_DIRI),
                     # CFL_factor: the reference's production value is 0.8 on its h = 1e-2 mesh; on this
                     # coarse stand-in the u_min = 0.01 floor alone would give Δt ≈ 19 at rest, so 0.05
                     dict(t_start=0.0, t_stop=float("inf"), Δt=1e-2, adaptive=True, CFL_factor=0.05),

@@ -279,14 +279,16 @@ def test_resume_makes_stepwise_calls_equal_one_call():
     assert not np.array_equal(a.xb.download(), c.xb.download())
 
 
-@pytest.mark.parametrize("b_order", [2, 1])
-def test_channel_basin_production_configuration_matches_oracle(b_order):
+@pytest.mark.parametrize("b_order,periodic", [(2, False), (1, False), (2, True), (1, True)])
+def test_channel_basin_production_configuration_matches_oracle(b_order, periodic):
     """BASELINE config 4 (declared substitute mesh): wind + surface buoyancy flux, adaptive BDF1, the
     convection parameterisation every step and the eddy-viscosity rebuild after step 10 — every
     "next" row of the scope table in one run — against the oracle's direct-solve path.  b_order = 1 is
-    the production choice (scratch/run.jl:152: P1 buoyancy under the P2-P1 flow)."""
+    the production choice (scratch/run.jl:152: P1 buoyancy under the P2-P1 flow); periodic = the channel
+    part y <= -1/2 periodic in x as in meshes/channel_basin_flat.jl:114-121 (slave DOFs identified with their
+    masters on the host: the device tables gather a seam DOF from the cells on both sides)."""
     from nupgcm_b200 import workloads as W
-    w = W.with_b_order(W.channel_basin_box(), b_order)
+    w = W.with_b_order(W.channel_basin_box(periodic=periodic), b_order)
     ops = W.host_operands(w)
     n = 12
     cpu = cpu_model_for(w, ops, solver="direct")

@@ -235,6 +235,46 @@ def test_model_steps_sharded_match_single_rank(ctx):
     assert np.array_equal(models[0].xb.download(), models[1].xb.download())
 
 
+def test_channel_production_configuration_sharded_matches_single_rank(ctx):
+    """BASELINE configs[3] on two ranks: periodic channel + basin box, P1 buoyancy, wind + surface flux, adaptive
+    BDF1 (CFL from the device every step), the convection rebuild of Kv every step and the eddy-viscosity
+    rebuild of the inversion matrix after step 10 — with BOTH solves sharded.  The rebuild kernels write the
+    caller-order values on every rank; the sharded solver tables are refreshed from them before the next solve."""
+    import nupgcm_b200 as npg
+    from nupgcm_b200 import workloads as W
+    w = W.with_b_order(W.channel_basin_box(periodic=True), 1)
+    ops = W.host_operands(w)
+    n = 12
+
+    def make(arch):
+        inv = npg.InversionToolkit(arch, ops["A"], ops["pscale"], ops["B"], ops["b0"], atol=0.0, rtol=1e-13,
+                                   itmax=3000000, drop_zeros=False)
+        ts = w.timestepper()
+        evo = npg.EvolutionToolkit(arch, ops, w.params, w.forcings, ts, atol=0.0, rtol=1e-14)
+        m = npg.Model(arch, w.params, w.forcings, w.fe_data(), inv, evo, ts, tables=ops["tables"])
+        m.xb.upload(ops["b_init"])
+        return m, ts
+
+    def steps(m, ts):
+        dts = []
+        for _ in range(n):
+            npg.run_(m, n_steps=1, resume=True)
+            dts.append(ts.Δt)
+        return dts
+
+    single, ts1 = make(npg.GPU(0))
+    dts1 = steps(single, ts1)
+    comms = local_ranks(2, ops["A"].shape[0])
+    models = [make(npg.GPU(0, comm=c)) for c in comms]
+    out = run_collective([lambda m=m, t=t: steps(m, t) for m, t in models])
+    for (m, _), dts in zip(models, out):
+        assert np.allclose(dts, dts1, rtol=1e-9)
+        assert rel(m.xb.download(), single.xb.download()) < 1e-8
+        assert rel(m.inversion.solver.x.download(), single.inversion.solver.x.download()) < 1e-8
+        assert all(r["gmres_solved"] and r["cg_solved"] for r in m.step_log)
+    assert np.array_equal(models[0][0].xb.download(), models[1][0].xb.download())
+
+
 def test_two_processes_over_ipc():
     """One process per GPU (torchrun, world size 2): CUDA IPC arenas, NVLink pushes."""
     import torch
