@@ -72,12 +72,16 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def measured_traffic(kernel="k_gmres"):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture
-    (profiles/ncu_traffic_r02.json, written from tools/profile_round.sh output); None if absent."""
+def measured_traffic(kernel="k_gmres_mgs", iterations=None):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/ncu_traffic_r02.json:
+    dram__bytes_read.sum + dram__bytes_write.sum of ONE k_gmres launch of 400 iterations on the h = 0.04 system,
+    application replay, profiles/ncu_gmres_stream_r02.txt), scaled to the iterations of this run's launches — the
+    traffic of the persistent kernel is proportional to its iteration count.  None if absent."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")
     try:
-        return float(json.load(open(p))[kernel]["dram_bytes_per_launch"])
+        k = json.load(open(p))[kernel]
+        per_iter = (float(k["dram_bytes_read"]) + float(k["dram_bytes_write"])) / float(k["iterations"])
+        return per_iter * float(iterations)
     except Exception:
         return None
 
@@ -404,7 +408,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": f"k_gmres (persistent GMRES(20), orth={orth}, one launch per invert!"
                                                    + (f", sharded over {world} GPUs)" if world > 1 else ")"),
                          "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
-                         "traffic": measured_traffic(f"k_gmres_{orth}") if world == 1 else None,
+                         "traffic": measured_traffic(f"k_gmres_{orth}", g_iters.mean()) if world == 1 and args.level == 1 else None,
                          "peak_source": peak_src + ("" if world == 1 else f" x {world} GPUs"),
                          "algorithmic_bytes_per_launch": g_bytes, "ms_per_launch": float(g_ms.mean()),
                          "nnz_counted": nnz, "share_of_step": float(g_ms.sum() / total_ms)},

@@ -1,6 +1,6 @@
 """BASELINE configs[3]: channel_basin with wind and surface-flux forcing on the GPUs of one box.
 
-    torchrun --nproc-per-node 8 tools/channel_run.py --n 32 64 8 --steps 30
+    torchrun --nproc-per-node 8 tools/channel_run.py --cells 32 64 8 --steps 30
 
 The reference's production set-up (scratch/run.jl:111-163): channel_basin_flat mesh (x-periodic channel for
 y <= -1/2, walled basin north of it; here the structured substitute box, meshes/channel_basin_flat.jl needs
@@ -22,7 +22,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, nargs=3, default=[32, 64, 8], help="box cells in x, y, z")
+    ap.add_argument("--cells", dest="n", type=int, nargs=3, default=[32, 64, 8], help="box cells in x, y, z")
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--orth", default="mgs", choices=["mgs", "cgs2f"])
     ap.add_argument("--b-order", type=int, default=1)
@@ -100,6 +100,9 @@ def main():
            "solve_share_of_run": float((g_ms.sum() + c_ms.sum()) * 1e-3 / t_run),
            "dt_first_last": [dts[0], dts[-1]], "t_end": ts.t,
            "all_solved": bool(all(r["gmres_solved"] and r["cg_solved"] for r in log)),
+           "per_step": {"gmres_iters": [int(v) for v in g_it], "gmres_solved": [bool(r["gmres_solved"]) for r in log],
+                        "cg_iters": [int(v) for v in c_it], "cg_solved": [bool(r["cg_solved"]) for r in log],
+                        "dt": [float(v) for v in dts]},
            "u_max_last": log[-1]["u_max"], "b_max_last": log[-1]["b_max"],
            "setup_s": {"host_assembly_per_rank": t_host, "device_tables_and_upload": t_dev},
            "device_memory_used_gb_rank0": (total - free) / 2 ** 30}
