@@ -208,6 +208,35 @@ def test_inversion_3d_sharded_streaming_form(ctx):
         os.environ.pop("NUPGCM_RESIDENT")
 
 
+@pytest.mark.parametrize("orth", [lib.ORTH_MGS, lib.ORTH_CGS2_FUSED])
+def test_sharded_streaming_vector_forms_with_many_rows_per_cta(ctx, orth):
+    """Once-refined bowl (N ~ 1.3e5) on 2 ranks of 24 CTAs: 2 700 rows per CTA, more than the register-resident
+    Arnoldi forms of the sharded kernels hold (4 rows per thread), so the STREAMING Gram-Schmidt forms run with
+    halo pushes — MGS with the new vector parked in the idle footprint arena (the path h = 0.02 takes on 8 GPUs)."""
+    from nupgcm_b200 import workloads as W
+    ops = W.host_operands(W.bowl_example(mesh=W.refined_bowl(1, h0=0.1)))
+    A = ops["A"].tocsr()
+    y = ops["B"] @ ops["b_init"] + ops["b0"]
+    ps = ops["pscale"]
+
+    def solve(c, dA):
+        x = c.vector(A.shape[0])
+        st, hist = lib.gmres_solve(dA, c.vector(y), x, pscale=ps, atol=0.0, rtol=1e-30, itmax=45,
+                                   memory=20, orth=orth, history=64)
+        return st.niter, hist, x.download()
+
+    os.environ["NUPGCM_GRID"] = "24"
+    try:
+        ref = solve(ctx, ctx.csr(A, drop_zeros=True))
+        res, _, _ = _sharded(2, A, solve, drop_zeros=True)
+    finally:
+        os.environ.pop("NUPGCM_GRID")
+    for niter, hist, x in res:
+        assert niter == ref[0] == 45
+        assert np.allclose(hist, ref[1], rtol=1e-8)
+        assert rel(x, ref[2]) < 1e-8
+
+
 def test_model_steps_sharded_match_single_rank(ctx):
     """Three timesteps of the 2-D bowl with both solves sharded over 2 ranks (state replicated,
     element RHS replicated) against the single-GPU model."""
