@@ -156,3 +156,30 @@ def test_oracle_block_preconditioned_gmres():
     ref = spla.spsolve(A.tocsc(), b)
     assert st.solved and st.niter < 1000 and M.inner_iters > 0
     assert np.linalg.norm(x - ref) / np.linalg.norm(ref) < 1e-3
+
+
+@pytest.mark.parametrize("b_order", [2, 1])
+def test_element_tables_velocity_map_against_assembled_matrices(b_order):
+    """Independence of the element-RHS checker from the product's DOF maps: with b = x_d (∇b = e_d, held exactly
+    by P1 and P2) and N² = 0 the BDF1 form is ∫(b − Δt u·∇b) d = M b − Δt G_d u, G_d = ∫ φᵢ (e_d·ψⱼ) assembled by
+    gridap_lite between the buoyancy test space and the velocity trial space.  That fixes `cell_u` (node order,
+    component order, RCM permutation, Dirichlet tail) and the ∇λ tables of `element_tables.py` — which kernel and
+    oracle share — against the matrix assembly, which is pinned to the reference's own fixture
+    (tests/test_fe_setup.py)."""
+    from nupgcm_b200.gridap_lite.fem import restrict
+    w, ops = workload("bowl_surface_flux", b_order=b_order)       # no buoyancy Dirichlet DOFs: b = x_d is admissible
+    fe = w.fe_data()
+    Bs, U, d = fe.spaces.B, fe.spaces.U, fe.dofs
+    assert Bs.ndiri == 0
+    tb = ops["tables"]
+    rng = np.random.default_rng(5)
+    u_g = rng.uniform(-1, 1, d.nu)                                # free velocity DOFs, Gridap order
+    m = fe.mesh.dΩ.matrix("mass", Bs, U)
+    dt = 0.37
+    for comp in range(3):
+        G, _ = restrict(m, Bs, U, {(0, comp): m})                 # velocity Dirichlet values are zero
+        b_g, _ = Bs.interpolate(lambda x, c=comp: x[:, c])
+        M_g = ops["M"][d.inv_p_b][:, d.inv_p_b]                   # back to Gridap order
+        expect = (M_g @ b_g - dt * (G @ u_g))[d.p_b]
+        out = rhs_adv(tb, 1, dt, 0.0, b_g[d.p_b], b_g[d.p_b], u_g[d.p_u], u_g[d.p_u])
+        assert np.linalg.norm(out - expect) / np.linalg.norm(expect) < 1e-12, comp
