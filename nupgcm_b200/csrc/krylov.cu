@@ -256,6 +256,10 @@ __host__ __device__ inline size_t exch_bank_slots(int gpad) {
     return (size_t)(kMaxReplicas + kPartialSlots) * gpad + (size_t)kBcastCopies * kBcastStride;
 }
 
+// Back-off between two polls of a flagged word (ns; 0 = spin).  Every CTA polls the same few cache lines, so
+// the polls themselves load the L2 slices that hold them (NUPGCM_POLL_SLEEP, tools/reduce_sweep.py).
+__constant__ int c_poll_sleep_ns = 0;
+
 // Wait (with watchdog) until the flagged word at p carries `gen`; returns its value.
 template <bool ACQUIRE, bool SYS = false>
 __device__ __forceinline__ double wait_flagged(const LLSlot *p, unsigned gen, unsigned long long *abort_word, bool &bad) {
@@ -266,6 +270,7 @@ __device__ __forceinline__ double wait_flagged(const LLSlot *p, unsigned gen, un
         ll_load_raw<ACQUIRE, SYS>(p, a, b);
         if ((unsigned)(a >> 32) == gen && (unsigned)(b >> 32) == gen)
             return __longlong_as_double((long long)((a & 0xffffffffULL) | (b << 32)));
+        if (c_poll_sleep_ns > 0) __nanosleep((unsigned)c_poll_sleep_ns);
         if ((++spins & 255u) == 0) {
             unsigned long long fl;
             asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(fl) : "l"(abort_word) : "memory");
@@ -2185,7 +2190,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
 // replicas of the reduction slots (NUPGCM_REPLICAS overrides); measured on B200 with
 // tools/reduce_cliff.py
 static int poll_config(int grid) {
-    int rep = grid > 100 ? 2 : 1;
+    // all 148 SMs spinning on the same ~19 cache lines sit past a knee of the L2 slices that hold them: at
+    // h = 0.04 (tools/reduce_sweep.py, profiles/reduce_sweep_r02.txt) MGS runs at 123 / 107 / 101 us per iteration
+    // with 1 / 2 / 4 replicas on 148 CTAs, and at 103 / 100 / 102 on 140 CTAs
+    int rep = grid > 100 ? 4 : 1;
     if (const char *er = getenv("NUPGCM_REPLICAS")) {
         const int v = atoi(er);
         if (v >= 1 && v <= kMaxReplicas) rep = v;
@@ -2417,6 +2425,15 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
 
     NUPGCM_CUDA(ctx, cudaMemsetAsync(ctx->d_barrier, 0, 4 * sizeof(unsigned long long), ctx->stream));
     NUPGCM_CUDA(ctx, cudaMemsetAsync(ctx->d_partials, 0, reduce_scratch_bytes(ctx->coop_grid), ctx->stream));
+    {
+        static int current_sleep = 0;                             // value held by the device constant
+        int want = 0;
+        if (const char *es = getenv("NUPGCM_POLL_SLEEP")) want = std::max(0, atoi(es));
+        if (want != current_sleep) {
+            NUPGCM_CUDA(ctx, cudaMemcpyToSymbolAsync(c_poll_sleep_ns, &want, sizeof(int), 0, cudaMemcpyHostToDevice, ctx->stream));
+            current_sleep = want;
+        }
+    }
     const char *trace_path = getenv("NUPGCM_TRACE_FILE");       // debug only
     unsigned long long *d_trace = nullptr;
     const size_t trace_words = (size_t)kTraceWindow * kTraceStamps * grid;

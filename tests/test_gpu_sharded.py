@@ -28,7 +28,7 @@ def _evol(ops, θ=0.05):
     return (ops["M"] + θ * (ops["Kh"] + ops["Kv"])).tocsr()
 
 
-def _sharded(nranks, A, solve, drop_zeros=False):
+def _sharded(nranks, A, solve, drop_zeros=False, grid=None):
     """Run `solve(ctx, dA)` collectively on `nranks` ranks sharing cuda:0; returns per-rank results.
 
     The ranks share ONE device here, so a device-wide synchronisation on one rank's thread (cudaFree
@@ -38,6 +38,9 @@ def _sharded(nranks, A, solve, drop_zeros=False):
     set-up, a rank's cudaFree only ever waits for its own device)."""
     import threading
     comms = local_ranks(nranks, A.shape[0])
+    if grid is not None:               # fewer CTAs per rank: set BEFORE sharding, so that the solver tables are built
+        for c in comms:                # here and not inside the collective solve (cudaFree = device-wide sync)
+            c.ctx.set_grid(grid)
     mats = [c.ctx.csr(A, drop_zeros=drop_zeros).shard(c) for c in comms]
     done = threading.Barrier(nranks)
 
@@ -225,12 +228,12 @@ def test_sharded_streaming_vector_forms_with_many_rows_per_cta(ctx, orth):
                                    memory=20, orth=orth, history=64)
         return st.niter, hist, x.download()
 
-    os.environ["NUPGCM_GRID"] = "24"
+    os.environ["NUPGCM_GRID"] = "48"           # single rank: the same 48 row blocks
     try:
         ref = solve(ctx, ctx.csr(A, drop_zeros=True))
-        res, _, _ = _sharded(2, A, solve, drop_zeros=True)
     finally:
         os.environ.pop("NUPGCM_GRID")
+    res, _, _ = _sharded(2, A, solve, drop_zeros=True, grid=24)
     for niter, hist, x in res:
         assert niter == ref[0] == 45
         assert np.allclose(hist, ref[1], rtol=1e-8)
