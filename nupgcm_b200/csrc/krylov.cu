@@ -2192,8 +2192,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gmres(const __grid_constant__ K
 static int poll_config(int grid) {
     // all 148 SMs spinning on the same ~19 cache lines sit past a knee of the L2 slices that hold them: at
     // h = 0.04 (tools/reduce_sweep.py, profiles/reduce_sweep_r02.txt) MGS runs at 123 / 107 / 101 us per iteration
-    // with 1 / 2 / 4 replicas on 148 CTAs, and at 103 / 100 / 102 on 140 CTAs
-    int rep = grid > 100 ? 4 : 1;
+    // with 1 / 2 / 4 replicas on 148 CTAs (8: 100; h = 0.08: 54 / 49 / 48 with 2 / 4 / 8), and at 103 / 100 / 102 on 140 CTAs
+    int rep = grid > 100 ? kMaxReplicas : 1;
     if (const char *er = getenv("NUPGCM_REPLICAS")) {
         const int v = atoi(er);
         if (v >= 1 && v <= kMaxReplicas) rep = v;

@@ -2,7 +2,7 @@
 load of the grid reductions: CTAs per GPU (NUPGCM_GRID), replicas of the reduction slots (NUPGCM_REPLICAS) and the
 back-off between two polls of a flagged word (NUPGCM_POLL_SLEEP, ns).  All three are read per solve.
 
-    python tools/reduce_sweep.py [level] [iters]"""
+    python tools/reduce_sweep.py [level] [iters] [grids, comma separated] [replicas] [sleeps]"""
 import os
 import sys
 
@@ -32,12 +32,13 @@ def run(orth):
     return 1e3 * st.device_ms / st.niter, st.rnorm / st.rnorm0
 
 
-for grid in (148, 140, 128, 112, 96):
+_list = lambda i, d: tuple(int(v) for v in sys.argv[i].split(",")) if len(sys.argv) > i else d      # noqa: E731
+for grid in _list(3, (148, 140, 128, 112, 96)):
     os.environ["NUPGCM_GRID"] = str(grid)
-    for rep in (1, 2, 4):
+    for rep in _list(4, (1, 2, 4)):
         os.environ["NUPGCM_REPLICAS"] = str(rep)
         row = []
-        for sleep in (0, 100, 300, 600):
+        for sleep in _list(5, (0, 100, 300, 600)):
             os.environ["NUPGCM_POLL_SLEEP"] = str(sleep)
             t, r = run(lib.ORTH_MGS)
             row.append(f"sleep {sleep:3d}: {t:6.1f}")
