@@ -2426,12 +2426,14 @@ static int32_t solve_common(bool gmres, const nupgcm_csr *A, const nupgcm_vec *d
     NUPGCM_CUDA(ctx, cudaMemsetAsync(ctx->d_barrier, 0, 4 * sizeof(unsigned long long), ctx->stream));
     NUPGCM_CUDA(ctx, cudaMemsetAsync(ctx->d_partials, 0, reduce_scratch_bytes(ctx->coop_grid), ctx->stream));
     {
-        static int current_sleep = 0;                             // value held by the device constant
+        // experiment switch: the constant is per device, so it is written on every solve while the switch is (or
+        // has just been) in use, and never touched otherwise
+        static bool sleep_in_use = false;
         int want = 0;
         if (const char *es = getenv("NUPGCM_POLL_SLEEP")) want = std::max(0, atoi(es));
-        if (want != current_sleep) {
+        if (want != 0 || sleep_in_use) {
             NUPGCM_CUDA(ctx, cudaMemcpyToSymbolAsync(c_poll_sleep_ns, &want, sizeof(int), 0, cudaMemcpyHostToDevice, ctx->stream));
-            current_sleep = want;
+            sleep_in_use = true;
         }
     }
     const char *trace_path = getenv("NUPGCM_TRACE_FILE");       // debug only
