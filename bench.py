@@ -444,11 +444,14 @@ def main():
         "metric": METRIC, "value": mgs["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": mgs["ms_per_step"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": dict(workload_config(args.level), N=mgs["N"], nnz=mgs["nnz"], nb=d.nb, orth="mgs",
-                       drop_zeros=not args.keep_zeros, host_setup_s=t_setup,
-                       parallelism="single GPU" if world == 1 else
-                       f"CG and GMRES row-block sharded over {world} GPUs (peer-memory halo pushes and "
-                       "reductions inside the persistent kernels); element RHS and vector kernels replicated"),
+        # `config` is the workload alone, identical in both arms (the driver compares them); what is specific to this
+        # arm and this run sits in `details`
+        "config": workload_config(args.level),
+        "details": dict(N=mgs["N"], nnz=mgs["nnz"], nb=d.nb, orth="mgs", drop_zeros=not args.keep_zeros,
+                        host_setup_s=t_setup,
+                        parallelism="single GPU" if world == 1 else
+                        f"CG and GMRES row-block sharded over {world} GPUs (peer-memory halo pushes and "
+                        "reductions inside the persistent kernels); element RHS and vector kernels replicated"),
         "iterations": mgs["iterations"],
         "clocks": clocks.summary(),
         "e2e": {"value": mgs["e2e"], "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes,
