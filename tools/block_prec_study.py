@@ -102,9 +102,52 @@ def exact_blocks(F, T):
     return lambda x: np.concatenate([luF.solve(x[:n1]), luT.solve(x[n1:])])
 
 
+def schwarz(h, parts_list=(148, 8), overlaps=(1, 2)):
+    """Restricted additive Schwarz on the persistent solvers' own row blocks (the library's RCM order and nnz-balanced
+    partition): a block = the CTA's rows + `overlap` layers of graph neighbours, inverted exactly."""
+    from nupgcm_b200 import lib
+    w = W.bowl_example(h=h)
+    ops = W.host_operands(w)
+    A = ops["A"].tocsr()
+    A.eliminate_zeros()
+    n = A.shape[0]
+    y = ops["B"] @ ops["b_init"] + ops["b0"]
+    p = lib.rcm_order(A)
+    Ap, yp = A[p][:, p].tocsr(), y[p]
+    res = lambda x: np.linalg.norm(Ap @ x - yp) / np.linalg.norm(yp)                  # noqa: E731
+    x, s = krylov.gmres(Ap, yp, x0=np.zeros(n), M=np.full(n, ops["pscale"]), atol=1e-6, rtol=1e-6, memory=20)
+    print(f"bowl3D h = {h:g} (N = {n}), scalar I/h^3: {s.niter} / {res(x):.1e}", flush=True)
+    rp = Ap.indptr
+    G = (abs(Ap) + abs(Ap).T).tocsr()
+    for parts in parts_list:
+        cost, total = rp[:-1] + 4.0 * np.arange(n), rp[n] + 4.0 * n                   # build_partition of csrc/csr.cu
+        part = [0] + [int(np.searchsorted(cost, total * q / parts)) for q in range(1, parts)] + [n]
+        for ov in overlaps:
+            sets = []
+            for i in range(parts):
+                idx = np.arange(part[i], part[i + 1])
+                for _ in range(ov):
+                    idx = np.unique(np.concatenate([idx, G[idx].indices]))
+                sets.append(idx)
+            lus = [spla.splu(Ap[idx][:, idx].tocsc()) for idx in sets]
+            own = [(idx >= part[i]) & (idx < part[i + 1]) for i, idx in enumerate(sets)]
+
+            def ras(r):
+                z = np.zeros(n)
+                for idx, lu, o in zip(sets, lus, own):
+                    z[idx[o]] = lu.solve(r[idx])[o]
+                return z
+            x, s = krylov.gmres(Ap, yp, x0=np.zeros(n), M=ras, atol=1e-6, rtol=1e-6, memory=20, itmax=3000)
+            print(f"   {parts:3d} blocks, overlap {ov}: {s.niter:5d} / {res(x):.1e}   mean block {np.mean([len(i) for i in sets]):.0f} rows "
+                  f"({n / parts:.0f} owned)", flush=True)
+
+
 def main():
-    """Default: scalar preconditioner against the block preconditioner with EXACT inner solves (its best case) on the
+    """`--schwarz [h]`: restricted additive Schwarz on the solvers' row blocks.  Default: scalar preconditioner against the block preconditioner with EXACT inner solves (its best case) on the
     3-D bowl and on the channel_basin box.  `--inner [h]`: the inner-preconditioner variants on the bowl (slow)."""
+    if "--schwarz" in sys.argv:
+        rest = [a for a in sys.argv[1:] if a != "--schwarz"]
+        return schwarz(float(rest[0]) if rest else 0.1)
     if "--inner" not in sys.argv:
         for name, w in (("bowl3D h = 0.1, examples/bowl_mixing.jl parameters (eps = 0.2, alpha = 0.5)", W.bowl_example(h=0.1)),
                         ("bowl2D h = 0.1 (bowl_mixing_tests.jl)", W.bowl_mixing(dim=2)),
