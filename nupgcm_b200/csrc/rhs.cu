@@ -3,8 +3,9 @@
 // Replaces the CPU Gridap `assemble_vector(d -> advection_lform(...), B_test)` of reference
 // src/model.jl:269-273 (forms :292-300), the `rhs_adv[perm]` + host->device copy of :274-275 and
 // the broadcast of :278.  Two kernels, no atomics:
-//   1. k_elem: one thread per cell evaluates the P2 fields at the quadrature points and writes
-//      the cell's n_loc elemental integrals to d_elem[i][cell] (tables are stored transposed so
+//   1. k_elem: one thread per cell evaluates the fields (velocity P2; buoyancy P2 or P1, `b_order` of
+//      src/spaces.jl:31-39) at the quadrature points and writes the cell's elemental integrals — one per local
+//      buoyancy DOF — to d_elem[i][cell] (tables are stored transposed so
 //      that consecutive threads read consecutive addresses; u and b are gathered through the
 //      cell's DOF indices, Dirichlet values living behind the free ones);
 //   2. k_gather: one thread per free buoyancy DOF sums its elemental slots in a FIXED order
